@@ -1,0 +1,207 @@
+"""ctypes binding of libflowb200.so (the C ABI declared in include/flowb200.h).
+
+There is deliberately no fallback: if the shared library is missing the import
+fails loudly, and on a machine without a CUDA device every compute entry point
+returns FB_ENODEVICE (raised as RuntimeError).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libflowb200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "flow_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "or `make -C flow_b200/csrc`. There is no CPU fallback." % LIB_PATH
+    )
+
+lib = C.CDLL(LIB_PATH)
+
+FB_OK, FB_EINVAL, FB_ENOCONV_NEWTON, FB_ENOCONV_KRYLOV, FB_ENAN, FB_ECUDA, FB_ENCCL, FB_ENOMEM, FB_ENODEVICE = range(9)
+FORWARD_EULER, BACKWARD_EULER, CRANK_NICOLSON = 0, 1, 2
+DEVICE_PTRS, ROTATIONAL, CHORIN = 1, 2, 4
+F_NONE, F_CONSTANT, F_NODAL, F_LOAD = 0, 1, 2, 3
+BICGSTAB, GMRES, CG = 0, 1, 2
+JACOBI, BLOCK_JACOBI, CHEBYSHEV = 0, 1, 2
+
+vp = C.c_void_p
+i64 = C.c_int64
+dbl = C.c_double
+pd = C.POINTER(C.c_double)
+pi32 = C.POINTER(C.c_int32)
+pi64 = C.POINTER(C.c_int64)
+pu8 = C.POINTER(C.c_uint8)
+
+
+class NSOpts(C.Structure):
+    _fields_ = [
+        ("momentum_solver", C.c_int),
+        ("momentum_precond", C.c_int),
+        ("pressure_precond", C.c_int),
+        ("newton_maxit", C.c_int),
+        ("newton_atol", C.c_double),
+        ("momentum_rtol", C.c_double),
+        ("momentum_maxit", C.c_int),
+        ("pressure_maxit", C.c_int),
+        ("correction_maxit", C.c_int),
+        ("gmres_restart", C.c_int),
+        ("check_every", C.c_int),
+        ("chebyshev_degree", C.c_int),
+        ("reserved", C.c_int * 8),
+    ]
+
+
+class NSStats(C.Structure):
+    _fields_ = [
+        ("newton_its", C.c_int),
+        ("momentum_its", C.c_int),
+        ("pressure_its", C.c_int),
+        ("correction_its", C.c_int),
+        ("newton_residual", C.c_double),
+        ("ms_tentative", C.c_double),
+        ("ms_pressure", C.c_double),
+        ("ms_correction", C.c_double),
+        ("ms_total", C.c_double),
+        ("ms_assembly_J", C.c_double),
+        ("ms_assembly_F", C.c_double),
+        ("ms_momentum_solve", C.c_double),
+        ("launches", C.c_int64),
+        ("reserved", C.c_double * 8),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+# every exported symbol of include/flowb200.h with its signature
+SIGNATURES = {
+    "fb_version": (C.c_int, []),
+    "fb_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+    "fb_ctx_destroy": (C.c_int, [vp]),
+    "fb_last_error": (C.c_char_p, [vp]),
+    "fb_status_string": (C.c_char_p, [C.c_int]),
+    "fb_ctx_launch_count": (C.c_int, [vp, pi64]),
+    "fb_ctx_timer_start": (C.c_int, [vp]),
+    "fb_ctx_timer_stop": (C.c_int, [vp, pd]),
+    "fb_mesh_create": (C.c_int, [vp, C.c_int, i64, pd, i64, pi32, C.POINTER(vp)]),
+    "fb_mesh_destroy": (C.c_int, [vp]),
+    "fb_mesh_info": (C.c_int, [vp, pi64, pi64, pi64, pi64]),
+    "fb_mesh_cells": (C.c_int, [vp, C.POINTER(pi32)]),
+    "fb_mesh_edges": (C.c_int, [vp, C.POINTER(pi32)]),
+    "fb_mesh_boundary_facets": (C.c_int, [vp, C.POINTER(pi32), C.POINTER(pi32)]),
+    "fb_space_create": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
+    "fb_space_destroy": (C.c_int, [vp]),
+    "fb_space_info": (C.c_int, [vp, pi64, pi64, C.POINTER(C.c_int)]),
+    "fb_space_dofmap": (C.c_int, [vp, C.POINTER(pi32)]),
+    "fb_space_node_coords": (C.c_int, [vp, C.POINTER(pd)]),
+    "fb_space_boundary_nodes": (C.c_int, [vp, C.POINTER(pu8)]),
+    "fb_space_pattern": (C.c_int, [vp, pi64, C.POINTER(pi64), C.POINTER(pi32)]),
+    "fb_assemble_mass": (C.c_int, [vp, C.POINTER(vp)]),
+    "fb_assemble_stiffness": (C.c_int, [vp, C.POINTER(vp)]),
+    "fb_assemble_lumped_mass": (C.c_int, [vp, pd]),
+    "fb_mat_destroy": (C.c_int, [vp]),
+    "fb_mat_info": (C.c_int, [vp, pi64, pi64, C.POINTER(C.c_int)]),
+    "fb_mat_values": (C.c_int, [vp, pd]),
+    "fb_mat_spmv": (C.c_int, [vp, C.c_int, pd, pd]),
+    "fb_mat_solve_cg": (C.c_int, [vp, C.c_int, pd, pd, i64, pi64, pd, dbl, C.c_int, C.POINTER(C.c_int)]),
+    "fb_mat_bench_spmv": (C.c_int, [vp, C.c_int, C.c_int, pd, pd]),
+    "fb_ns_opts_default": (C.c_int, [C.POINTER(NSOpts)]),
+    "fb_ns_create": (C.c_int, [vp, vp, C.POINTER(NSOpts), C.POINTER(vp)]),
+    "fb_ns_destroy": (C.c_int, [vp]),
+    "fb_ns_step": (
+        C.c_int,
+        [vp, dbl, dbl, dbl, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, i64, pi64, pd, i64, pi64, pd, dbl, vp, vp,
+         C.POINTER(NSStats)],
+    ),
+    "fb_ns_residual": (C.c_int, [vp, dbl, dbl, dbl, dbl, pd, pd, pd, pd, pd, C.c_int]),
+    "fb_ns_matrix": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+    "fb_ns_pressure_rhs": (C.c_int, [vp, dbl, dbl, dbl, C.c_int, pd, pd, pd]),
+    "fb_ns_correction_rhs": (C.c_int, [vp, dbl, dbl, dbl, C.c_int, pd, pd, pd, pd]),
+    "fb_heat_create": (C.c_int, [vp, vp, pd, dbl, dbl, dbl, pd, C.POINTER(vp)]),
+    "fb_heat_destroy": (C.c_int, [vp]),
+    "fb_heat_eval": (C.c_int, [vp, dbl, dbl, pd, pd]),
+    "fb_heat_solve": (C.c_int, [vp, dbl, dbl, pd, i64, pi64, pd, dbl, C.c_int, pd, C.POINTER(C.c_int)]),
+    "fb_heat_matrix": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+    "fb_stokes_solve": (
+        C.c_int,
+        [vp, vp, dbl, C.c_int, pd, i64, pi64, pd, i64, pi64, pd, dbl, C.c_int, pd, pd, C.POINTER(C.c_int)],
+    ),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _f = getattr(lib, _name)  # AttributeError here == symbol missing from the .so
+    _f.restype = _res
+    _f.argtypes = _args
+
+
+class FlowError(RuntimeError):
+    """Raised for every non-zero status; non-convergence keeps the reference's RuntimeError
+    contract (error_on_nonconvergence, caught at tests/test_boussinesq.py:254)."""
+
+    def __init__(self, status, message):
+        RuntimeError.__init__(self, message)
+        self.status = status
+
+
+def check(status, ctx=None, what=""):
+    if status == FB_OK:
+        return
+    msg = lib.fb_status_string(status).decode()
+    if ctx:
+        detail = lib.fb_last_error(ctx).decode()
+        if detail:
+            msg = "%s: %s" % (msg, detail)
+    if what:
+        msg = "%s: %s" % (what, msg)
+    if status == FB_EINVAL:
+        raise AssertionError(msg) if "must be > 0" in msg else ValueError(msg)
+    raise FlowError(status, msg)
+
+
+def as_pd(a):
+    return a.ctypes.data_as(pd)
+
+
+def as_pi64(a):
+    return a.ctypes.data_as(pi64)
+
+
+def as_pi32(a):
+    return a.ctypes.data_as(pi32)
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+_contexts = {}
+
+
+def context(device=None):
+    """One context per device; device None -> cuda:LOCAL_RANK if a GPU is usable, else host-only (-1)."""
+    if device is None:
+        device = int(os.environ.get("FLOW_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        if device not in _contexts:
+            h = vp()
+            st = lib.fb_ctx_create(device, C.byref(h))
+            if st == FB_ENODEVICE:
+                device = -1
+            else:
+                check(st, None, "fb_ctx_create")
+                _contexts[device] = h
+    if device not in _contexts:
+        h = vp()
+        check(lib.fb_ctx_create(device, C.byref(h)), None, "fb_ctx_create")
+        _contexts[device] = h
+    return _contexts[device]
+
+
+def has_device():
+    ctx = context()
+    for dev, h in _contexts.items():
+        if h is ctx or h.value == ctx.value:
+            return dev >= 0
+    return False

@@ -1,0 +1,832 @@
+// C ABI of libflowb200.so: contexts, assembled operators, the Navier-Stokes
+// pressure-correction step, the heat operator.  See include/flowb200.h for the
+// reference call each entry point replaces.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "fb_ops.h"
+
+#define FB_API_BEGIN(ctxexpr) \
+  fb_ctx *_ctx = (ctxexpr);   \
+  try {
+#define FB_API_END                                          \
+  }                                                         \
+  catch (const fb_cuda_error &e) {                          \
+    return fb_fail(_ctx, e.status, e.what());               \
+  }                                                         \
+  catch (const std::bad_alloc &) {                          \
+    return fb_fail(_ctx, FB_ENOMEM, "host out of memory");  \
+  }                                                         \
+  catch (const std::exception &e) {                         \
+    return fb_fail(_ctx, FB_ECUDA, e.what());               \
+  }                                                         \
+  return FB_OK;
+
+#define FB_NEED_DEVICE(ctx)                                                                                   \
+  if (!(ctx) || !(ctx)->dev)                                                                                  \
+    return fb_fail((ctx), FB_ENODEVICE, "this context has no CUDA device (host-only); no CPU compute path exists")
+
+static DevSpace *dev_space(fb_space *s) {
+  if (!s->dev) {
+    std::unique_ptr<DevSpace> d(new DevSpace());
+    dev_space_build(s, *d);
+    s->dev = d.release();
+  }
+  return static_cast<DevSpace *>(s->dev);
+}
+
+// ---- small local kernels ----------------------------------------------------
+__global__ void k_scale_add_diag(int64_t nnz, int64_t n, double beta, const double *__restrict__ A, double alpha,
+                                 const double *__restrict__ mdiag, const int *__restrict__ diag, double *__restrict__ S) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz; k += stride) S[k] = beta * A[k];
+}
+__global__ void k_add_diag(int64_t n, double alpha, const double *__restrict__ mdiag, const int *__restrict__ diag,
+                           double *__restrict__ S) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    S[diag[i]] += alpha * mdiag[i];
+}
+__global__ void k_heat_eval(int64_t n, double alpha, double beta, const double *__restrict__ mdiag,
+                            const double *__restrict__ u, const double *__restrict__ Au, const double *__restrict__ b,
+                            double *__restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = alpha * mdiag[i] * u[i] + beta * (Au[i] + b[i]);
+}
+__global__ void k_fill_interleaved(int64_t nnodes, int D, double c0, double c1, double c2, double *x) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nnodes * D; t += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t % D);
+    x[t] = i == 0 ? c0 : (i == 1 ? c1 : c2);
+  }
+}
+__global__ void k_sin_fill(int64_t n, double *x) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = sin((double)i);
+}
+
+static inline int vgrid(fb_ctx *ctx, int64_t n) {
+  int64_t g = (n + 255) / 256;
+  const int cap = ctx->dev->sm_count * 8;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(g, cap));
+}
+
+extern "C" {
+
+int fb_version(void) { return 100; }
+
+const char *fb_status_string(int status) {
+  switch (status) {
+    case FB_OK: return "ok";
+    case FB_EINVAL: return "invalid argument";
+    case FB_ENOCONV_NEWTON: return "Newton solver did not converge";
+    case FB_ENOCONV_KRYLOV: return "Krylov solver did not converge";
+    case FB_ENAN: return "NaN or breakdown in solver";
+    case FB_ECUDA: return "CUDA error";
+    case FB_ENCCL: return "NCCL error";
+    case FB_ENOMEM: return "out of memory";
+    case FB_ENODEVICE: return "no CUDA device in this context";
+    default: return "unknown status";
+  }
+}
+
+int fb_ctx_create(int device, fb_ctx **out) {
+  if (!out) return FB_EINVAL;
+  fb_ctx *ctx = new fb_ctx();
+  ctx->device = device;
+  if (device < 0) {
+    *out = ctx;
+    return FB_OK;
+  }
+  try {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= device) {
+      delete ctx;
+      return FB_ENODEVICE;
+    }
+    FB_CUDA(cudaSetDevice(device));
+    fb_device_state *dv = new fb_device_state();
+    ctx->dev = dv;
+    FB_CUDA(cudaStreamCreateWithFlags(&dv->stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    FB_CUDA(cudaGetDeviceProperties(&prop, device));
+    dv->sm_count = prop.multiProcessorCount;
+    FB_CUDA(cudaMalloc((void **)&dv->red, sizeof(double) * FB_NSLOTS));
+    FB_CUDA(cudaMalloc((void **)&dv->partials, sizeof(double) * FB_NSLOTS * FB_MAX_RED_BLOCKS));
+    FB_CUDA(cudaMalloc((void **)&dv->counter, sizeof(unsigned int)));
+    FB_CUDA(cudaMalloc((void **)&dv->flag, sizeof(int)));
+    FB_CUDA(cudaMalloc((void **)&dv->iters, sizeof(int)));
+    FB_CUDA(cudaMemset(dv->counter, 0, sizeof(unsigned int)));
+    FB_CUDA(cudaMemset(dv->flag, 0, sizeof(int)));
+    FB_CUDA(cudaMemset(dv->iters, 0, sizeof(int)));
+    FB_CUDA(cudaMemset(dv->red, 0, sizeof(double) * FB_NSLOTS));
+    FB_CUDA(cudaMallocHost((void **)&dv->host_pinned, sizeof(double) * 64));
+    for (auto &ev : dv->ev) FB_CUDA(cudaEventCreate(&ev));
+  } catch (const fb_cuda_error &e) {
+    fprintf(stderr, "fb_ctx_create: %s\n", e.what());
+    delete ctx;
+    return e.status;
+  }
+  *out = ctx;
+  return FB_OK;
+}
+
+int fb_ctx_destroy(fb_ctx *ctx) {
+  if (!ctx) return FB_EINVAL;
+  if (ctx->dev) {
+    fb_device_state *dv = ctx->dev;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(dv->stream);
+    cudaFree(dv->red);
+    cudaFree(dv->partials);
+    cudaFree(dv->counter);
+    cudaFree(dv->flag);
+    cudaFree(dv->iters);
+    cudaFreeHost(dv->host_pinned);
+    for (auto &ev : dv->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(dv->stream);
+    delete dv;
+  }
+  delete ctx;
+  return FB_OK;
+}
+
+const char *fb_last_error(fb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int fb_ctx_launch_count(fb_ctx *ctx, int64_t *count) {
+  if (!ctx || !count) return FB_EINVAL;
+  *count = ctx->launches;
+  return FB_OK;
+}
+
+int fb_ctx_timer_start(fb_ctx *ctx) {
+  FB_NEED_DEVICE(ctx);
+  FB_API_BEGIN(ctx)
+  FB_CUDA(cudaEventRecord(_ctx->dev->ev[6], _ctx->dev->stream));
+  FB_API_END
+}
+
+int fb_ctx_timer_stop(fb_ctx *ctx, double *ms) {
+  FB_NEED_DEVICE(ctx);
+  if (!ms) return FB_EINVAL;
+  FB_API_BEGIN(ctx)
+  FB_CUDA(cudaEventRecord(_ctx->dev->ev[7], _ctx->dev->stream));
+  FB_CUDA(cudaEventSynchronize(_ctx->dev->ev[7]));
+  float t = 0;
+  FB_CUDA(cudaEventElapsedTime(&t, _ctx->dev->ev[6], _ctx->dev->ev[7]));
+  *ms = t;
+  FB_API_END
+}
+
+int fb_mesh_destroy(fb_mesh *m) {
+  delete m;
+  return FB_OK;
+}
+
+int fb_space_destroy(fb_space *s) {
+  if (!s) return FB_OK;
+  delete static_cast<DevSpace *>(s->dev);
+  delete s;
+  return FB_OK;
+}
+
+// ---- assembled operators -----------------------------------------------------
+static int assemble_mat(fb_space *space, int kind, fb_mat **out) {
+  if (!space || !out) return FB_EINVAL;
+  FB_NEED_DEVICE(space->mesh->ctx);
+  FB_API_BEGIN(space->mesh->ctx)
+  DevSpace *sp = dev_space(space);
+  std::unique_ptr<fb_mat> m(new fb_mat());
+  m->ctx = _ctx;
+  m->sp = sp;
+  m->block = 1;
+  m->val.alloc((size_t)sp->nnz);
+  assemble_constant(_ctx, *sp, kind, m->val.p);
+  FB_CUDA(cudaStreamSynchronize(_ctx->dev->stream));
+  *out = m.release();
+  FB_API_END
+}
+
+int fb_assemble_mass(fb_space *space, fb_mat **out) { return assemble_mat(space, 1, out); }
+int fb_assemble_stiffness(fb_space *space, fb_mat **out) { return assemble_mat(space, 0, out); }
+
+int fb_assemble_lumped_mass(fb_space *space, double *diag_out) {
+  if (!space || !diag_out) return FB_EINVAL;
+  FB_NEED_DEVICE(space->mesh->ctx);
+  FB_API_BEGIN(space->mesh->ctx)
+  DevSpace *sp = dev_space(space);
+  DBuf<double> d;
+  d.alloc((size_t)sp->nnodes);
+  assemble_lumped(_ctx, *sp, d.p);
+  FB_CUDA(cudaMemcpyAsync(diag_out, d.p, sizeof(double) * sp->nnodes, cudaMemcpyDeviceToHost, _ctx->dev->stream));
+  FB_CUDA(cudaStreamSynchronize(_ctx->dev->stream));
+  FB_API_END
+}
+
+int fb_mat_destroy(fb_mat *mat) {
+  delete mat;
+  return FB_OK;
+}
+
+int fb_mat_info(fb_mat *mat, int64_t *nrows, int64_t *nnz_blocks, int *block) {
+  if (!mat) return FB_EINVAL;
+  if (nrows) *nrows = mat->sp->nnodes;
+  if (nnz_blocks) *nnz_blocks = mat->sp->nnz;
+  if (block) *block = mat->block;
+  return FB_OK;
+}
+
+int fb_mat_values(fb_mat *mat, double *values_out) {
+  if (!mat || !values_out) return FB_EINVAL;
+  FB_API_BEGIN(mat->ctx)
+  FB_CUDA(cudaMemcpyAsync(values_out, mat->val.p, sizeof(double) * mat->val.n, cudaMemcpyDeviceToHost, _ctx->dev->stream));
+  FB_CUDA(cudaStreamSynchronize(_ctx->dev->stream));
+  FB_API_END
+}
+
+int fb_mat_spmv(fb_mat *mat, int ncomp, const double *x, double *y) {
+  if (!mat || !x || !y) return FB_EINVAL;
+  if (mat->block == 1 && (ncomp < 1 || ncomp > 3)) return fb_fail(mat->ctx, FB_EINVAL, "fb_mat_spmv: ncomp must be 1..3");
+  FB_API_BEGIN(mat->ctx)
+  LinOp A = make_linop(*mat, ncomp, nullptr);
+  const int64_t n = A.ndofs();
+  DBuf<double> dx, dy;
+  cudaStream_t st = _ctx->dev->stream;
+  dx.upload(x, (size_t)n, st);
+  dy.alloc((size_t)n);
+  spmv(_ctx, A, dx.p, dy.p);
+  FB_CUDA(cudaMemcpyAsync(y, dy.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(cudaStreamSynchronize(st));
+  FB_API_END
+}
+
+int fb_mat_bench_spmv(fb_mat *mat, int ncomp, int reps, double *ms_avg, double *bytes) {
+  if (!mat || reps < 1) return FB_EINVAL;
+  FB_API_BEGIN(mat->ctx)
+  LinOp A = make_linop(*mat, ncomp, nullptr);
+  const int64_t n = A.ndofs();
+  fb_device_state *dv = _ctx->dev;
+  DBuf<double> dx, dy;
+  dx.alloc((size_t)n);
+  dy.alloc((size_t)n);
+  FB_LAUNCH(_ctx, k_sin_fill, vgrid(_ctx, n), 256, 0, n, dx.p);
+  for (int i = 0; i < 3; ++i) spmv(_ctx, A, dx.p, dy.p);
+  FB_CUDA(cudaEventRecord(dv->ev[8], dv->stream));
+  for (int i = 0; i < reps; ++i) spmv(_ctx, A, dx.p, dy.p);
+  FB_CUDA(cudaEventRecord(dv->ev[9], dv->stream));
+  FB_CUDA(cudaEventSynchronize(dv->ev[9]));
+  float ms = 0;
+  FB_CUDA(cudaEventElapsedTime(&ms, dv->ev[8], dv->ev[9]));
+  if (ms_avg) *ms_avg = ms / reps;
+  if (bytes) {
+    // scalar-CSR algorithmic bytes of the interleaved system
+    const int b = A.dofs_per_node();
+    const double nnz_scalar = (double)mat->sp->nnz * (mat->block > 1 ? b * b : b);
+    const double nrows_scalar = (double)mat->sp->nnodes * b;
+    *bytes = nnz_scalar * 12.0 + nrows_scalar * 20.0;
+  }
+  FB_API_END
+}
+
+// masked Jacobi-PCG on a scalar matrix with `ncomp` interleaved components (symmetric elimination)
+static int solve_cg_masked(fb_ctx *ctx, const fb_mat &M, int ncomp, double *b_dev /* modified */, double *x_dev,
+                           int64_t nbc, const int64_t *bc_dofs_dev, const double *bc_vals_dev, double g2,
+                           uint8_t *mask_dev, double *dinv_dev, double *xg_dev, double *tmp_dev, double rtol, int maxit,
+                           int check_every, KrylovWork &kw, int *iters) {
+  const int64_t n = M.sp->nnodes * ncomp;
+  LinOp Afull = make_linop(M, ncomp, nullptr);
+  const uint8_t *mask = nullptr;
+  if (nbc > 0) {
+    mask_build(ctx, mask_dev, n, bc_dofs_dev, nbc);
+    mask = mask_dev;
+    // lift: b <- b - A xg on free rows, 0 on constrained rows
+    vec_fill(ctx, xg_dev, 0.0, n);
+    vec_set_at(ctx, xg_dev, bc_dofs_dev, bc_vals_dev, nbc);
+    spmv(ctx, Afull, xg_dev, tmp_dev);
+    vec_axpy(ctx, b_dev, -1.0, tmp_dev, n);
+    vec_zero_at(ctx, b_dev, bc_dofs_dev, nbc);
+  }
+  jacobi_setup_scalar(ctx, *M.sp, M.val.p, ncomp, mask, dinv_dev);
+  LinOp A = make_linop(M, ncomp, mask);
+  int st = krylov_pcg(ctx, A, dinv_dev, b_dev, x_dev, rtol, g2, maxit, check_every, kw, iters);
+  if (nbc > 0) vec_axpy(ctx, x_dev, 1.0, xg_dev, n);
+  return st;
+}
+
+int fb_mat_solve_cg(fb_mat *mat, int ncomp, const double *b, double *x, int64_t nbc, const int64_t *bc_dofs,
+                    const double *bc_vals, double rtol, int maxit, int *iterations) {
+  if (!mat || !b || !x || mat->block != 1 || ncomp < 1 || ncomp > 3) return FB_EINVAL;
+  if (nbc > 0 && (!bc_dofs || !bc_vals)) return FB_EINVAL;
+  FB_API_BEGIN(mat->ctx)
+  cudaStream_t st = _ctx->dev->stream;
+  const int64_t n = mat->sp->nnodes * ncomp;
+  DBuf<double> db, dx, dinv, xg, tmp, dvals;
+  DBuf<int64_t> ddofs;
+  DBuf<uint8_t> mask;
+  db.upload(b, (size_t)n, st);
+  dx.alloc((size_t)n);
+  dinv.alloc((size_t)n);
+  xg.alloc((size_t)n);
+  tmp.alloc((size_t)n);
+  mask.alloc((size_t)n);
+  double g2 = 0.0;
+  if (nbc > 0) {
+    ddofs.upload(bc_dofs, (size_t)nbc, st);
+    dvals.upload(bc_vals, (size_t)nbc, st);
+    for (int64_t i = 0; i < nbc; ++i) {
+      if (bc_dofs[i] < 0 || bc_dofs[i] >= n) return fb_fail(_ctx, FB_EINVAL, "fb_mat_solve_cg: Dirichlet dof out of range");
+      g2 += bc_vals[i] * bc_vals[i];
+    }
+  }
+  KrylovWork kw;
+  int its = 0;
+  int status = solve_cg_masked(_ctx, *mat, ncomp, db.p, dx.p, nbc, ddofs.p, dvals.p, g2, mask.p, dinv.p, xg.p, tmp.p, rtol,
+                               maxit, 50, kw, &its);
+  if (iterations) *iterations = its;
+  FB_CUDA(cudaMemcpyAsync(x, dx.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(cudaStreamSynchronize(st));
+  if (status != FB_OK) return fb_fail(_ctx, status, "fb_mat_solve_cg: CG did not converge");
+  FB_API_END
+}
+
+}  // extern "C"
+
+// =============================================================================
+// Navier-Stokes stepper
+// =============================================================================
+struct fb_ns {
+  fb_ctx *ctx = nullptr;
+  fb_space *Wh = nullptr, *Ph = nullptr;
+  DevSpace *W = nullptr, *P = nullptr;
+  int D = 2;
+  int64_t nu = 0, np = 0;
+  fb_ns_opts opts;
+  fb_mat Ap, Mu, J;
+  DBuf<double> u0, p0, ui, p1, u1, F, delta, load, ftmp, bp, bu, dinv_p, dinv_u, binv, tmp_u, tmp_p, xg_u, xg_p, Ap_bc;
+  DBuf<uint8_t> mask_u, mask_p;
+  DBuf<int64_t> ubc_dofs, pbc_dofs;
+  DBuf<double> ubc_vals, pbc_vals;
+  KrylovWork kw_u, kw_p;
+};
+
+static void ns_upload(fb_ns *ns, DBuf<double> &dst, const double *src, int64_t n, bool dev) {
+  cudaStream_t st = ns->ctx->dev->stream;
+  dst.alloc((size_t)n);
+  FB_CUDA(cudaMemcpyAsync(dst.p, src, sizeof(double) * n, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+}
+
+// load = M (x) I . ((1-theta) f0 + theta f1) for CONSTANT / NODAL forcing, or the blended LOAD vectors
+static bool ns_build_load(fb_ns *ns, int forcing, const double *f0, const double *f1, double theta, bool dev) {
+  fb_ctx *ctx = ns->ctx;
+  cudaStream_t st = ctx->dev->stream;
+  const int D = ns->D;
+  const int64_t n = ns->nu;
+  const double w0 = 1.0 - theta, w1 = theta;
+  if (forcing == FB_F_NONE || (!f0 && !f1)) return false;
+  if ((w0 != 0.0 && !f0) || (w1 != 0.0 && !f1)) throw fb_cuda_error(FB_EINVAL, "forcing: f0/f1 required by the time scheme is NULL");
+  ns->load.alloc((size_t)n);
+  ns->ftmp.alloc((size_t)n);
+  if (forcing == FB_F_CONSTANT) {
+    double c[3] = {0, 0, 0};
+    for (int i = 0; i < D; ++i) c[i] = (w0 != 0.0 ? w0 * f0[i] : 0.0) + (w1 != 0.0 ? w1 * f1[i] : 0.0);
+    FB_LAUNCH(ctx, k_fill_interleaved, vgrid(ctx, n), 256, 0, ns->Mu.sp->nnodes, D, c[0], c[1], c[2], ns->ftmp.p);
+    spmv(ctx, make_linop(ns->Mu, D, nullptr), ns->ftmp.p, ns->load.p);
+    return true;
+  }
+  // NODAL / LOAD: blend on device
+  DBuf<double> &a = ns->tmp_u;  // staging
+  a.alloc((size_t)n);
+  vec_fill(ctx, ns->ftmp.p, 0.0, n);
+  const cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (w0 != 0.0) {
+    FB_CUDA(cudaMemcpyAsync(a.p, f0, sizeof(double) * n, kind, st));
+    vec_axpy(ctx, ns->ftmp.p, w0, a.p, n);
+  }
+  if (w1 != 0.0) {
+    FB_CUDA(cudaMemcpyAsync(a.p, f1, sizeof(double) * n, kind, st));
+    vec_axpy(ctx, ns->ftmp.p, w1, a.p, n);
+  }
+  if (forcing == FB_F_NODAL)
+    spmv(ctx, make_linop(ns->Mu, D, nullptr), ns->ftmp.p, ns->load.p);
+  else
+    FB_CUDA(cudaMemcpyAsync(ns->load.p, ns->ftmp.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+  return true;
+}
+
+static void ns_assemble_F(fb_ns *ns, const MomentumArgs &a, bool have_load) {
+  assemble_momentum_F(ns->ctx, *ns->W, a, ns->F.p);
+  if (have_load) vec_axpy(ns->ctx, ns->F.p, -a.dt / a.rho, ns->load.p, ns->nu);
+}
+
+extern "C" {
+
+int fb_ns_opts_default(fb_ns_opts *o) {
+  if (!o) return FB_EINVAL;
+  std::memset(o, 0, sizeof(*o));
+  o->momentum_solver = FB_BICGSTAB;
+  o->momentum_precond = FB_BLOCK_JACOBI;
+  o->pressure_precond = FB_JACOBI;
+  o->newton_maxit = 10;
+  o->newton_atol = 1e-10;
+  o->momentum_rtol = 1e-12;
+  o->momentum_maxit = 1000;
+  o->pressure_maxit = 20000;
+  o->correction_maxit = 1000;
+  o->gmres_restart = 30;
+  o->check_every = 0;  // 0: automatic
+  o->chebyshev_degree = 4;
+  return FB_OK;
+}
+
+int fb_ns_create(fb_space *Wsp, fb_space *Psp, const fb_ns_opts *opts, fb_ns **out) {
+  if (!Wsp || !Psp || !out) return FB_EINVAL;
+  fb_ctx *ctx = Wsp->mesh->ctx;
+  FB_NEED_DEVICE(ctx);
+  if (Wsp->mesh != Psp->mesh) return fb_fail(ctx, FB_EINVAL, "fb_ns_create: W and P live on different meshes");
+  if (Wsp->degree != 2 || Wsp->ncomp != Wsp->mesh->dim || Psp->degree != 1 || Psp->ncomp != 1)
+    return fb_fail(ctx, FB_EINVAL, "fb_ns_create: need W = vector P2 (ncomp == gdim) and P = scalar P1");
+  FB_API_BEGIN(ctx)
+  std::unique_ptr<fb_ns> ns(new fb_ns());
+  ns->ctx = ctx;
+  ns->Wh = Wsp;
+  ns->Ph = Psp;
+  ns->W = dev_space(Wsp);
+  ns->P = dev_space(Psp);
+  ns->D = Wsp->mesh->dim;
+  ns->nu = Wsp->nnodes * ns->D;
+  ns->np = Psp->nnodes;
+  if (opts)
+    ns->opts = *opts;
+  else
+    fb_ns_opts_default(&ns->opts);
+  const int D = ns->D;
+  ns->Ap.ctx = ns->Mu.ctx = ns->J.ctx = ctx;
+  ns->Ap.sp = ns->P;
+  ns->Ap.block = 1;
+  ns->Ap.val.alloc((size_t)ns->P->nnz);
+  assemble_constant(ctx, *ns->P, 0, ns->Ap.val.p);
+  ns->Mu.sp = ns->W;
+  ns->Mu.block = 1;
+  ns->Mu.val.alloc((size_t)ns->W->nnz);
+  assemble_constant(ctx, *ns->W, 1, ns->Mu.val.p);
+  ns->J.sp = ns->W;
+  ns->J.block = D;
+  ns->J.val.alloc((size_t)ns->W->nnz * D * D);
+  for (DBuf<double> *v : {&ns->u0, &ns->ui, &ns->u1, &ns->F, &ns->delta, &ns->bu, &ns->dinv_u, &ns->tmp_u, &ns->xg_u})
+    v->alloc((size_t)ns->nu);
+  for (DBuf<double> *v : {&ns->p0, &ns->p1, &ns->bp, &ns->dinv_p, &ns->tmp_p, &ns->xg_p}) v->alloc((size_t)ns->np);
+  ns->binv.alloc((size_t)Wsp->nnodes * D * D);
+  ns->mask_u.alloc((size_t)ns->nu);
+  ns->mask_p.alloc((size_t)ns->np);
+  FB_CUDA(cudaStreamSynchronize(ctx->dev->stream));
+  *out = ns.release();
+  FB_API_END
+}
+
+int fb_ns_destroy(fb_ns *ns) {
+  delete ns;
+  return FB_OK;
+}
+
+int fb_ns_matrix(fb_ns *ns, int which, fb_mat **out) {
+  if (!ns || !out) return FB_EINVAL;
+  *out = which == 0 ? &ns->Ap : (which == 1 ? &ns->Mu : &ns->J);
+  return FB_OK;
+}
+
+int fb_ns_residual(fb_ns *ns, double dt, double rho, double mu, double theta, const double *ui, const double *u0,
+                   const double *p0, const double *load, double *F_out, int want_J) {
+  if (!ns || !ui || !u0 || !p0 || !F_out) return FB_EINVAL;
+  FB_API_BEGIN(ns->ctx)
+  cudaStream_t st = _ctx->dev->stream;
+  ns_upload(ns, ns->ui, ui, ns->nu, false);
+  ns_upload(ns, ns->u0, u0, ns->nu, false);
+  ns_upload(ns, ns->p0, p0, ns->np, false);
+  MomentumArgs a{dt, rho, mu, theta, ns->ui.p, ns->u0.p, ns->p0.p};
+  bool have_load = false;
+  if (load) {
+    ns_upload(ns, ns->load, load, ns->nu, false);
+    have_load = true;
+  }
+  ns_assemble_F(ns, a, have_load);
+  if (want_J) assemble_momentum_J(_ctx, *ns->W, a, ns->J.val.p);
+  FB_CUDA(cudaMemcpyAsync(F_out, ns->F.p, sizeof(double) * ns->nu, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(cudaStreamSynchronize(st));
+  FB_API_END
+}
+
+int fb_ns_pressure_rhs(fb_ns *ns, double dt, double rho, double mu, int rotational, const double *ui, const double *p0,
+                       double *b_out) {
+  if (!ns || !ui || !p0 || !b_out) return FB_EINVAL;
+  FB_API_BEGIN(ns->ctx)
+  cudaStream_t st = _ctx->dev->stream;
+  ns_upload(ns, ns->ui, ui, ns->nu, false);
+  ns_upload(ns, ns->p0, p0, ns->np, false);
+  assemble_pressure_rhs(_ctx, *ns->W, *ns->P, dt, rho, mu, rotational, ns->ui.p, ns->p0.p, ns->bp.p);
+  FB_CUDA(cudaMemcpyAsync(b_out, ns->bp.p, sizeof(double) * ns->np, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(cudaStreamSynchronize(st));
+  FB_API_END
+}
+
+int fb_ns_correction_rhs(fb_ns *ns, double dt, double rho, double mu, int rotational, const double *ui, const double *p1,
+                         const double *p0, double *b_out) {
+  if (!ns || !ui || !p0 || !p1 || !b_out) return FB_EINVAL;
+  FB_API_BEGIN(ns->ctx)
+  cudaStream_t st = _ctx->dev->stream;
+  ns_upload(ns, ns->ui, ui, ns->nu, false);
+  ns_upload(ns, ns->p0, p0, ns->np, false);
+  ns_upload(ns, ns->p1, p1, ns->np, false);
+  spmv(_ctx, make_linop(ns->Mu, ns->D, nullptr), ns->ui.p, ns->bu.p);
+  assemble_correction_grad(_ctx, *ns->W, dt, rho, mu, rotational, ns->ui.p, ns->p1.p, ns->p0.p, ns->bu.p);
+  FB_CUDA(cudaMemcpyAsync(b_out, ns->bu.p, sizeof(double) * ns->nu, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(cudaStreamSynchronize(st));
+  FB_API_END
+}
+
+int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flags, const double *u0, const double *p0,
+               int forcing, const double *f0, const double *f1, int64_t n_ubc, const int64_t *ubc_dofs,
+               const double *ubc_vals, int64_t n_pbc, const int64_t *pbc_dofs, const double *pbc_vals, double tol,
+               double *u1, double *p1, fb_ns_stats *stats) {
+  if (!ns) return FB_EINVAL;
+  fb_ctx *ctx = ns->ctx;
+  if (!u0 || !p0 || !u1 || !p1) return fb_fail(ctx, FB_EINVAL, "fb_ns_step: null state pointer");
+  // asserts of pressure_correction.py:488-489
+  if (!(dt > 0.0)) return fb_fail(ctx, FB_EINVAL, "fb_ns_step: dt must be > 0");
+  if (!(mu > 0.0)) return fb_fail(ctx, FB_EINVAL, "fb_ns_step: mu must be > 0");
+  if (!(rho > 0.0)) return fb_fail(ctx, FB_EINVAL, "fb_ns_step: rho must be > 0");
+  if (scheme < 0 || scheme > 2) return fb_fail(ctx, FB_EINVAL, "fb_ns_step: unknown time scheme");
+  if ((n_ubc > 0 && (!ubc_dofs || !ubc_vals)) || (n_pbc > 0 && (!pbc_dofs || !pbc_vals)) || n_ubc < 0 || n_pbc < 0)
+    return fb_fail(ctx, FB_EINVAL, "fb_ns_step: bad Dirichlet arrays");
+  for (int64_t i = 0; i < n_ubc; ++i)
+    if (ubc_dofs[i] < 0 || ubc_dofs[i] >= ns->nu) return fb_fail(ctx, FB_EINVAL, "fb_ns_step: velocity Dirichlet dof out of range");
+  for (int64_t i = 0; i < n_pbc; ++i)
+    if (pbc_dofs[i] < 0 || pbc_dofs[i] >= ns->np) return fb_fail(ctx, FB_EINVAL, "fb_ns_step: pressure Dirichlet dof out of range");
+  FB_API_BEGIN(ctx)
+  fb_device_state *dv = ctx->dev;
+  cudaStream_t st = dv->stream;
+  const bool dev = (flags & FB_DEVICE_PTRS) != 0;
+  const int rotational = (flags & FB_ROTATIONAL) ? 1 : 0;
+  const double theta = scheme == FB_FORWARD_EULER ? 0.0 : (scheme == FB_BACKWARD_EULER ? 1.0 : 0.5);
+  const int D = ns->D;
+  const int64_t nu = ns->nu, np = ns->np;
+  const fb_ns_opts &o = ns->opts;
+  const int64_t launches0 = ctx->launches;
+  fb_ns_stats s;
+  std::memset(&s, 0, sizeof(s));
+
+  FB_CUDA(cudaEventRecord(dv->ev[0], st));
+  ns_upload(ns, ns->u0, u0, nu, dev);
+  if (flags & FB_CHORIN)
+    ns->p0.zero(st);  // pressure_correction.py:545
+  else
+    ns_upload(ns, ns->p0, p0, np, dev);
+  const bool have_load = ns_build_load(ns, forcing, f0, f1, theta, dev);
+  double g2u = 0.0, g2p = 0.0;
+  if (n_ubc > 0) {
+    ns->ubc_dofs.upload(ubc_dofs, (size_t)n_ubc, st);
+    ns->ubc_vals.upload(ubc_vals, (size_t)n_ubc, st);
+    for (int64_t i = 0; i < n_ubc; ++i) g2u += ubc_vals[i] * ubc_vals[i];
+  }
+  if (n_pbc > 0) {
+    ns->pbc_dofs.upload(pbc_dofs, (size_t)n_pbc, st);
+    ns->pbc_vals.upload(pbc_vals, (size_t)n_pbc, st);
+    for (int64_t i = 0; i < n_pbc; ++i) g2p += pbc_vals[i] * pbc_vals[i];
+  }
+
+  // ---- tentative velocity: Newton on F1(ui) = 0 (pressure_correction.py:147-255)
+  FB_CUDA(cudaMemcpyAsync(ns->ui.p, ns->u0.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));  // :220
+  MomentumArgs ma{dt, rho, mu, theta, ns->ui.p, ns->u0.p, ns->p0.p};
+  auto residual = [&]() {
+    ns_assemble_F(ns, ma, have_load);
+    bc_residual(ctx, ns->F.p, ns->ui.p, ns->ubc_dofs.p, ns->ubc_vals.p, n_ubc);
+    return vec_norm2_sync(ctx, ns->F.p, nu);
+  };
+  double r = residual();
+  int newton = 0;
+  const int mom_check = o.check_every > 0 ? o.check_every : 2;
+  float ms;
+  while (!(r < o.newton_atol)) {
+    if (r != r) return fb_fail(ctx, FB_ENAN, "fb_ns_step: NaN in the momentum residual");
+    if (newton >= o.newton_maxit) {
+      char buf[160];
+      snprintf(buf, sizeof buf, "Newton solver did not converge in %d iterations (|F| = %.3e)", newton, r);
+      return fb_fail(ctx, FB_ENOCONV_NEWTON, buf);
+    }
+    FB_CUDA(cudaEventRecord(dv->ev[4], st));
+    assemble_momentum_J(ctx, *ns->W, ma, ns->J.val.p);
+    bc_rows_identity_blocked(ctx, *ns->W, D, ns->J.val.p, ns->ubc_dofs.p, n_ubc);
+    jacobi_setup_blocked(ctx, *ns->W, D, ns->J.val.p, o.momentum_precond == FB_BLOCK_JACOBI ? 1 : 0, ns->binv.p);
+    FB_CUDA(cudaEventRecord(dv->ev[5], st));
+    const double atol_inner = std::max(0.1 * o.newton_atol, o.momentum_rtol * r);
+    int its = 0;
+    const LinOp Jop = make_linop(ns->J, 1, nullptr);
+    // Only the first Newton update moves the Dirichlet dofs (delta = ui - g there); lift them so
+    // that the Krylov space lives on the free dofs (BiCGStab breaks down otherwise).
+    const bool lifted = (newton == 0 && n_ubc > 0);
+    if (lifted) lift_identity_rows(ctx, Jop, ns->F.p, ns->ubc_dofs.p, n_ubc, ns->xg_u.p, ns->tmp_u.p);
+    int status = krylov_bicgstab(ctx, Jop, ns->binv.p, ns->F.p, ns->delta.p, atol_inner, o.momentum_maxit, mom_check,
+                                 ns->kw_u, &its);
+    if (lifted) vec_axpy(ctx, ns->delta.p, 1.0, ns->xg_u.p, nu);
+    s.momentum_its += its;
+    FB_CUDA(cudaEventRecord(dv->ev[10], st));
+    if (status != FB_OK) {
+      char buf[160];
+      snprintf(buf, sizeof buf, "momentum Krylov solver failed after %d iterations (%s)", its, fb_status_string(status));
+      return fb_fail(ctx, status == FB_ENAN ? FB_ENAN : FB_ENOCONV_KRYLOV, buf);
+    }
+    vec_axpy(ctx, ns->ui.p, -1.0, ns->delta.p, nu);
+    ++newton;
+    r = residual();
+    FB_CUDA(cudaEventElapsedTime(&ms, dv->ev[4], dv->ev[5]));
+    s.ms_assembly_J += ms;
+    FB_CUDA(cudaEventElapsedTime(&ms, dv->ev[5], dv->ev[10]));
+    s.ms_momentum_solve += ms;
+  }
+  s.newton_its = newton;
+  s.newton_residual = r;
+  FB_CUDA(cudaEventRecord(dv->ev[1], st));
+
+  // ---- pressure Poisson (pressure_correction.py:258-433)
+  assemble_pressure_rhs(ctx, *ns->W, *ns->P, dt, rho, mu, rotational, ns->ui.p, ns->p0.p, ns->bp.p);
+  const int p_check = o.check_every > 0 ? o.check_every : 50;
+  int status;
+  if (n_pbc > 0) {
+    // solve(a2 == L2, bcs, symmetric=True): zero rows+columns, lifted RHS (:325-339)
+    ns->Ap_bc.alloc((size_t)ns->P->nnz);
+    mask_build(ctx, ns->mask_p.p, np, ns->pbc_dofs.p, n_pbc);
+    vec_fill(ctx, ns->xg_p.p, 0.0, np);
+    vec_set_at(ctx, ns->xg_p.p, ns->pbc_dofs.p, ns->pbc_vals.p, n_pbc);
+    spmv(ctx, make_linop(ns->Ap, 1, nullptr), ns->xg_p.p, ns->tmp_p.p);
+    vec_axpy(ctx, ns->bp.p, -1.0, ns->tmp_p.p, np);
+    vec_set_at(ctx, ns->bp.p, ns->pbc_dofs.p, ns->pbc_vals.p, n_pbc);
+    FB_CUDA(cudaMemcpyAsync(ns->Ap_bc.p, ns->Ap.val.p, sizeof(double) * ns->P->nnz, cudaMemcpyDeviceToDevice, st));
+    bc_symmetric_scalar(ctx, *ns->P, ns->Ap_bc.p, ns->mask_p.p);
+    jacobi_setup_scalar(ctx, *ns->P, ns->Ap_bc.p, 1, nullptr, ns->dinv_p.p);
+    LinOp A = make_linop(ns->Ap, 1, nullptr);
+    A.val = ns->Ap_bc.p;
+    status = krylov_pcg(ctx, A, ns->dinv_p.p, ns->bp.p, ns->p1.p, tol, 0.0, o.pressure_maxit, p_check, ns->kw_p,
+                        &s.pressure_its);
+  } else {
+    // pure Neumann: CG on the singular, consistent system from x0 = 0 (:340-432)
+    jacobi_setup_scalar(ctx, *ns->P, ns->Ap.val.p, 1, nullptr, ns->dinv_p.p);
+    status = krylov_pcg(ctx, make_linop(ns->Ap, 1, nullptr), ns->dinv_p.p, ns->bp.p, ns->p1.p, tol, 0.0,
+                        o.pressure_maxit, p_check, ns->kw_p, &s.pressure_its);
+  }
+  if (status != FB_OK) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "pressure CG failed after %d iterations (%s)", s.pressure_its, fb_status_string(status));
+    return fb_fail(ctx, status == FB_ENAN ? FB_ENAN : FB_ENOCONV_KRYLOV, buf);
+  }
+  FB_CUDA(cudaEventRecord(dv->ev[2], st));
+
+  // ---- velocity correction (pressure_correction.py:436-465)
+  spmv(ctx, make_linop(ns->Mu, D, nullptr), ns->ui.p, ns->bu.p);
+  assemble_correction_grad(ctx, *ns->W, dt, rho, mu, rotational, ns->ui.p, ns->p1.p, ns->p0.p, ns->bu.p);
+  status = solve_cg_masked(ctx, ns->Mu, D, ns->bu.p, ns->u1.p, n_ubc, ns->ubc_dofs.p, ns->ubc_vals.p, g2u, ns->mask_u.p,
+                           ns->dinv_u.p, ns->xg_u.p, ns->tmp_u.p, tol, o.correction_maxit,
+                           o.check_every > 0 ? o.check_every : 10, ns->kw_u, &s.correction_its);
+  if (status != FB_OK) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "velocity-correction CG failed after %d iterations (%s)", s.correction_its,
+             fb_status_string(status));
+    return fb_fail(ctx, status == FB_ENAN ? FB_ENAN : FB_ENOCONV_KRYLOV, buf);
+  }
+  (void)g2p;
+  const cudaMemcpyKind back = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  FB_CUDA(cudaMemcpyAsync(u1, ns->u1.p, sizeof(double) * nu, back, st));
+  FB_CUDA(cudaMemcpyAsync(p1, ns->p1.p, sizeof(double) * np, back, st));
+  FB_CUDA(cudaEventRecord(dv->ev[3], st));
+  FB_CUDA(cudaEventSynchronize(dv->ev[3]));
+  FB_CUDA(cudaEventElapsedTime(&ms, dv->ev[0], dv->ev[1]));
+  s.ms_tentative = ms;
+  FB_CUDA(cudaEventElapsedTime(&ms, dv->ev[1], dv->ev[2]));
+  s.ms_pressure = ms;
+  FB_CUDA(cudaEventElapsedTime(&ms, dv->ev[2], dv->ev[3]));
+  s.ms_correction = ms;
+  FB_CUDA(cudaEventElapsedTime(&ms, dv->ev[0], dv->ev[3]));
+  s.ms_total = ms;
+  s.launches = ctx->launches - launches0;
+  if (stats) *stats = s;
+  FB_API_END
+}
+
+}  // extern "C"
+
+// =============================================================================
+// heat (heat.py:20-122)
+// =============================================================================
+struct fb_heat {
+  fb_ctx *ctx = nullptr;
+  DevSpace *V = nullptr;
+  fb_mat A;
+  DBuf<double> S, mdiag, b, u, Au, out, rhs, x, dinv, bc_vals;
+  DBuf<int64_t> bc_dofs;
+  DBuf<uint8_t> mask;
+  KrylovWork kw;
+};
+
+extern "C" {
+
+int fb_heat_create(fb_space *Vsp, fb_space *Wsp, const double *conv, double kappa, double rho, double cp,
+                   const double *source_load, fb_heat **out) {
+  if (!Vsp || !out) return FB_EINVAL;
+  fb_ctx *ctx = Vsp->mesh->ctx;
+  FB_NEED_DEVICE(ctx);
+  if (Vsp->ncomp != 1) return fb_fail(ctx, FB_EINVAL, "fb_heat_create: V must be scalar");
+  if (conv && (!Wsp || Wsp->degree != 2 || Wsp->ncomp != Wsp->mesh->dim || Wsp->mesh != Vsp->mesh))
+    return fb_fail(ctx, FB_EINVAL, "fb_heat_create: conv needs a vector P2 space on the same mesh");
+  FB_API_BEGIN(ctx)
+  cudaStream_t st = ctx->dev->stream;
+  std::unique_ptr<fb_heat> h(new fb_heat());
+  h->ctx = ctx;
+  h->V = dev_space(Vsp);
+  DevSpace *W = conv ? dev_space(Wsp) : nullptr;
+  const int64_t n = h->V->nnodes;
+  h->A.ctx = ctx;
+  h->A.sp = h->V;
+  h->A.block = 1;
+  h->A.val.alloc((size_t)h->V->nnz);
+  DBuf<double> dconv;
+  if (conv) dconv.upload(conv, (size_t)Wsp->nnodes * Wsp->ncomp, st);
+  assemble_heat(ctx, *h->V, W, dconv.p, kappa / (rho * cp), h->A.val.p);
+  h->mdiag.alloc((size_t)n);
+  assemble_lumped(ctx, *h->V, h->mdiag.p);
+  h->b.alloc((size_t)n);
+  if (source_load)
+    FB_CUDA(cudaMemcpyAsync(h->b.p, source_load, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  else
+    h->b.zero(st);
+  for (DBuf<double> *v : {&h->u, &h->Au, &h->out, &h->rhs, &h->x, &h->dinv}) v->alloc((size_t)n);
+  h->S.alloc((size_t)h->V->nnz);
+  h->mask.alloc((size_t)n);
+  FB_CUDA(cudaStreamSynchronize(st));
+  *out = h.release();
+  FB_API_END
+}
+
+int fb_heat_destroy(fb_heat *h) {
+  delete h;
+  return FB_OK;
+}
+
+int fb_heat_matrix(fb_heat *h, int which, fb_mat **out) {
+  if (!h || !out || which != 0) return FB_EINVAL;
+  *out = &h->A;
+  return FB_OK;
+}
+
+int fb_heat_eval(fb_heat *h, double alpha, double beta, const double *u, double *out) {
+  if (!h || !u || !out) return FB_EINVAL;
+  FB_API_BEGIN(h->ctx)
+  cudaStream_t st = _ctx->dev->stream;
+  const int64_t n = h->V->nnodes;
+  FB_CUDA(cudaMemcpyAsync(h->u.p, u, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  spmv(_ctx, make_linop(h->A, 1, nullptr), h->u.p, h->Au.p);
+  FB_LAUNCH(_ctx, k_heat_eval, vgrid(_ctx, n), 256, 0, n, alpha, beta, h->mdiag.p, h->u.p, h->Au.p, h->b.p, h->out.p);
+  FB_CUDA(cudaMemcpyAsync(out, h->out.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(cudaStreamSynchronize(st));
+  FB_API_END
+}
+
+int fb_heat_solve(fb_heat *h, double alpha, double beta, double *b, int64_t nbc, const int64_t *bc_dofs,
+                  const double *bc_vals, double rtol, int maxit, double *x, int *iterations) {
+  if (!h || !b || !x) return FB_EINVAL;
+  if (nbc > 0 && (!bc_dofs || !bc_vals)) return FB_EINVAL;
+  FB_API_BEGIN(h->ctx)
+  cudaStream_t st = _ctx->dev->stream;
+  const int64_t n = h->V->nnodes, nnz = h->V->nnz;
+  for (int64_t i = 0; i < nbc; ++i) {
+    if (bc_dofs[i] < 0 || bc_dofs[i] >= n) return fb_fail(_ctx, FB_EINVAL, "fb_heat_solve: Dirichlet dof out of range");
+    b[bc_dofs[i]] = bc_vals[i];  // bc.apply(A, b) mutates the caller's b (heat.py:113-114)
+  }
+  FB_CUDA(cudaMemcpyAsync(h->rhs.p, b, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  // S = alpha M + beta A   (heat.py:106)
+  FB_LAUNCH(_ctx, k_scale_add_diag, vgrid(_ctx, nnz), 256, 0, nnz, n, beta, h->A.val.p, alpha, h->mdiag.p, h->V->diag.p, h->S.p);
+  FB_LAUNCH(_ctx, k_add_diag, vgrid(_ctx, n), 256, 0, n, alpha, h->mdiag.p, h->V->diag.p, h->S.p);
+  if (nbc > 0) {
+    h->bc_dofs.upload(bc_dofs, (size_t)nbc, st);
+    mask_build(_ctx, h->mask.p, n, h->bc_dofs.p, nbc);
+    bc_rows_identity_scalar(_ctx, *h->V, h->S.p, h->mask.p);
+  }
+  jacobi_setup_scalar(_ctx, *h->V, h->S.p, 1, nullptr, h->dinv.p);
+  const double bnorm = vec_norm2_sync(_ctx, h->rhs.p, n);
+  LinOp A = make_linop(h->A, 1, nullptr);
+  A.val = h->S.p;
+  int its = 0;
+  if (nbc > 0) lift_identity_rows(_ctx, A, h->rhs.p, h->bc_dofs.p, nbc, h->u.p, h->Au.p);
+  int status = krylov_bicgstab(_ctx, A, h->dinv.p, h->rhs.p, h->x.p, rtol * bnorm, maxit, 10, h->kw, &its);
+  if (nbc > 0) vec_axpy(_ctx, h->x.p, 1.0, h->u.p, n);
+  if (iterations) *iterations = its;
+  FB_CUDA(cudaMemcpyAsync(x, h->x.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(cudaStreamSynchronize(st));
+  if (status != FB_OK) return fb_fail(_ctx, status == FB_ENAN ? FB_ENAN : FB_ENOCONV_KRYLOV, "fb_heat_solve: BiCGStab failed");
+  FB_API_END
+}
+
+int fb_stokes_solve(fb_space *W, fb_space *P, double mu, int forcing, const double *f, int64_t n_ubc,
+                    const int64_t *ubc_dofs, const double *ubc_vals, int64_t n_pbc, const int64_t *pbc_dofs,
+                    const double *pbc_vals, double tol, int maxit, double *u, double *p, int *iterations);
+
+}  // extern "C"

@@ -1,0 +1,279 @@
+// Element-level math of the hot-path forms: affine simplex geometry, P1/P2 Lagrange
+// bases in barycentric coordinates (UFC ordering) and the pointwise
+// integrands of the momentum residual / Jacobian (pressure_correction.py:135-144,
+// :169-190, :202).  Everything here is FB_HD so that tests/hostsim can compile the
+// very same routines for the CPU-only unit tests; the shipped library only ever
+// calls them from CUDA kernels.
+#pragma once
+
+#if defined(__CUDACC__)
+#define FB_HD __host__ __device__ __forceinline__
+#else
+#define FB_HD inline
+#endif
+
+template <int D>
+struct Elem {
+  static constexpr int NV = D + 1;
+  static constexpr int NE = (D == 2) ? 3 : 6;
+  static constexpr int NL1 = NV;
+  static constexpr int NL2 = NV + NE;
+};
+
+// local edge e of a simplex joins local vertices edge_v<D>(e,0) < edge_v<D>(e,1)
+template <int D>
+FB_HD int edge_v(int e, int k) {
+  if (D == 2) {
+    // (1,2), (0,2), (0,1)
+    return k == 0 ? (e == 0 ? 1 : 0) : (e == 2 ? 1 : 2);
+  } else {
+    // (2,3), (1,3), (1,2), (0,3), (0,2), (0,1)
+    const int a = (e == 0) ? 2 : ((e == 1 || e == 2) ? 1 : 0);
+    const int b = (e == 0 || e == 1 || e == 3) ? 3 : ((e == 2 || e == 4) ? 2 : 1);
+    return k == 0 ? a : b;
+  }
+}
+
+// grad(lambda_m) (rows) and cell volume from the D+1 vertex coordinates X[v*D+k]
+template <int D>
+FB_HD void fb_geometry(const double *X, double glam[D + 1][D], double &vol) {
+  if (D == 2) {
+    const double ax = X[2] - X[0], ay = X[3] - X[1];
+    const double bx = X[4] - X[0], by = X[5] - X[1];
+    const double det = ax * by - bx * ay;
+    const double inv = 1.0 / det;
+    glam[1][0] = by * inv;
+    glam[1][1] = -bx * inv;
+    glam[2][0] = -ay * inv;
+    glam[2][1] = ax * inv;
+    glam[0][0] = -(glam[1][0] + glam[2][0]);
+    glam[0][1] = -(glam[1][1] + glam[2][1]);
+    vol = 0.5 * (det < 0 ? -det : det);
+  } else {
+    const double a0 = X[3] - X[0], a1 = X[4] - X[1], a2 = X[5] - X[2];
+    const double b0 = X[6] - X[0], b1 = X[7] - X[1], b2 = X[8] - X[2];
+    const double c0 = X[9] - X[0], c1 = X[10] - X[1], c2 = X[11] - X[2];
+    // cross products
+    const double bc0 = b1 * c2 - b2 * c1, bc1 = b2 * c0 - b0 * c2, bc2 = b0 * c1 - b1 * c0;
+    const double ca0 = c1 * a2 - c2 * a1, ca1 = c2 * a0 - c0 * a2, ca2 = c0 * a1 - c1 * a0;
+    const double ab0 = a1 * b2 - a2 * b1, ab1 = a2 * b0 - a0 * b2, ab2 = a0 * b1 - a1 * b0;
+    const double det = a0 * bc0 + a1 * bc1 + a2 * bc2;
+    const double inv = 1.0 / det;
+    glam[1][0] = bc0 * inv;
+    glam[1][1] = bc1 * inv;
+    glam[1][2] = bc2 * inv;
+    glam[2][0] = ca0 * inv;
+    glam[2][1] = ca1 * inv;
+    glam[2][2] = ca2 * inv;
+    glam[3][0] = ab0 * inv;
+    glam[3][1] = ab1 * inv;
+    glam[3][2] = ab2 * inv;
+    for (int k = 0; k < 3; ++k) glam[0][k] = -(glam[1][k] + glam[2][k] + glam[3][k]);
+    vol = (det < 0 ? -det : det) / 6.0;
+  }
+}
+
+// P2 basis function `a` at barycentric point lam
+template <int D>
+FB_HD double fb_p2_phi(int a, const double *lam) {
+  if (a <= D) return lam[a] * (2.0 * lam[a] - 1.0);
+  const int e = a - (D + 1);
+  return 4.0 * lam[edge_v<D>(e, 0)] * lam[edge_v<D>(e, 1)];
+}
+
+// physical gradient of P2 basis function `a` at lam
+template <int D>
+FB_HD void fb_p2_grad(int a, const double *lam, const double glam[D + 1][D], double g[D]) {
+  if (a <= D) {
+    const double s = 4.0 * lam[a] - 1.0;
+    for (int k = 0; k < D; ++k) g[k] = s * glam[a][k];
+  } else {
+    const int e = a - (D + 1);
+    const int va = edge_v<D>(e, 0), vb = edge_v<D>(e, 1);
+    const double sa = 4.0 * lam[vb], sb = 4.0 * lam[va];
+    for (int k = 0; k < D; ++k) g[k] = sa * glam[va][k] + sb * glam[vb][k];
+  }
+}
+
+// second derivatives d_k d_i phi_a (constant per cell)
+template <int D>
+FB_HD void fb_p2_hess(int a, const double glam[D + 1][D], double H[D][D]) {
+  if (a <= D) {
+    for (int i = 0; i < D; ++i)
+      for (int k = 0; k < D; ++k) H[i][k] = 4.0 * glam[a][i] * glam[a][k];
+  } else {
+    const int e = a - (D + 1);
+    const int va = edge_v<D>(e, 0), vb = edge_v<D>(e, 1);
+    for (int i = 0; i < D; ++i)
+      for (int k = 0; k < D; ++k) H[i][k] = 4.0 * (glam[va][i] * glam[vb][k] + glam[vb][i] * glam[va][k]);
+  }
+}
+
+// integral of P2 basis function a over the cell divided by the cell volume
+template <int D>
+FB_HD double fb_p2_mean(int a) {
+  if (D == 2) return a <= D ? 0.0 : 1.0 / 3.0;
+  return a <= D ? -1.0 / 20.0 : 1.0 / 5.0;
+}
+
+// ---- momentum integrands ----------------------------------------------------
+// One quadrature point's contribution to the D x D Jacobian block (test a, trial b):
+//   J[i][j] += w * { delta_ij [ phi_a phi_b + c1 ((u.grad phi_b) phi_a - (u.grad phi_a) phi_b) + c2 grad phi_a.grad phi_b ]
+//                    + c1 ( phi_a phi_b d_j u_i - d_j phi_a phi_b u_i ) + c2 d_i phi_b d_j phi_a }
+// with c1 = theta*dt/2 and c2 = theta*dt*mu/rho   (derivative(F1, ui), pressure_correction.py:202)
+template <int D>
+FB_HD void fb_jac_point(double w, double c1, double c2, double pa, double pb, const double ga[D], const double gb[D],
+                        const double u[D], const double gu[D][D], double J[D][D]) {
+  double uga = 0.0, ugb = 0.0, gab = 0.0;
+  for (int k = 0; k < D; ++k) {
+    uga += u[k] * ga[k];
+    ugb += u[k] * gb[k];
+    gab += ga[k] * gb[k];
+  }
+  const double m = w * pa * pb;
+  const double dg = m + w * (c1 * (ugb * pa - uga * pb) + c2 * gab);
+  const double c1m = c1 * m, c1wb = c1 * w * pb, c2w = c2 * w;
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) {
+      double v = c1m * gu[i][j] - c1wb * ga[j] * u[i] + c2w * gb[i] * ga[j];
+      if (i == j) v += dg;
+      J[i][j] += v;
+    }
+}
+
+// One quadrature point's contribution to  coef * R_cell(u; phi_a e_i)  without the forcing term:
+//   R = -rho/2 [ ((grad u)u)_i phi_a - (u.grad phi_a) u_i ] - 2 mu eps(u)_ik d_k phi_a + p0 d_i phi_a
+// (pressure_correction.py:138-141).  Returns the value for component i.
+template <int D>
+FB_HD double fb_rhs_point(int i, double rho, double mu, double pa, const double ga[D], const double u[D],
+                          const double gu[D][D], double p0) {
+  double conv = 0.0, uga = 0.0, visc = 0.0;
+  for (int k = 0; k < D; ++k) {
+    conv += gu[i][k] * u[k];
+    uga += u[k] * ga[k];
+    visc += (gu[i][k] + gu[k][i]) * ga[k];
+  }
+  return -0.5 * rho * (conv * pa - uga * u[i]) - mu * visc + p0 * ga[i];
+}
+
+// ---- exterior-facet integrands (pressure_correction.py:142-143) ------------------
+// phi_a vanishes identically on facet f (opposite local vertex f) unless node a lies on it
+template <int D>
+FB_HD bool fb_node_on_facet(int a, int f) {
+  if (a <= D) return a != f;
+  return edge_v<D>(a - (D + 1), 0) != f && edge_v<D>(a - (D + 1), 1) != f;
+}
+
+// barycentric point of the parent cell from facet-rule point q (qlam: nq x D)
+template <int D>
+FB_HD void fb_facet_point(int f, const double *qlam, int q, double lam[D + 1]) {
+  int n = 0;
+  for (int m = 0; m <= D; ++m) lam[m] = (m == f) ? 0.0 : qlam[q * D + n++];
+}
+
+// R_facet(u; phi_a e_i) = sum_q w_q phi_a [ -p0 n_i + mu ((grad u)^T n)_i ] |facet|
+// Ue: NL2 x D cell coefficients of u, p0e: D+1 vertex values of p0
+template <int D>
+FB_HD double fb_facet_F(int ta, int ti, int f, const double glam[D + 1][D], double vol, const double *qlam,
+                        const double *qw, int nq, const double *Ue, const double *p0e, double mu) {
+  constexpr int NL = Elem<D>::NL2;
+  double nA[D];  // outward normal times facet measure
+  for (int k = 0; k < D; ++k) nA[k] = -glam[f][k] * (D * vol);
+  double acc = 0.0;
+  for (int q = 0; q < nq; ++q) {
+    double lam[D + 1];
+    fb_facet_point<D>(f, qlam, q, lam);
+    const double pa = fb_p2_phi<D>(ta, lam);
+    double p0 = 0.0;
+    for (int v = 0; v <= D; ++v) p0 += p0e[v] * lam[v];
+    double gtn = 0.0;  // sum_k d_i u_k n_k
+    for (int b = 0; b < NL; ++b) {
+      double gb[D];
+      fb_p2_grad<D>(b, lam, glam, gb);
+      double un = 0.0;
+      for (int k = 0; k < D; ++k) un += Ue[b * D + k] * nA[k];
+      gtn += gb[ti] * un;
+    }
+    acc += qw[q] * pa * (-p0 * nA[ti] + mu * gtn);
+  }
+  return acc;
+}
+
+// B[i][j] = sum_q w_q phi_a d_i phi_b n_j |facet|   (derivative of ((grad u)^T n, v)_ds)
+template <int D>
+FB_HD void fb_facet_J(int ta, int tb, int f, const double glam[D + 1][D], double vol, const double *qlam,
+                      const double *qw, int nq, double B[D][D]) {
+  double nA[D], gs[D];
+  for (int k = 0; k < D; ++k) {
+    nA[k] = -glam[f][k] * (D * vol);
+    gs[k] = 0.0;
+  }
+  for (int q = 0; q < nq; ++q) {
+    double lam[D + 1], gb[D];
+    fb_facet_point<D>(f, qlam, q, lam);
+    const double pa = fb_p2_phi<D>(ta, lam);
+    fb_p2_grad<D>(tb, lam, glam, gb);
+    for (int k = 0; k < D; ++k) gs[k] += qw[q] * pa * gb[k];
+  }
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) B[i][j] = gs[i] * nA[j];
+}
+
+// ---- pressure / correction right-hand sides per cell -----------------------------
+// be[v] = -rho/dt (div u, psi_v) + (grad p0, grad psi_v) [- mu (grad div u, grad psi_v)]
+// (pressure_correction.py:318-323); q2lam/q2w: degree-2 cell rule
+template <int D>
+FB_HD void fb_pressure_rhs_cell(const double glam[D + 1][D], double vol, const double *q2lam, const double *q2w, int nq,
+                                const double *Ue, const double *p0e, double dt, double rho, double mu, int rotational,
+                                double be[D + 1]) {
+  constexpr int NL = Elem<D>::NL2;
+  for (int v = 0; v <= D; ++v) be[v] = 0.0;
+  for (int q = 0; q < nq; ++q) {
+    const double *lam = q2lam + q * (D + 1);
+    double div = 0.0;
+    for (int a = 0; a < NL; ++a) {
+      double g[D];
+      fb_p2_grad<D>(a, lam, glam, g);
+      for (int i = 0; i < D; ++i) div += Ue[a * D + i] * g[i];
+    }
+    const double w = -rho / dt * q2w[q] * vol * div;
+    for (int v = 0; v <= D; ++v) be[v] += w * lam[v];
+  }
+  double gv[D];
+  for (int k = 0; k < D; ++k) {
+    gv[k] = 0.0;
+    for (int v = 0; v <= D; ++v) gv[k] += p0e[v] * glam[v][k];
+  }
+  if (rotational) {
+    for (int a = 0; a < NL; ++a) {
+      double H[D][D];
+      fb_p2_hess<D>(a, glam, H);
+      for (int k = 0; k < D; ++k)
+        for (int i = 0; i < D; ++i) gv[k] -= mu * Ue[a * D + i] * H[i][k];
+    }
+  }
+  for (int v = 0; v <= D; ++v) {
+    double s = 0.0;
+    for (int k = 0; k < D; ++k) s += gv[k] * glam[v][k];
+    be[v] += vol * s;
+  }
+}
+
+// grad(phi), phi = p1 - p0 [+ mu div u]  (pressure_correction.py:444-446), constant per cell
+template <int D>
+FB_HD void fb_correction_gradphi(const double glam[D + 1][D], const double *Ue, const double *dpe, double mu,
+                                 int rotational, double gphi[D]) {
+  constexpr int NL = Elem<D>::NL2;
+  for (int k = 0; k < D; ++k) {
+    gphi[k] = 0.0;
+    for (int v = 0; v <= D; ++v) gphi[k] += dpe[v] * glam[v][k];
+  }
+  if (rotational) {
+    for (int a = 0; a < NL; ++a) {
+      double H[D][D];
+      fb_p2_hess<D>(a, glam, H);
+      for (int k = 0; k < D; ++k)
+        for (int i = 0; i < D; ++i) gphi[k] += mu * Ue[a * D + i] * H[i][k];
+    }
+  }
+}

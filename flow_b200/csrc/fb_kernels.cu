@@ -1,0 +1,1153 @@
+// CUDA kernels of the hot path (sm_100a): pattern/scatter-map setup, element assembly
+// (P1 stiffness, P2 mass, momentum residual + Jacobian, pressure / correction right-hand
+// sides, heat operator), Dirichlet application, fp64 CSR / block-CSR SpMV with fused dot
+// products, and the vector kernels.  fp64 throughout; bandwidth / atomic bound, so no
+// tensor cores (BASELINE.json north_star).
+//
+// Storage of a D x D block matrix ("row-planar block CSR"): block row I with nb blocks
+// holds D consecutive scalar rows of nb*D values each, i.e. the value array IS the
+// scalar CSR value array of the interleaved system; only the column indices are
+// compressed to one int per block.  SpMV lanes stream each scalar row contiguously
+// (coalesced) and share one x gather between the D rows.
+#include <algorithm>
+#include <vector>
+
+#include "fb_element.cuh"
+#include "fb_ops.h"
+
+namespace hq {
+#define FB_TABLE static const
+#include "fb_quadrature.h"
+#undef FB_TABLE
+}  // namespace hq
+namespace dq {
+#define FB_TABLE static __constant__ const
+#include "fb_quadrature.h"
+#undef FB_TABLE
+}  // namespace dq
+
+// ---- quadrature accessors ---------------------------------------------------
+template <int D>
+struct Q5;  // degree-5 cell rule
+template <>
+struct Q5<2> {
+  static constexpr int NQ = dq::TRI_D5_NQ;
+  __device__ static double lam(int q, int m) { return dq::TRI_D5_LAM[q][m]; }
+  __device__ static double w(int q) { return dq::TRI_D5_W[q]; }
+  static double hlam(int q, int m) { return hq::TRI_D5_LAM[q][m]; }
+  static double hw(int q) { return hq::TRI_D5_W[q]; }
+};
+template <>
+struct Q5<3> {
+  static constexpr int NQ = dq::TET_D5_NQ;
+  __device__ static double lam(int q, int m) { return dq::TET_D5_LAM[q][m]; }
+  __device__ static double w(int q) { return dq::TET_D5_W[q]; }
+  static double hlam(int q, int m) { return hq::TET_D5_LAM[q][m]; }
+  static double hw(int q) { return hq::TET_D5_W[q]; }
+};
+template <int D>
+struct Q2;  // degree-2 cell rule
+template <>
+struct Q2<2> {
+  static constexpr int NQ = dq::TRI_D2_NQ;
+  __device__ static const double *lam_ptr() { return &dq::TRI_D2_LAM[0][0]; }
+  __device__ static const double *w_ptr() { return dq::TRI_D2_W; }
+  __device__ static double lam(int q, int m) { return dq::TRI_D2_LAM[q][m]; }
+  __device__ static double w(int q) { return dq::TRI_D2_W[q]; }
+};
+template <>
+struct Q2<3> {
+  static constexpr int NQ = dq::TET_D2_NQ;
+  __device__ static const double *lam_ptr() { return &dq::TET_D2_LAM[0][0]; }
+  __device__ static const double *w_ptr() { return dq::TET_D2_W; }
+  __device__ static double lam(int q, int m) { return dq::TET_D2_LAM[q][m]; }
+  __device__ static double w(int q) { return dq::TET_D2_W[q]; }
+};
+template <int D>
+struct QF;  // facet rule (degree 5) in facet barycentrics (D entries)
+template <>
+struct QF<2> {
+  static constexpr int NQ = dq::SEG_D5_NQ;
+  __device__ static const double *lam_ptr() { return &dq::SEG_D5_LAM[0][0]; }
+  __device__ static const double *w_ptr() { return dq::SEG_D5_W; }
+};
+template <>
+struct QF<3> {
+  static constexpr int NQ = dq::TRI_D5_NQ;
+  __device__ static const double *lam_ptr() { return &dq::TRI_D5_LAM[0][0]; }
+  __device__ static const double *w_ptr() { return dq::TRI_D5_W; }
+};
+
+__constant__ double c_mref2[6 * 6];    // P2 reference mass / |K|, triangle
+__constant__ double c_mref3[10 * 10];  // tetrahedron
+static bool g_mref_uploaded = false;
+
+template <int D>
+static void upload_mref_dim(double *dst_symbol_host) {
+  constexpr int NL = Elem<D>::NL2;
+  for (int a = 0; a < NL; ++a)
+    for (int b = 0; b < NL; ++b) {
+      double s = 0;
+      for (int q = 0; q < Q5<D>::NQ; ++q) {
+        double lam[D + 1];
+        for (int m = 0; m <= D; ++m) lam[m] = Q5<D>::hlam(q, m);
+        s += Q5<D>::hw(q) * fb_p2_phi<D>(a, lam) * fb_p2_phi<D>(b, lam);
+      }
+      dst_symbol_host[a * NL + b] = s;
+    }
+}
+
+static void upload_mref() {
+  if (g_mref_uploaded) return;
+  double m2[36], m3[100];
+  upload_mref_dim<2>(m2);
+  upload_mref_dim<3>(m3);
+  FB_CUDA(cudaMemcpyToSymbol(c_mref2, m2, sizeof(m2)));
+  FB_CUDA(cudaMemcpyToSymbol(c_mref3, m3, sizeof(m3)));
+  g_mref_uploaded = true;
+}
+
+static inline int grid_for(int64_t work_items, int block, int cap) {
+  int64_t g = (work_items + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+// =============================================================================
+// setup kernels
+// =============================================================================
+__global__ void k_scatter_map(int64_t nc, int nl, const int *__restrict__ cell_nodes, const int *__restrict__ rowptr,
+                              const int *__restrict__ col, int *__restrict__ smap) {
+  const int64_t total = nc * nl * nl;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = t / (nl * nl);
+    const int r = (int)(t - c * nl * nl);
+    const int a = r / nl, b = r - a * nl;
+    const int I = cell_nodes[c * nl + a], J = cell_nodes[c * nl + b];
+    int lo = rowptr[I], hi = rowptr[I + 1] - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (col[mid] < J)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    smap[t] = lo;
+  }
+}
+
+__global__ void k_diag_slot(int64_t n, const int *__restrict__ rowptr, const int *__restrict__ col, int *__restrict__ diag) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int lo = rowptr[i], hi = rowptr[i + 1] - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (col[mid] < (int)i)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    diag[i] = lo;
+  }
+}
+
+void dev_space_build(fb_space *s, DevSpace &d) {
+  fb_ctx *ctx = s->mesh->ctx;
+  cudaStream_t st = ctx->dev->stream;
+  upload_mref();
+  fb_space_build_pattern(s);
+  const fb_mesh *m = s->mesh;
+  d.ctx = ctx;
+  d.dim = m->dim;
+  d.nl = s->nl;
+  d.degree = s->degree;
+  d.nnodes = s->nnodes;
+  d.nc = m->nc;
+  d.nnz = (int64_t)s->indices.size();
+  if (d.nnz * (int64_t)(m->dim * m->dim) > (int64_t)8e9 || d.nnz > INT32_MAX)
+    throw fb_cuda_error(FB_EINVAL, "pattern too large for one GPU (partition the mesh)");
+  d.xyz.upload(m->xyz.data(), m->xyz.size(), st);
+  d.cell_nodes.upload(s->cell_nodes.data(), s->cell_nodes.size(), st);
+  std::vector<int> rp(s->nnodes + 1);
+  for (int64_t i = 0; i <= s->nnodes; ++i) rp[i] = (int)s->indptr[i];
+  d.rowptr.upload(rp.data(), rp.size(), st);
+  d.col.upload(s->indices.data(), s->indices.size(), st);
+  d.diag.alloc(s->nnodes);
+  d.smap.alloc((size_t)d.nc * d.nl * d.nl);
+  d.nbf = (int64_t)m->bf_cell.size();
+  d.bf_cell.upload(m->bf_cell.data(), m->bf_cell.size(), st);
+  d.bf_local.upload(m->bf_local.data(), m->bf_local.size(), st);
+  FB_LAUNCH(ctx, k_scatter_map, grid_for(d.nc * d.nl * d.nl, 256, 148 * 16), 256, 0, d.nc, d.nl, d.cell_nodes.p,
+            d.rowptr.p, d.col.p, d.smap.p);
+  FB_LAUNCH(ctx, k_diag_slot, grid_for(d.nnodes, 256, 148 * 16), 256, 0, d.nnodes, d.rowptr.p, d.col.p, d.diag.p);
+  FB_CUDA(cudaStreamSynchronize(st));  // rp is a temporary
+}
+
+LinOp make_linop(const fb_mat &m, int ncomp, const uint8_t *mask) {
+  LinOp A;
+  A.block = m.block;
+  A.ncomp = m.block > 1 ? 1 : ncomp;
+  A.nrows = m.sp->nnodes;
+  A.rowptr = m.sp->rowptr.p;
+  A.col = m.sp->col.p;
+  A.val = m.val.p;
+  A.mask = mask;
+  return A;
+}
+
+// =============================================================================
+// constant operators: one thread per (cell, a, b)
+// =============================================================================
+template <int D, int DEG, int KIND>
+__global__ void k_assemble_constant(int64_t nc, const int *__restrict__ cell_nodes, const double *__restrict__ xyz,
+                                    const int *__restrict__ smap, double *__restrict__ val) {
+  constexpr int NL = DEG == 1 ? Elem<D>::NL1 : Elem<D>::NL2;
+  const int64_t total = nc * NL * NL;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = t / (NL * NL);
+    const int r = (int)(t - c * NL * NL);
+    const int a = r / NL, b = r - a * NL;
+    double X[(D + 1) * D];
+#pragma unroll
+    for (int v = 0; v <= D; ++v) {
+      const int node = cell_nodes[c * NL + v];
+#pragma unroll
+      for (int k = 0; k < D; ++k) X[v * D + k] = xyz[(int64_t)node * D + k];
+    }
+    double glam[D + 1][D], vol;
+    fb_geometry<D>(X, glam, vol);
+    double e = 0.0;
+    if (KIND == 1) {  // mass
+      if (DEG == 1)
+        e = vol * (a == b ? 2.0 : 1.0) / ((D + 1) * (D + 2));
+      else
+        e = vol * (D == 2 ? c_mref2[a * NL + b] : c_mref3[a * NL + b]);
+    } else {  // stiffness
+      if (DEG == 1) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) e += glam[a][k] * glam[b][k];
+        e *= vol;
+      } else {
+        for (int q = 0; q < Q2<D>::NQ; ++q) {
+          double lam[D + 1], ga[D], gb[D];
+#pragma unroll
+          for (int m = 0; m <= D; ++m) lam[m] = Q2<D>::lam(q, m);
+          fb_p2_grad<D>(a, lam, glam, ga);
+          fb_p2_grad<D>(b, lam, glam, gb);
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) s += ga[k] * gb[k];
+          e += Q2<D>::w(q) * s;
+        }
+        e *= vol;
+      }
+    }
+    atomicAdd(&val[smap[t]], e);
+  }
+}
+
+void assemble_constant(fb_ctx *ctx, DevSpace &sp, int kind, double *val) {
+  FB_CUDA(cudaMemsetAsync(val, 0, sizeof(double) * sp.nnz, ctx->dev->stream));
+  const int g = grid_for(sp.nc * sp.nl * sp.nl, 256, 148 * 32);
+#define FB_AC(D, DEG, KIND)                                                                                     \
+  FB_LAUNCH(ctx, (k_assemble_constant<D, DEG, KIND>), g, 256, 0, sp.nc, sp.cell_nodes.p, sp.xyz.p, sp.smap.p, val)
+  if (sp.dim == 2 && sp.degree == 1 && kind == 0) FB_AC(2, 1, 0);
+  else if (sp.dim == 2 && sp.degree == 1) FB_AC(2, 1, 1);
+  else if (sp.dim == 2 && kind == 0) FB_AC(2, 2, 0);
+  else if (sp.dim == 2) FB_AC(2, 2, 1);
+  else if (sp.degree == 1 && kind == 0) FB_AC(3, 1, 0);
+  else if (sp.degree == 1) FB_AC(3, 1, 1);
+  else if (kind == 0) FB_AC(3, 2, 0);
+  else FB_AC(3, 2, 1);
+#undef FB_AC
+}
+
+template <int D>
+__global__ void k_lumped(int64_t nc, int nl, const int *__restrict__ cell_nodes, const double *__restrict__ xyz,
+                         double *__restrict__ diag) {
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
+    double X[(D + 1) * D];
+    int nodes[D + 1];
+    for (int v = 0; v <= D; ++v) {
+      nodes[v] = cell_nodes[c * nl + v];
+      for (int k = 0; k < D; ++k) X[v * D + k] = xyz[(int64_t)nodes[v] * D + k];
+    }
+    double glam[D + 1][D], vol;
+    fb_geometry<D>(X, glam, vol);
+    for (int v = 0; v <= D; ++v) atomicAdd(&diag[nodes[v]], vol / (D + 1));
+  }
+}
+
+void assemble_lumped(fb_ctx *ctx, DevSpace &sp, double *diag) {
+  FB_CUDA(cudaMemsetAsync(diag, 0, sizeof(double) * sp.nnodes, ctx->dev->stream));
+  const int g = grid_for(sp.nc, 256, 148 * 16);
+  if (sp.dim == 2)
+    FB_LAUNCH(ctx, k_lumped<2>, g, 256, 0, sp.nc, sp.nl, sp.cell_nodes.p, sp.xyz.p, diag);
+  else
+    FB_LAUNCH(ctx, k_lumped<3>, g, 256, 0, sp.nc, sp.nl, sp.cell_nodes.p, sp.xyz.p, diag);
+}
+
+// =============================================================================
+// SpMV
+// =============================================================================
+// scalar CSR times NC interleaved vectors; T lanes cooperate on a row.
+template <int NC, int T, int DOT>
+__global__ void __launch_bounds__(256)
+    k_spmm(int64_t nrows, const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val,
+           const uint8_t *__restrict__ mask, const double *__restrict__ x, double *__restrict__ y,
+           const double *__restrict__ w, double *partials, unsigned int *counter, double *red, int slot,
+           const int *__restrict__ flag) {
+  if (flag && *flag) return;
+  const int lane = threadIdx.x % T;
+  const int64_t group = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / T;
+  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / T;
+  double d[2] = {0.0, 0.0};
+  const int64_t nrows_pad = ((nrows + ngroups - 1) / ngroups) * ngroups;  // keep shuffles convergent
+  for (int64_t row = group; row < nrows_pad; row += ngroups) {
+    double acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+    if (row < nrows) {
+      const int r0 = rowptr[row], r1 = rowptr[row + 1];
+      for (int k = r0 + lane; k < r1; k += T) {
+        const double a = __ldcs(&val[k]);
+        const int64_t j = col[k];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] += a * x[j * NC + c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int o = T / 2; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    if (row < nrows && lane < NC) {
+      // lane c finalises component c
+      double yc = acc[0];
+#pragma unroll
+      for (int c = 1; c < NC; ++c)
+        if (lane == c) yc = acc[c];
+      const int64_t dof = row * NC + lane;
+      if (mask && mask[dof]) yc = x[dof];
+      y[dof] = yc;
+      if (DOT >= 1) d[0] += w[dof] * yc;
+      if (DOT >= 2) d[1] += yc * yc;
+    }
+  }
+  if (DOT >= 1) {
+    if (DOT == 1) {
+      double v1[1] = {d[0]};
+      fb_grid_reduce<1>(v1, partials, counter, red, slot);
+    } else {
+      fb_grid_reduce<2>(d, partials, counter, red, slot);
+    }
+  }
+}
+
+// D x D row-planar block CSR; one warp (T = 32) or half warp per block row.
+template <int D, int T, int DOT>
+__global__ void __launch_bounds__(256)
+    k_bspmv(int64_t nrows, const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val,
+            const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, double *partials,
+            unsigned int *counter, double *red, int slot, const int *__restrict__ flag) {
+  if (flag && *flag) return;
+  const int lane = threadIdx.x % T;
+  const int64_t group = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / T;
+  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / T;
+  double d[2] = {0.0, 0.0};
+  const int64_t nrows_pad = ((nrows + ngroups - 1) / ngroups) * ngroups;
+  for (int64_t row = group; row < nrows_pad; row += ngroups) {
+    double acc[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) acc[i] = 0.0;
+    if (row < nrows) {
+      const int r0 = rowptr[row];
+      const int len = (rowptr[row + 1] - r0) * D;
+      const double *v = val + (int64_t)r0 * (D * D);
+      for (int t = lane; t < len; t += T) {
+        const int blk = t / D;
+        const int j = t - blk * D;
+        const double xv = x[(int64_t)col[r0 + blk] * D + j];
+#pragma unroll
+        for (int i = 0; i < D; ++i) acc[i] += __ldcs(&v[i * len + t]) * xv;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int o = T / 2; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    if (row < nrows && lane < D) {
+      double yc = acc[0];
+#pragma unroll
+      for (int i = 1; i < D; ++i)
+        if (lane == i) yc = acc[i];
+      const int64_t dof = row * D + lane;
+      y[dof] = yc;
+      if (DOT >= 1) d[0] += w[dof] * yc;
+      if (DOT >= 2) d[1] += yc * yc;
+    }
+  }
+  if (DOT >= 1) {
+    if (DOT == 1) {
+      double v1[1] = {d[0]};
+      fb_grid_reduce<1>(v1, partials, counter, red, slot);
+    } else {
+      fb_grid_reduce<2>(d, partials, counter, red, slot);
+    }
+  }
+}
+
+template <int NC, int T>
+static void launch_spmm(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_mode, const double *w, int slot,
+                        const int *flag) {
+  fb_device_state *dv = ctx->dev;
+  const int block = 256;
+  const int64_t rows_per_block = block / T;
+  const int g = grid_for((A.nrows + rows_per_block - 1) / rows_per_block * block, block, dv->sm_count * 8);
+#define FB_SP(DOT)                                                                                                  \
+  FB_LAUNCH(ctx, (k_spmm<NC, T, DOT>), g, block, 0, A.nrows, A.rowptr, A.col, A.val, A.mask, x, y, w, dv->partials, \
+            dv->counter, dv->red, slot, flag)
+  if (dot_mode == 0) FB_SP(0);
+  else if (dot_mode == 1) FB_SP(1);
+  else FB_SP(2);
+#undef FB_SP
+}
+
+template <int D, int T>
+static void launch_bspmv(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_mode, const double *w, int slot,
+                         const int *flag) {
+  fb_device_state *dv = ctx->dev;
+  const int block = 256;
+  const int64_t rows_per_block = block / T;
+  const int g = grid_for((A.nrows + rows_per_block - 1) / rows_per_block * block, block, dv->sm_count * 8);
+#define FB_BS(DOT)                                                                                             \
+  FB_LAUNCH(ctx, (k_bspmv<D, T, DOT>), g, block, 0, A.nrows, A.rowptr, A.col, A.val, x, y, w, dv->partials,   \
+            dv->counter, dv->red, slot, flag)
+  if (dot_mode == 0) FB_BS(0);
+  else if (dot_mode == 1) FB_BS(1);
+  else FB_BS(2);
+#undef FB_BS
+}
+
+void spmv(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_mode, const double *w, int slot,
+          const int *flag) {
+  if (A.block == 2) return launch_bspmv<2, 16>(ctx, A, x, y, dot_mode, w, slot, flag);
+  if (A.block == 3) return launch_bspmv<3, 32>(ctx, A, x, y, dot_mode, w, slot, flag);
+  // scalar: pick lanes per row from the average row length
+  switch (A.ncomp) {
+    case 1:
+      return launch_spmm<1, 8>(ctx, A, x, y, dot_mode, w, slot, flag);
+    case 2:
+      return launch_spmm<2, 8>(ctx, A, x, y, dot_mode, w, slot, flag);
+    case 3:
+      return launch_spmm<3, 16>(ctx, A, x, y, dot_mode, w, slot, flag);
+    default:
+      throw fb_cuda_error(FB_EINVAL, "spmv: ncomp must be 1..3");
+  }
+}
+
+// =============================================================================
+// vector kernels
+// =============================================================================
+__global__ void k_fill(double *x, double a, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = a;
+}
+__global__ void k_axpy(double *y, double a, const double *__restrict__ x, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] += a * x[i];
+}
+__global__ void k_axpby(double *z, double a, const double *x, double b, const double *y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    z[i] = a * x[i] + b * y[i];
+}
+__global__ void k_dot(const double *__restrict__ x, const double *__restrict__ y, int64_t n, double *partials,
+                      unsigned int *counter, double *red, int slot) {
+  double v[1] = {0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    v[0] += x[i] * y[i];
+  fb_grid_reduce<1>(v, partials, counter, red, slot);
+}
+__global__ void k_mask_set(uint8_t *mask, const int64_t *__restrict__ dofs, int64_t nbc) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nbc; i += (int64_t)gridDim.x * blockDim.x)
+    mask[dofs[i]] = 1;
+}
+__global__ void k_set_at(double *x, const int64_t *__restrict__ dofs, const double *__restrict__ vals, int64_t nbc) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nbc; i += (int64_t)gridDim.x * blockDim.x)
+    x[dofs[i]] = vals ? vals[i] : 0.0;
+}
+__global__ void k_copy_at(double *dst, const double *__restrict__ src, const int64_t *__restrict__ dofs, int64_t nbc) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nbc; i += (int64_t)gridDim.x * blockDim.x)
+    dst[dofs[i]] = src[dofs[i]];
+}
+__global__ void k_bc_residual(double *F, const double *__restrict__ x, const int64_t *__restrict__ dofs,
+                              const double *__restrict__ vals, int64_t nbc) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nbc; i += (int64_t)gridDim.x * blockDim.x)
+    F[dofs[i]] = x[dofs[i]] - vals[i];
+}
+
+static inline int vgrid(fb_ctx *ctx, int64_t n) { return grid_for(n, 256, ctx->dev->sm_count * 8); }
+
+void vec_fill(fb_ctx *ctx, double *x, double a, int64_t n) { FB_LAUNCH(ctx, k_fill, vgrid(ctx, n), 256, 0, x, a, n); }
+void vec_axpy(fb_ctx *ctx, double *y, double a, const double *x, int64_t n) {
+  FB_LAUNCH(ctx, k_axpy, vgrid(ctx, n), 256, 0, y, a, x, n);
+}
+void vec_axpby(fb_ctx *ctx, double *z, double a, const double *x, double b, const double *y, int64_t n) {
+  FB_LAUNCH(ctx, k_axpby, vgrid(ctx, n), 256, 0, z, a, x, b, y, n);
+}
+void vec_dot(fb_ctx *ctx, const double *x, const double *y, int64_t n, int slot) {
+  fb_device_state *dv = ctx->dev;
+  FB_LAUNCH(ctx, k_dot, vgrid(ctx, n), 256, 0, x, y, n, dv->partials, dv->counter, dv->red, slot);
+}
+double vec_norm2_sync(fb_ctx *ctx, const double *x, int64_t n) {
+  fb_device_state *dv = ctx->dev;
+  vec_dot(ctx, x, x, n, FB_NSLOTS - 1);
+  FB_CUDA(cudaMemcpyAsync(dv->host_pinned, dv->red + (FB_NSLOTS - 1), sizeof(double), cudaMemcpyDeviceToHost, dv->stream));
+  FB_CUDA(cudaStreamSynchronize(dv->stream));
+  return sqrt(dv->host_pinned[0]);
+}
+void mask_build(fb_ctx *ctx, uint8_t *mask, int64_t ndofs, const int64_t *dofs, int64_t nbc) {
+  FB_CUDA(cudaMemsetAsync(mask, 0, ndofs, ctx->dev->stream));
+  if (nbc > 0) FB_LAUNCH(ctx, k_mask_set, vgrid(ctx, nbc), 256, 0, mask, dofs, nbc);
+}
+void vec_set_at(fb_ctx *ctx, double *x, const int64_t *dofs, const double *vals, int64_t nbc) {
+  if (nbc > 0) FB_LAUNCH(ctx, k_set_at, vgrid(ctx, nbc), 256, 0, x, dofs, vals, nbc);
+}
+void vec_zero_at(fb_ctx *ctx, double *x, const int64_t *dofs, int64_t nbc) {
+  if (nbc > 0) FB_LAUNCH(ctx, k_set_at, vgrid(ctx, nbc), 256, 0, x, dofs, (const double *)nullptr, nbc);
+}
+void vec_copy_at(fb_ctx *ctx, double *dst, const double *src, const int64_t *dofs, int64_t nbc) {
+  if (nbc > 0) FB_LAUNCH(ctx, k_copy_at, vgrid(ctx, nbc), 256, 0, dst, src, dofs, nbc);
+}
+// Lift the constrained unknowns of a system whose constrained rows are identity rows:
+// xg = b on the constrained dofs (0 elsewhere), b <- b - A xg with b = 0 on constrained rows.
+// Afterwards every Krylov vector vanishes on those dofs; add xg back to the solution.
+void lift_identity_rows(fb_ctx *ctx, const LinOp &A, double *b, const int64_t *dofs, int64_t nbc, double *xg, double *tmp) {
+  const int64_t n = A.ndofs();
+  vec_fill(ctx, xg, 0.0, n);
+  vec_copy_at(ctx, xg, b, dofs, nbc);
+  spmv(ctx, A, xg, tmp);
+  vec_axpy(ctx, b, -1.0, tmp, n);
+  vec_zero_at(ctx, b, dofs, nbc);
+}
+void bc_residual(fb_ctx *ctx, double *F, const double *x, const int64_t *dofs, const double *vals, int64_t nbc) {
+  if (nbc > 0) FB_LAUNCH(ctx, k_bc_residual, vgrid(ctx, nbc), 256, 0, F, x, dofs, vals, nbc);
+}
+
+// =============================================================================
+// Dirichlet application on matrices  (DirichletBC.apply / assemble_system [EXT])
+// =============================================================================
+// Newton Jacobian rows -> identity (non-symmetric apply, pressure_correction.py:226)
+template <int D>
+__global__ void k_bc_rows_blocked(const int *__restrict__ rowptr, const int *__restrict__ diag, double *__restrict__ val,
+                                  const int64_t *__restrict__ dofs, int64_t nbc) {
+  // one warp per constrained dof
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t b = warp; b < nbc; b += nwarps) {
+    const int64_t dof = dofs[b];
+    const int64_t I = dof / D;
+    const int i = (int)(dof - I * D);
+    const int r0 = rowptr[I];
+    const int len = (rowptr[I + 1] - r0) * D;
+    double *row = val + (int64_t)r0 * (D * D) + (int64_t)i * len;
+    const int dpos = (diag[I] - r0) * D + i;
+    for (int t = lane; t < len; t += 32) row[t] = (t == dpos) ? 1.0 : 0.0;
+  }
+}
+
+void bc_rows_identity_blocked(fb_ctx *ctx, const DevSpace &sp, int D, double *val, const int64_t *dofs, int64_t nbc) {
+  if (nbc <= 0) return;
+  const int g = grid_for(nbc * 32, 256, ctx->dev->sm_count * 8);
+  if (D == 2)
+    FB_LAUNCH(ctx, k_bc_rows_blocked<2>, g, 256, 0, sp.rowptr.p, sp.diag.p, val, dofs, nbc);
+  else
+    FB_LAUNCH(ctx, k_bc_rows_blocked<3>, g, 256, 0, sp.rowptr.p, sp.diag.p, val, dofs, nbc);
+}
+
+// scalar matrix: SYM = 1 zero row + column with unit diagonal, SYM = 0 row only
+template <int SYM>
+__global__ void k_bc_scalar(int64_t n, const int *__restrict__ rowptr, const int *__restrict__ col,
+                            double *__restrict__ val, const uint8_t *__restrict__ mask) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool mi = mask[i];
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+      const int j = col[k];
+      if (mi)
+        val[k] = (j == (int)i) ? 1.0 : 0.0;
+      else if (SYM && mask[j])
+        val[k] = 0.0;
+    }
+  }
+}
+
+void bc_symmetric_scalar(fb_ctx *ctx, const DevSpace &sp, double *val, const uint8_t *mask) {
+  FB_LAUNCH(ctx, k_bc_scalar<1>, vgrid(ctx, sp.nnodes), 256, 0, sp.nnodes, sp.rowptr.p, sp.col.p, val, mask);
+}
+void bc_rows_identity_scalar(fb_ctx *ctx, const DevSpace &sp, double *val, const uint8_t *mask) {
+  FB_LAUNCH(ctx, k_bc_scalar<0>, vgrid(ctx, sp.nnodes), 256, 0, sp.nnodes, sp.rowptr.p, sp.col.p, val, mask);
+}
+
+// =============================================================================
+// Jacobi / block-Jacobi setup
+// =============================================================================
+__global__ void k_jacobi_scalar(int64_t n, int ncomp, const int *__restrict__ diag, const double *__restrict__ val,
+                                const uint8_t *__restrict__ mask, double *__restrict__ dinv) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n * ncomp; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / ncomp;
+    const double dd = val[diag[i]];
+    dinv[t] = (mask && mask[t]) ? 1.0 : 1.0 / dd;
+  }
+}
+
+void jacobi_setup_scalar(fb_ctx *ctx, const DevSpace &sp, const double *val, int ncomp, const uint8_t *mask, double *dinv) {
+  FB_LAUNCH(ctx, k_jacobi_scalar, vgrid(ctx, sp.nnodes * ncomp), 256, 0, sp.nnodes, ncomp, sp.diag.p, val, mask, dinv);
+}
+
+template <int D>
+__global__ void k_jacobi_blocked(int64_t n, const int *__restrict__ rowptr, const int *__restrict__ diag,
+                                 const double *__restrict__ val, int block_mode, double *__restrict__ binv) {
+  for (int64_t I = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; I < n; I += (int64_t)gridDim.x * blockDim.x) {
+    const int r0 = rowptr[I];
+    const int len = (rowptr[I + 1] - r0) * D;
+    const double *base = val + (int64_t)r0 * (D * D) + (int64_t)(diag[I] - r0) * D;
+    double A[D][D], B[D][D];
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < D; ++j) A[i][j] = base[(int64_t)i * len + j];
+    if (block_mode == 0) {
+      for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) B[i][j] = (i == j) ? 1.0 / A[i][i] : 0.0;
+    } else if (D == 2) {
+      const double det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+      const double inv = 1.0 / det;
+      B[0][0] = A[1][1] * inv;
+      B[0][1] = -A[0][1] * inv;
+      B[1][0] = -A[1][0] * inv;
+      B[1][1] = A[0][0] * inv;
+    } else {
+      const double c00 = A[1][1] * A[2 % D][2 % D] - A[1][2 % D] * A[2 % D][1];
+      const double c01 = A[1][2 % D] * A[2 % D][0] - A[1][0] * A[2 % D][2 % D];
+      const double c02 = A[1][0] * A[2 % D][1] - A[1][1] * A[2 % D][0];
+      const double det = A[0][0] * c00 + A[0][1] * c01 + A[0][2 % D] * c02;
+      const double inv = 1.0 / det;
+      B[0][0] = c00 * inv;
+      B[1][0] = c01 * inv;
+      B[2 % D][0] = c02 * inv;
+      B[0][1] = (A[0][2 % D] * A[2 % D][1] - A[0][1] * A[2 % D][2 % D]) * inv;
+      B[1][1] = (A[0][0] * A[2 % D][2 % D] - A[0][2 % D] * A[2 % D][0]) * inv;
+      B[2 % D][1] = (A[0][1] * A[2 % D][0] - A[0][0] * A[2 % D][1]) * inv;
+      B[0][2 % D] = (A[0][1] * A[1][2 % D] - A[0][2 % D] * A[1][1]) * inv;
+      B[1][2 % D] = (A[0][2 % D] * A[1][0] - A[0][0] * A[1][2 % D]) * inv;
+      B[2 % D][2 % D] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) * inv;
+    }
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < D; ++j) binv[I * (D * D) + i * D + j] = B[i][j];
+  }
+}
+
+void jacobi_setup_blocked(fb_ctx *ctx, const DevSpace &sp, int D, const double *val, int block_mode, double *binv) {
+  const int g = vgrid(ctx, sp.nnodes);
+  if (D == 2)
+    FB_LAUNCH(ctx, k_jacobi_blocked<2>, g, 256, 0, sp.nnodes, sp.rowptr.p, sp.diag.p, val, block_mode, binv);
+  else
+    FB_LAUNCH(ctx, k_jacobi_blocked<3>, g, 256, 0, sp.nnodes, sp.rowptr.p, sp.diag.p, val, block_mode, binv);
+}
+
+// =============================================================================
+// momentum residual and Jacobian: one warp per cell
+// =============================================================================
+constexpr int MOM_WARPS = 4;
+
+template <int D>
+struct MomShared {
+  static constexpr int NL = Elem<D>::NL2;
+  static constexpr int NQ = Q5<D>::NQ;
+  double phi[NQ][NL];
+  double U[MOM_WARPS][NL][D];
+  double g[MOM_WARPS][NQ][NL][D];
+  double uq[MOM_WARPS][NQ][D];
+  double gu[MOM_WARPS][NQ][D][D];
+  double p0q[MOM_WARPS][NQ];
+};
+
+template <int D>
+__device__ __forceinline__ void mom_fill_phi(MomShared<D> &s) {
+  constexpr int NL = Elem<D>::NL2, NQ = Q5<D>::NQ;
+  for (int t = threadIdx.x; t < NQ * NL; t += blockDim.x) {
+    const int q = t / NL, a = t - q * NL;
+    double lam[D + 1];
+#pragma unroll
+    for (int m = 0; m <= D; ++m) lam[m] = Q5<D>::lam(q, m);
+    s.phi[q][a] = fb_p2_phi<D>(a, lam);
+  }
+}
+
+// gather the cell's coefficients of `u`, tabulate gradients and evaluate u, grad u at all points
+template <int D>
+__device__ __forceinline__ void mom_phase_a(MomShared<D> &s, int wid, int lane, const int *__restrict__ cn,
+                                            const double *__restrict__ u, const double glam[D + 1][D], bool first,
+                                            bool need_grad) {
+  constexpr int NL = Elem<D>::NL2, NQ = Q5<D>::NQ;
+  if (lane < NL) {
+    const int64_t node = cn[lane];
+#pragma unroll
+    for (int i = 0; i < D; ++i) s.U[wid][lane][i] = u[node * D + i];
+  }
+  if (first) {
+    for (int t = lane; t < NQ * NL; t += 32) {
+      const int q = t / NL, a = t - q * NL;
+      double lam[D + 1], g[D];
+#pragma unroll
+      for (int m = 0; m <= D; ++m) lam[m] = Q5<D>::lam(q, m);
+      fb_p2_grad<D>(a, lam, glam, g);
+#pragma unroll
+      for (int k = 0; k < D; ++k) s.g[wid][q][a][k] = g[k];
+    }
+  }
+  __syncwarp();
+  constexpr int PER_Q = D * (D + 1);
+  for (int t = lane; t < NQ * PER_Q; t += 32) {
+    const int q = t / PER_Q;
+    const int r = t - q * PER_Q;
+    const int i = r / (D + 1), kk = r - i * (D + 1);
+    double acc = 0.0;
+    if (kk == 0) {
+#pragma unroll
+      for (int a = 0; a < NL; ++a) acc += s.U[wid][a][i] * s.phi[q][a];
+      s.uq[wid][q][i] = acc;
+    } else if (need_grad) {
+#pragma unroll
+      for (int a = 0; a < NL; ++a) acc += s.U[wid][a][i] * s.g[wid][q][a][kk - 1];
+      s.gu[wid][q][i][kk - 1] = acc;
+    }
+  }
+  __syncwarp();
+}
+
+template <int D>
+__device__ __forceinline__ void cell_geometry(const int *__restrict__ cn, const double *__restrict__ xyz,
+                                              double glam[D + 1][D], double &vol) {
+  double X[(D + 1) * D];
+#pragma unroll
+  for (int v = 0; v <= D; ++v) {
+    const int64_t node = cn[v];
+#pragma unroll
+    for (int k = 0; k < D; ++k) X[v * D + k] = xyz[node * D + k];
+  }
+  fb_geometry<D>(X, glam, vol);
+}
+
+template <int D>
+__global__ void __launch_bounds__(MOM_WARPS * 32)
+    k_momentum_F(int64_t nc, const int *__restrict__ cell_nodes, const double *__restrict__ xyz, MomentumArgs a,
+                 double *__restrict__ F) {
+  constexpr int NL = Elem<D>::NL2, NQ = Q5<D>::NQ;
+  __shared__ MomShared<D> s;
+  mom_fill_phi<D>(s);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t warp0 = blockIdx.x * (int64_t)MOM_WARPS + wid;
+  const int64_t nwarps = (int64_t)gridDim.x * MOM_WARPS;
+  const double cdt = a.dt / a.rho;
+  for (int64_t c = warp0; c < nc; c += nwarps) {
+    const int *cn = cell_nodes + c * NL;
+    double glam[D + 1][D], vol;
+    cell_geometry<D>(cn, xyz, glam, vol);
+    if (lane < NQ) {
+      double p = 0.0;
+#pragma unroll
+      for (int v = 0; v <= D; ++v) p += a.p0[cn[v]] * Q5<D>::lam(lane, v);
+      s.p0q[wid][lane] = p;
+    }
+    const int ta = lane / D, ti = lane - ta * D;
+    const bool active = lane < NL * D;
+    double acc = 0.0;
+    // ---- state ui: + (ui, v) - dt/rho theta R(ui)
+    mom_phase_a<D>(s, wid, lane, cn, a.ui, glam, true, a.theta != 0.0);
+    if (active) {
+      for (int q = 0; q < NQ; ++q) {
+        const double w = Q5<D>::w(q) * vol;
+        const double pa = s.phi[q][ta];
+        acc += w * pa * s.uq[wid][q][ti];
+        if (a.theta != 0.0) {
+          double ga[D], u[D], gu[D][D];
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            ga[k] = s.g[wid][q][ta][k];
+            u[k] = s.uq[wid][q][k];
+#pragma unroll
+            for (int l = 0; l < D; ++l) gu[k][l] = s.gu[wid][q][k][l];
+          }
+          acc -= cdt * a.theta * w * fb_rhs_point<D>(ti, a.rho, a.mu, pa, ga, u, gu, s.p0q[wid][q]);
+        }
+      }
+    }
+    __syncwarp();
+    // ---- state u0: - (u0, v) - dt/rho (1-theta) R(u0)
+    mom_phase_a<D>(s, wid, lane, cn, a.u0, glam, false, a.theta != 1.0);
+    if (active) {
+      for (int q = 0; q < NQ; ++q) {
+        const double w = Q5<D>::w(q) * vol;
+        const double pa = s.phi[q][ta];
+        acc -= w * pa * s.uq[wid][q][ti];
+        if (a.theta != 1.0) {
+          double ga[D], u[D], gu[D][D];
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            ga[k] = s.g[wid][q][ta][k];
+            u[k] = s.uq[wid][q][k];
+#pragma unroll
+            for (int l = 0; l < D; ++l) gu[k][l] = s.gu[wid][q][k][l];
+          }
+          acc -= cdt * (1.0 - a.theta) * w * fb_rhs_point<D>(ti, a.rho, a.mu, pa, ga, u, gu, s.p0q[wid][q]);
+        }
+      }
+      atomicAdd(&F[(int64_t)cn[ta] * D + ti], acc);
+    }
+    __syncwarp();
+  }
+}
+
+// boundary-facet part of F: -dt/rho [ -(p0 n, v)_ds + mu ((grad u)^T n, v)_ds ]  (pressure_correction.py:142-143)
+template <int D>
+__global__ void k_momentum_F_facets(int64_t nbf, const int *__restrict__ bf_cell, const int *__restrict__ bf_local,
+                                    const int *__restrict__ cell_nodes, const double *__restrict__ xyz, MomentumArgs a,
+                                    double *__restrict__ F) {
+  constexpr int NL = Elem<D>::NL2;
+  const int64_t total = nbf * NL * D;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t fidx = t / (NL * D);
+    const int r = (int)(t - fidx * NL * D);
+    const int ta = r / D, ti = r - ta * D;
+    const int64_t c = bf_cell[fidx];
+    const int f = bf_local[fidx];
+    const int *cn = cell_nodes + c * NL;
+    if (!fb_node_on_facet<D>(ta, f)) continue;
+    double glam[D + 1][D], vol;
+    cell_geometry<D>(cn, xyz, glam, vol);
+    double Ue[NL * D], p0e[D + 1];
+    for (int b = 0; b < NL; ++b) {
+      const int64_t node = cn[b];
+      for (int k = 0; k < D; ++k)
+        Ue[b * D + k] = a.theta * a.ui[node * D + k] + (1.0 - a.theta) * a.u0[node * D + k];
+    }
+    for (int v = 0; v <= D; ++v) p0e[v] = a.p0[cn[v]];
+    const double acc = fb_facet_F<D>(ta, ti, f, glam, vol, QF<D>::lam_ptr(), QF<D>::w_ptr(), QF<D>::NQ, Ue, p0e, a.mu);
+    atomicAdd(&F[(int64_t)cn[ta] * D + ti], -(a.dt / a.rho) * acc);
+  }
+}
+
+void assemble_momentum_F(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F) {
+  FB_CUDA(cudaMemsetAsync(F, 0, sizeof(double) * W.nnodes * W.dim, ctx->dev->stream));
+  const int g = grid_for(W.nc * 32, MOM_WARPS * 32, ctx->dev->sm_count * 16);
+  const int gf = grid_for(W.nbf * W.nl * W.dim, 128, ctx->dev->sm_count * 16);
+  if (W.dim == 2) {
+    FB_LAUNCH(ctx, k_momentum_F<2>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.xyz.p, a, F);
+    if (W.nbf) FB_LAUNCH(ctx, k_momentum_F_facets<2>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.xyz.p, a, F);
+  } else {
+    FB_LAUNCH(ctx, k_momentum_F<3>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.xyz.p, a, F);
+    if (W.nbf) FB_LAUNCH(ctx, k_momentum_F_facets<3>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.xyz.p, a, F);
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(MOM_WARPS * 32)
+    k_momentum_J(int64_t nc, const int *__restrict__ cell_nodes, const double *__restrict__ xyz,
+                 const int *__restrict__ rowptr, const int *__restrict__ smap, MomentumArgs a, double *__restrict__ val) {
+  constexpr int NL = Elem<D>::NL2, NQ = Q5<D>::NQ, NP = NL * NL, R = (NP + 31) / 32;
+  __shared__ MomShared<D> s;
+  mom_fill_phi<D>(s);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t warp0 = blockIdx.x * (int64_t)MOM_WARPS + wid;
+  const int64_t nwarps = (int64_t)gridDim.x * MOM_WARPS;
+  const double c1 = 0.5 * a.theta * a.dt, c2 = a.theta * a.dt * a.mu / a.rho;
+  for (int64_t c = warp0; c < nc; c += nwarps) {
+    const int *cn = cell_nodes + c * NL;
+    double glam[D + 1][D], vol;
+    cell_geometry<D>(cn, xyz, glam, vol);
+    mom_phase_a<D>(s, wid, lane, cn, a.ui, glam, true, true);
+    double acc[R][D][D];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc[r][i][j] = 0.0;
+    for (int q = 0; q < NQ; ++q) {
+      const double w = Q5<D>::w(q) * vol;
+      double u[D], gu[D][D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        u[k] = s.uq[wid][q][k];
+#pragma unroll
+        for (int l = 0; l < D; ++l) gu[k][l] = s.gu[wid][q][k][l];
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int p = lane + 32 * r;
+        if (p < NP) {
+          const int pa_i = p / NL, pb_i = p - pa_i * NL;
+          double ga[D], gb[D];
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            ga[k] = s.g[wid][q][pa_i][k];
+            gb[k] = s.g[wid][q][pb_i][k];
+          }
+          fb_jac_point<D>(w, c1, c2, s.phi[q][pa_i], s.phi[q][pb_i], ga, gb, u, gu, acc[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int p = lane + 32 * r;
+      if (p < NP) {
+        const int pa_i = p / NL;
+        const int I = cn[pa_i];
+        const int r0 = rowptr[I];
+        const int len = (rowptr[I + 1] - r0) * D;
+        const int slot = smap[c * NP + p];
+        double *base = val + (int64_t)r0 * (D * D) + (int64_t)(slot - r0) * D;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = 0; j < D; ++j) atomicAdd(base + (int64_t)i * len + j, acc[r][i][j]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// boundary-facet part of J: -theta dt/rho mu ((grad delta)^T n, v)_ds
+template <int D>
+__global__ void k_momentum_J_facets(int64_t nbf, const int *__restrict__ bf_cell, const int *__restrict__ bf_local,
+                                    const int *__restrict__ cell_nodes, const double *__restrict__ xyz,
+                                    const int *__restrict__ rowptr, const int *__restrict__ smap, MomentumArgs a,
+                                    double *__restrict__ val) {
+  constexpr int NL = Elem<D>::NL2, NP = NL * NL;
+  const int64_t total = nbf * NP;
+  const double coef = -a.theta * a.dt / a.rho * a.mu;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t fidx = t / NP;
+    const int p = (int)(t - fidx * NP);
+    const int ta = p / NL, tb = p - ta * NL;
+    const int64_t c = bf_cell[fidx];
+    const int f = bf_local[fidx];
+    const int *cn = cell_nodes + c * NL;
+    if (!fb_node_on_facet<D>(ta, f)) continue;
+    double glam[D + 1][D], vol;
+    cell_geometry<D>(cn, xyz, glam, vol);
+    double B[D][D];
+    fb_facet_J<D>(ta, tb, f, glam, vol, QF<D>::lam_ptr(), QF<D>::w_ptr(), QF<D>::NQ, B);
+    const int I = cn[ta];
+    const int r0 = rowptr[I];
+    const int len = (rowptr[I + 1] - r0) * D;
+    const int slot = smap[c * NP + p];
+    double *base = val + (int64_t)r0 * (D * D) + (int64_t)(slot - r0) * D;
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < D; ++j) atomicAdd(base + (int64_t)i * len + j, coef * B[i][j]);
+  }
+}
+
+void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *Jval) {
+  const int D = W.dim;
+  FB_CUDA(cudaMemsetAsync(Jval, 0, sizeof(double) * W.nnz * D * D, ctx->dev->stream));
+  const int g = grid_for(W.nc * 32, MOM_WARPS * 32, ctx->dev->sm_count * 16);
+  const int gf = grid_for(W.nbf * W.nl * W.nl, 128, ctx->dev->sm_count * 16);
+  if (D == 2) {
+    FB_LAUNCH(ctx, k_momentum_J<2>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
+    if (W.nbf && a.theta != 0.0)
+      FB_LAUNCH(ctx, k_momentum_J_facets<2>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.xyz.p,
+                W.rowptr.p, W.smap.p, a, Jval);
+  } else {
+    FB_LAUNCH(ctx, k_momentum_J<3>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
+    if (W.nbf && a.theta != 0.0)
+      FB_LAUNCH(ctx, k_momentum_J_facets<3>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.xyz.p,
+                W.rowptr.p, W.smap.p, a, Jval);
+  }
+}
+
+// =============================================================================
+// pressure / correction right-hand sides: one thread per cell
+// =============================================================================
+template <int D>
+__global__ void k_pressure_rhs(int64_t nc, const int *__restrict__ cell_nodes, const double *__restrict__ xyz, double dt,
+                               double rho, double mu, int rotational, const double *__restrict__ ui,
+                               const double *__restrict__ p0, double *__restrict__ b) {
+  constexpr int NL = Elem<D>::NL2;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
+    const int *cn = cell_nodes + c * NL;
+    double glam[D + 1][D], vol;
+    cell_geometry<D>(cn, xyz, glam, vol);
+    double Ue[NL * D], p0e[D + 1], be[D + 1];
+    for (int a = 0; a < NL; ++a)
+      for (int i = 0; i < D; ++i) Ue[a * D + i] = ui[(int64_t)cn[a] * D + i];
+    for (int v = 0; v <= D; ++v) p0e[v] = p0[cn[v]];
+    fb_pressure_rhs_cell<D>(glam, vol, Q2<D>::lam_ptr(), Q2<D>::w_ptr(), Q2<D>::NQ, Ue, p0e, dt, rho, mu, rotational, be);
+    for (int v = 0; v <= D; ++v) atomicAdd(&b[cn[v]], be[v]);
+  }
+}
+
+void assemble_pressure_rhs(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, double dt, double rho, double mu,
+                           int rotational, const double *ui, const double *p0, double *b) {
+  FB_CUDA(cudaMemsetAsync(b, 0, sizeof(double) * P.nnodes, ctx->dev->stream));
+  const int g = grid_for(W.nc, 128, ctx->dev->sm_count * 32);
+  if (W.dim == 2)
+    FB_LAUNCH(ctx, k_pressure_rhs<2>, g, 128, 0, W.nc, W.cell_nodes.p, W.xyz.p, dt, rho, mu, rotational, ui, p0, b);
+  else
+    FB_LAUNCH(ctx, k_pressure_rhs<3>, g, 128, 0, W.nc, W.cell_nodes.p, W.xyz.p, dt, rho, mu, rotational, ui, p0, b);
+}
+
+template <int D>
+__global__ void k_correction_grad(int64_t nc, const int *__restrict__ cell_nodes, const double *__restrict__ xyz,
+                                  double dt, double rho, double mu, int rotational, const double *__restrict__ ui,
+                                  const double *__restrict__ p1, const double *__restrict__ p0, double *__restrict__ b) {
+  constexpr int NL = Elem<D>::NL2;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
+    const int *cn = cell_nodes + c * NL;
+    double glam[D + 1][D], vol;
+    cell_geometry<D>(cn, xyz, glam, vol);
+    double Ue[NL * D], dpe[D + 1], gphi[D];
+    if (rotational)
+      for (int a = 0; a < NL; ++a)
+        for (int i = 0; i < D; ++i) Ue[a * D + i] = ui[(int64_t)cn[a] * D + i];
+    for (int v = 0; v <= D; ++v) dpe[v] = p1[cn[v]] - p0[cn[v]];
+    fb_correction_gradphi<D>(glam, Ue, dpe, mu, rotational, gphi);
+    const double coef = -dt / rho * vol;
+    for (int a = 0; a < NL; ++a) {
+      const double m = coef * fb_p2_mean<D>(a);
+      if (m != 0.0)
+        for (int k = 0; k < D; ++k) atomicAdd(&b[(int64_t)cn[a] * D + k], m * gphi[k]);
+    }
+  }
+}
+
+void assemble_correction_grad(fb_ctx *ctx, const DevSpace &W, double dt, double rho, double mu, int rotational,
+                              const double *ui, const double *p1, const double *p0, double *b) {
+  const int g = grid_for(W.nc, 128, ctx->dev->sm_count * 32);
+  if (W.dim == 2)
+    FB_LAUNCH(ctx, k_correction_grad<2>, g, 128, 0, W.nc, W.cell_nodes.p, W.xyz.p, dt, rho, mu, rotational, ui, p1, p0, b);
+  else
+    FB_LAUNCH(ctx, k_correction_grad<3>, g, 128, 0, W.nc, W.cell_nodes.p, W.xyz.p, dt, rho, mu, rotational, ui, p1, p0, b);
+}
+
+// =============================================================================
+// heat operator (heat.py:54-58): one thread per (cell, a, b)
+// =============================================================================
+template <int D, int DEG>
+__global__ void k_heat(int64_t nc, const int *__restrict__ cell_nodes, const int *__restrict__ wcell_nodes,
+                       const double *__restrict__ xyz, const int *__restrict__ smap, const double *__restrict__ conv,
+                       double kdiff, double *__restrict__ val) {
+  constexpr int NL = DEG == 1 ? Elem<D>::NL1 : Elem<D>::NL2;
+  constexpr int NLW = Elem<D>::NL2;
+  const int64_t total = nc * NL * NL;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = t / (NL * NL);
+    const int r = (int)(t - c * NL * NL);
+    const int a = r / NL, b = r - a * NL;
+    const int *cn = cell_nodes + c * NL;
+    double glam[D + 1][D], vol;
+    cell_geometry<D>(cn, xyz, glam, vol);
+    double e = 0.0;
+    for (int q = 0; q < Q5<D>::NQ; ++q) {
+      double lam[D + 1], ga[D], gb[D];
+      for (int m = 0; m <= D; ++m) lam[m] = Q5<D>::lam(q, m);
+      double pa;
+      if (DEG == 1) {
+        pa = lam[a];
+        for (int k = 0; k < D; ++k) {
+          ga[k] = glam[a][k];
+          gb[k] = glam[b][k];
+        }
+      } else {
+        pa = fb_p2_phi<D>(a, lam);
+        fb_p2_grad<D>(a, lam, glam, ga);
+        fb_p2_grad<D>(b, lam, glam, gb);
+      }
+      double s = 0.0;
+      for (int k = 0; k < D; ++k) s -= kdiff * ga[k] * gb[k];
+      if (conv) {
+        const int *wn = wcell_nodes + c * NLW;
+        double cg = 0.0;
+        for (int n = 0; n < NLW; ++n) {
+          const double pn = fb_p2_phi<D>(n, lam);
+          for (int k = 0; k < D; ++k) cg += pn * conv[(int64_t)wn[n] * D + k] * gb[k];
+        }
+        s -= cg * pa;
+      }
+      e += Q5<D>::w(q) * s;
+    }
+    atomicAdd(&val[smap[t]], e * vol);
+  }
+}
+
+void assemble_heat(fb_ctx *ctx, const DevSpace &V, const DevSpace *W, const double *conv, double kdiff, double *val) {
+  FB_CUDA(cudaMemsetAsync(val, 0, sizeof(double) * V.nnz, ctx->dev->stream));
+  const int g = grid_for(V.nc * V.nl * V.nl, 128, ctx->dev->sm_count * 32);
+  const int *wcn = W ? W->cell_nodes.p : nullptr;
+  if (!W) conv = nullptr;
+#define FB_HT(D, DEG) \
+  FB_LAUNCH(ctx, (k_heat<D, DEG>), g, 128, 0, V.nc, V.cell_nodes.p, wcn, V.xyz.p, V.smap.p, conv, kdiff, val)
+  if (V.dim == 2 && V.degree == 1) FB_HT(2, 1);
+  else if (V.dim == 2) FB_HT(2, 2);
+  else if (V.degree == 1) FB_HT(3, 1);
+  else FB_HT(3, 2);
+#undef FB_HT
+}
+
+// =============================================================================
+// Stokes divergence block, matrix-free (stokes.py:40-42):  (B u)_a = -int psi_a div u,  (B^T p)_(b,j) = -int p d_j phi_b
+// =============================================================================
+template <int D, int TRANSPOSE>
+__global__ void k_stokes_div(int64_t nc, const int *__restrict__ cell_nodes, const double *__restrict__ xyz,
+                             const double *__restrict__ in, double *__restrict__ out) {
+  constexpr int NL = Elem<D>::NL2;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
+    const int *cn = cell_nodes + c * NL;
+    double glam[D + 1][D], vol;
+    cell_geometry<D>(cn, xyz, glam, vol);
+    if (!TRANSPOSE) {
+      double be[D + 1];
+      for (int v = 0; v <= D; ++v) be[v] = 0.0;
+      for (int q = 0; q < Q2<D>::NQ; ++q) {
+        double lam[D + 1];
+        for (int m = 0; m <= D; ++m) lam[m] = Q2<D>::lam(q, m);
+        double div = 0.0;
+        for (int a = 0; a < NL; ++a) {
+          double g[D];
+          fb_p2_grad<D>(a, lam, glam, g);
+          for (int i = 0; i < D; ++i) div += in[(int64_t)cn[a] * D + i] * g[i];
+        }
+        for (int v = 0; v <= D; ++v) be[v] -= Q2<D>::w(q) * vol * div * lam[v];
+      }
+      for (int v = 0; v <= D; ++v) atomicAdd(&out[cn[v]], be[v]);
+    } else {
+      for (int q = 0; q < Q2<D>::NQ; ++q) {
+        double lam[D + 1];
+        for (int m = 0; m <= D; ++m) lam[m] = Q2<D>::lam(q, m);
+        double p = 0.0;
+        for (int v = 0; v <= D; ++v) p += in[cn[v]] * lam[v];
+        const double w = -Q2<D>::w(q) * vol * p;
+        for (int a = 0; a < NL; ++a) {
+          double g[D];
+          fb_p2_grad<D>(a, lam, glam, g);
+          for (int i = 0; i < D; ++i) atomicAdd(&out[(int64_t)cn[a] * D + i], w * g[i]);
+        }
+      }
+    }
+  }
+}
+
+void stokes_div(fb_ctx *ctx, const DevSpace &W, const double *u, double *out_p) {
+  const int g = grid_for(W.nc, 128, ctx->dev->sm_count * 32);
+  if (W.dim == 2)
+    FB_LAUNCH(ctx, (k_stokes_div<2, 0>), g, 128, 0, W.nc, W.cell_nodes.p, W.xyz.p, u, out_p);
+  else
+    FB_LAUNCH(ctx, (k_stokes_div<3, 0>), g, 128, 0, W.nc, W.cell_nodes.p, W.xyz.p, u, out_p);
+}
+void stokes_grad(fb_ctx *ctx, const DevSpace &W, const double *p, double *out_u) {
+  const int g = grid_for(W.nc, 128, ctx->dev->sm_count * 32);
+  if (W.dim == 2)
+    FB_LAUNCH(ctx, (k_stokes_div<2, 1>), g, 128, 0, W.nc, W.cell_nodes.p, W.xyz.p, p, out_u);
+  else
+    FB_LAUNCH(ctx, (k_stokes_div<3, 1>), g, 128, 0, W.nc, W.cell_nodes.p, W.xyz.p, p, out_u);
+}

@@ -1,0 +1,106 @@
+// Host-callable launchers of the CUDA kernels in fb_kernels.cu / fb_krylov.cu.
+#pragma once
+#include "fb_device.cuh"
+
+// Device copy of a node space: dof map, node-level CSR pattern, element->slot scatter map.
+struct DevSpace {
+  fb_ctx *ctx = nullptr;
+  int dim = 0, nl = 0, degree = 0;
+  int64_t nnodes = 0, nc = 0, nnz = 0, nbf = 0;
+  DBuf<double> xyz;         // vertex coordinates (mesh.nv * dim)
+  DBuf<int> cell_nodes;     // nc * nl
+  DBuf<int> rowptr;         // nnodes + 1
+  DBuf<int> col;            // nnz
+  DBuf<int> diag;           // nnodes: slot of the diagonal entry
+  DBuf<int> smap;           // nc * nl * nl: CSR slot of (node_a, node_b)
+  DBuf<int> bf_cell, bf_local;
+};
+
+struct fb_mat {
+  fb_ctx *ctx = nullptr;
+  DevSpace *sp = nullptr;  // pattern owner (not owned)
+  int block = 1;           // 1: scalar node matrix; D: D x D blocks stored row-planar
+  DBuf<double> val;        // nnz * block * block
+  bool owned_space = false;
+};
+
+// Linear operator view handed to SpMV / Krylov
+struct LinOp {
+  int block = 1;   // 1 or D
+  int ncomp = 1;   // interleaved components sharing a scalar matrix (block == 1)
+  int64_t nrows = 0;  // node rows
+  const int *rowptr = nullptr;
+  const int *col = nullptr;
+  const double *val = nullptr;
+  const uint8_t *mask = nullptr;  // per dof: 1 -> identity row (Dirichlet); may be null
+  int64_t ndofs() const { return nrows * (block > 1 ? block : ncomp); }
+  int dofs_per_node() const { return block > 1 ? block : ncomp; }
+};
+
+LinOp make_linop(const fb_mat &m, int ncomp, const uint8_t *mask);
+
+// ---- setup
+void dev_space_build(fb_space *s, DevSpace &d);
+// kind: 0 P1/P2 stiffness, 1 mass
+void assemble_constant(fb_ctx *ctx, DevSpace &sp, int kind, double *val);
+void assemble_lumped(fb_ctx *ctx, DevSpace &sp, double *diag);
+
+// ---- SpMV: y = A x; dot_mode 0 none, 1: red[slot] = w.y, 2: red[slot] = w.y and red[slot+1] = y.y
+void spmv(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_mode = 0, const double *w = nullptr,
+          int slot = 0, const int *flag = nullptr);
+
+// ---- vector kernels
+void vec_fill(fb_ctx *ctx, double *x, double a, int64_t n);
+void vec_axpy(fb_ctx *ctx, double *y, double a, const double *x, int64_t n);          // y += a x
+void vec_axpby(fb_ctx *ctx, double *z, double a, const double *x, double b, const double *y, int64_t n);  // z = a x + b y
+void vec_dot(fb_ctx *ctx, const double *x, const double *y, int64_t n, int slot);     // red[slot] = x.y
+double vec_norm2_sync(fb_ctx *ctx, const double *x, int64_t n);                       // host-synchronous
+void mask_build(fb_ctx *ctx, uint8_t *mask, int64_t ndofs, const int64_t *dofs, int64_t nbc);
+void vec_set_at(fb_ctx *ctx, double *x, const int64_t *dofs, const double *vals, int64_t nbc);   // x[dofs] = vals
+void vec_zero_at(fb_ctx *ctx, double *x, const int64_t *dofs, int64_t nbc);
+void vec_copy_at(fb_ctx *ctx, double *dst, const double *src, const int64_t *dofs, int64_t nbc);
+void lift_identity_rows(fb_ctx *ctx, const LinOp &A, double *b, const int64_t *dofs, int64_t nbc, double *xg, double *tmp);
+void bc_residual(fb_ctx *ctx, double *F, const double *x, const int64_t *dofs, const double *vals, int64_t nbc);
+
+// ---- Dirichlet on matrices
+void bc_rows_identity_blocked(fb_ctx *ctx, const DevSpace &sp, int D, double *val, const int64_t *dofs, int64_t nbc);
+void bc_symmetric_scalar(fb_ctx *ctx, const DevSpace &sp, double *val, const uint8_t *mask);
+void bc_rows_identity_scalar(fb_ctx *ctx, const DevSpace &sp, double *val, const uint8_t *mask);
+
+// ---- preconditioners: inverse diagonal (block == 1: per node, replicated over comps by the caller's kernels)
+void jacobi_setup_scalar(fb_ctx *ctx, const DevSpace &sp, const double *val, int ncomp, const uint8_t *mask, double *dinv);
+// D x D inverse diagonal blocks (block_mode 0: point Jacobi stored as diagonal blocks, 1: full block inverse)
+void jacobi_setup_blocked(fb_ctx *ctx, const DevSpace &sp, int D, const double *val, int block_mode, double *binv);
+
+// ---- Navier-Stokes element kernels (D = dim of W)
+struct MomentumArgs {
+  double dt, rho, mu, theta;
+  const double *ui, *u0, *p0;
+};
+void assemble_momentum_F(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F);
+void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *Jval);
+void assemble_pressure_rhs(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, double dt, double rho, double mu,
+                           int rotational, const double *ui, const double *p0, double *b);
+// adds -dt/rho (grad phi, v) to b (which already holds M ui)
+void assemble_correction_grad(fb_ctx *ctx, const DevSpace &W, double dt, double rho, double mu, int rotational,
+                              const double *ui, const double *p1, const double *p0, double *b);
+// heat operator A (heat.py:54-58): -(kappa/rho_cp) grad u.grad v - (conv.grad u) v on V's pattern
+void assemble_heat(fb_ctx *ctx, const DevSpace &V, const DevSpace *W, const double *conv, double kdiff, double *val);
+// B x and B^T y for the divergence block of stokes.py:40-42 (matrix-free)
+void stokes_div(fb_ctx *ctx, const DevSpace &W, const double *u, double *out_p);
+void stokes_grad(fb_ctx *ctx, const DevSpace &W, const double *p, double *out_u);
+
+// ---- Krylov (fb_krylov.cu).  All vectors are device pointers; return FB_OK / FB_ENOCONV_KRYLOV / FB_ENAN.
+struct KrylovWork {
+  DBuf<double> v[10];
+  void ensure(int count, int64_t n) {
+    for (int i = 0; i < count; ++i) v[i].alloc((size_t)n);
+  }
+};
+// Jacobi-PCG, stopping test ||M^-1 r|| <= rtol * ref  (ref <= 0: ref = ||M^-1 b||)
+int krylov_pcg(fb_ctx *ctx, const LinOp &A, const double *dinv, const double *b, double *x, double rtol, double ref_extra2,
+               int maxit, int check_every, KrylovWork &w, int *iters);
+// right-preconditioned BiCGStab with D x D block inverse (A.block > 1) or diagonal dinv (A.block == 1);
+// stops when ||r||_2 <= atol
+int krylov_bicgstab(fb_ctx *ctx, const LinOp &A, const double *minv, const double *b, double *x, double atol, int maxit,
+                    int check_every, KrylovWork &w, int *iters);

@@ -1,0 +1,186 @@
+/* flowb200.h -- C ABI of libflowb200.so, the B200-native engine behind flow's
+ * time-stepping hot path.
+ *
+ * The reference (nschloe/flow) has no FFI of its own: its boundary to native
+ * code is DOLFIN's Python API.  Each entry point below
+ * names the reference call it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - every function returns an int status (FB_OK == 0); nothing throws or aborts
+ *     across the ABI; fb_last_error(ctx) holds a message for the last failure.
+ *   - the caller owns every input/output array (plain host buffers unless
+ *     FB_DEVICE_PTRS is passed); the library owns handles and all device memory.
+ *   - numbering is the canonical one (oracle/fem.py): vertex nodes in vertex
+ *     order, then edge nodes in lexicographic (min,max) order; vector dofs are
+ *     interleaved, dof = ncomp*node + comp.
+ *   - a context created with device = -1 is host-only: mesh / space / pattern
+ *     queries work, every compute entry point returns FB_ENODEVICE.  There is no
+ *     CPU compute path in this library.
+ */
+#ifndef FLOWB200_H
+#define FLOWB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fb_ctx fb_ctx;
+typedef struct fb_mesh fb_mesh;
+typedef struct fb_space fb_space;
+typedef struct fb_mat fb_mat;
+typedef struct fb_ns fb_ns;
+typedef struct fb_heat fb_heat;
+
+enum fb_status {
+  FB_OK = 0,
+  FB_EINVAL = 1,         /* asserts at pressure_correction.py:488-489, stokes.py:23 */
+  FB_ENOCONV_NEWTON = 2, /* error_on_nonconvergence, pressure_correction.py:236 */
+  FB_ENOCONV_KRYLOV = 3, /* pressure_correction.py:337,424,462; stokes.py:139 */
+  FB_ENAN = 4,
+  FB_ECUDA = 5,
+  FB_ENCCL = 6,
+  FB_ENOMEM = 7,
+  FB_ENODEVICE = 8
+};
+
+enum fb_scheme { FB_FORWARD_EULER = 0, FB_BACKWARD_EULER = 1, FB_CRANK_NICOLSON = 2 };
+enum fb_flags { FB_DEVICE_PTRS = 1, FB_ROTATIONAL = 2, FB_CHORIN = 4 };
+enum fb_forcing { FB_F_NONE = 0, FB_F_CONSTANT = 1, FB_F_NODAL = 2, FB_F_LOAD = 3 };
+enum fb_krylov { FB_BICGSTAB = 0, FB_GMRES = 1, FB_CG = 2 };
+enum fb_precond { FB_JACOBI = 0, FB_BLOCK_JACOBI = 1, FB_CHEBYSHEV = 2 };
+
+/* ---- context ---------------------------------------------------------- */
+int fb_version(void);
+int fb_ctx_create(int device, fb_ctx **out);
+int fb_ctx_destroy(fb_ctx *ctx);
+const char *fb_last_error(fb_ctx *ctx);
+const char *fb_status_string(int status);
+/* number of kernels this context has launched so far (bench.py gpu_launches) */
+int fb_ctx_launch_count(fb_ctx *ctx, int64_t *count);
+/* CUDA-event stopwatch on the context's own stream (the stream every kernel is launched on) */
+int fb_ctx_timer_start(fb_ctx *ctx);
+int fb_ctx_timer_stop(fb_ctx *ctx, double *ms);
+
+/* ---- mesh: replaces dolfin.Mesh / UnitSquareMesh / RectangleMesh / BoxMesh
+ * (tests/test_navier_stokes.py:82,144,176; tests/test_sealed_box.py:53).
+ * cells: ncells*(gdim+1) vertex indices; they are sorted per cell (UFC order). */
+int fb_mesh_create(fb_ctx *ctx, int gdim, int64_t nverts, const double *xyz, int64_t ncells,
+                   const int32_t *cells, fb_mesh **out);
+int fb_mesh_destroy(fb_mesh *mesh);
+int fb_mesh_info(fb_mesh *mesh, int64_t *nverts, int64_t *ncells, int64_t *nedges, int64_t *nbfacets);
+int fb_mesh_cells(fb_mesh *mesh, const int32_t **cells);
+int fb_mesh_edges(fb_mesh *mesh, const int32_t **edges);
+int fb_mesh_boundary_facets(fb_mesh *mesh, const int32_t **cell, const int32_t **local_facet);
+
+/* ---- function space: replaces FunctionSpace / VectorFunctionSpace and their dof maps
+ * (tests/test_navier_stokes.py:282-283; tests/test_sealed_box.py:59-61). degree in {1,2}. */
+int fb_space_create(fb_mesh *mesh, int degree, int ncomp, fb_space **out);
+int fb_space_destroy(fb_space *space);
+int fb_space_info(fb_space *space, int64_t *nnodes, int64_t *ndofs, int *nodes_per_cell);
+int fb_space_dofmap(fb_space *space, const int32_t **cell_nodes);
+int fb_space_node_coords(fb_space *space, const double **xyz);
+int fb_space_boundary_nodes(fb_space *space, const uint8_t **flags);
+/* node-level CSR sparsity pattern (columns ascending) -- the pattern of assemble() */
+int fb_space_pattern(fb_space *space, int64_t *nnz, const int64_t **indptr, const int32_t **indices);
+
+/* ---- assembled operators: replaces dolfin.assemble(a) for the constant forms
+ * u*v*dx (pressure_correction.py:442) and dot(grad p, grad q)*dx (:317), plus
+ * the vertex-quadrature mass of heat.py:39-45. */
+int fb_assemble_mass(fb_space *space, fb_mat **out);
+int fb_assemble_stiffness(fb_space *space, fb_mat **out);
+int fb_assemble_lumped_mass(fb_space *space, double *diag_out);
+int fb_mat_destroy(fb_mat *mat);
+/* block = 1: scalar node matrix; block = d: d x d blocks (momentum Jacobian).
+ * values_out (caller-allocated, nnz*block*block doubles) receives scalar-CSR
+ * values of the interleaved system, row-major within each block row. */
+int fb_mat_info(fb_mat *mat, int64_t *nrows, int64_t *nnz_blocks, int *block);
+int fb_mat_values(fb_mat *mat, double *values_out);
+/* y = A x for `ncomp` interleaved components sharing a scalar matrix (block==1),
+ * or the blocked product (block==d, ncomp ignored). Host buffers. */
+int fb_mat_spmv(fb_mat *mat, int ncomp, const double *x, double *y);
+/* Jacobi-PCG on a scalar SPD matrix applied to ncomp interleaved components with
+ * symmetric Dirichlet elimination: replaces solve(a==L, bcs, 'cg', symmetric=True)
+ * (pressure_correction.py:451-464) and project() in the tests. */
+int fb_mat_solve_cg(fb_mat *mat, int ncomp, const double *b, double *x, int64_t nbc, const int64_t *bc_dofs,
+                    const double *bc_vals, double rtol, int maxit, int *iterations);
+/* SpMV micro-benchmark on resident data: runs `reps` products, returns avg ms and algorithmic bytes */
+int fb_mat_bench_spmv(fb_mat *mat, int ncomp, int reps, double *ms_avg, double *bytes);
+
+/* ---- Navier-Stokes pressure-correction step: replaces _step
+ * (pressure_correction.py:468-518) = _compute_tentative_velocity (:147-255) +
+ * _compute_pressure (:258-433) + _compute_velocity_correction (:436-465). */
+typedef struct fb_ns_opts {
+  int momentum_solver;   /* fb_krylov: FB_BICGSTAB (default) or FB_GMRES */
+  int momentum_precond;  /* FB_JACOBI or FB_BLOCK_JACOBI (default) */
+  int pressure_precond;  /* FB_JACOBI (default) or FB_CHEBYSHEV */
+  int newton_maxit;      /* 10, pressure_correction.py:232 */
+  double newton_atol;    /* 1e-10, pressure_correction.py:499 */
+  double momentum_rtol;  /* inner Krylov tolerance relative to |F| (inexact Newton), default 1e-6 */
+  int momentum_maxit;    /* 1000 (commented-out block, pressure_correction.py:249) */
+  int pressure_maxit;    /* Krylov cap for the Poisson solve; default 20000 (Jacobi needs more than AMG's 1000) */
+  int correction_maxit;  /* default 1000 */
+  int gmres_restart;     /* 30 (PETSc default) */
+  int check_every;       /* Krylov iterations enqueued between host convergence checks */
+  int chebyshev_degree;  /* default 4 */
+  int reserved[8];
+} fb_ns_opts;
+
+typedef struct fb_ns_stats {
+  int newton_its;
+  int momentum_its; /* total Krylov iterations over all Newton steps */
+  int pressure_its;
+  int correction_its;
+  double newton_residual;
+  double ms_tentative, ms_pressure, ms_correction, ms_total; /* CUDA-event times */
+  double ms_assembly_J, ms_assembly_F, ms_momentum_solve;
+  int64_t launches;
+  double reserved[8];
+} fb_ns_stats;
+
+int fb_ns_opts_default(fb_ns_opts *opts);
+/* W: vector P2 space (ncomp == gdim), P: scalar P1 space on the same mesh. */
+int fb_ns_create(fb_space *W, fb_space *P, const fb_ns_opts *opts, fb_ns **out);
+int fb_ns_destroy(fb_ns *ns);
+/* One step.  scheme: fb_scheme; flags: FB_ROTATIONAL | FB_CHORIN | FB_DEVICE_PTRS.
+ * forcing: fb_forcing; f0/f1 = f at t_n / t_{n+1}: gdim doubles (CONSTANT), ndofs(W)
+ * doubles of nodal values (NODAL) or of the load vector int f.v dx (LOAD); NULL == 0.
+ * u_bc / p_bc: Dirichlet dofs + values (DirichletBC already evaluated at dof coordinates).
+ * tol: the reference's `tol` argument (Krylov rtol of the Poisson and correction solves). */
+int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flags, const double *u0, const double *p0,
+               int forcing, const double *f0, const double *f1, int64_t n_ubc, const int64_t *ubc_dofs,
+               const double *ubc_vals, int64_t n_pbc, const int64_t *pbc_dofs, const double *pbc_vals, double tol,
+               double *u1, double *p1, fb_ns_stats *stats);
+/* parity/debug: F1(ui) (and J if want_J) of pressure_correction.py:169-202 without BCs.
+ * theta = 0, 1, 0.5; load = time-weighted load vector or NULL. */
+int fb_ns_residual(fb_ns *ns, double dt, double rho, double mu, double theta, const double *ui, const double *u0,
+                   const double *p0, const double *load, double *F_out, int want_J);
+/* which: 0 = P1 stiffness, 1 = scalar P2 mass, 2 = last momentum Jacobian (borrowed handles) */
+int fb_ns_matrix(fb_ns *ns, int which, fb_mat **out);
+/* parity/debug: right-hand sides L2 (pressure_correction.py:318-323) and L3 (:448-449) */
+int fb_ns_pressure_rhs(fb_ns *ns, double dt, double rho, double mu, int rotational, const double *ui, const double *p0,
+                       double *b_out);
+int fb_ns_correction_rhs(fb_ns *ns, double dt, double rho, double mu, int rotational, const double *ui,
+                         const double *p1, const double *p0, double *b_out);
+
+/* ---- heat: replaces flow.heat.Heat (heat.py:20-122).  V scalar P1/P2, W vector P2 (conv) or NULL */
+int fb_heat_create(fb_space *V, fb_space *W, const double *conv, double kappa, double rho, double cp,
+                   const double *source_load, fb_heat **out);
+int fb_heat_destroy(fb_heat *heat);
+/* alpha*M*u + beta*(A*u + b)   (heat.py:92-101) */
+int fb_heat_eval(fb_heat *heat, double alpha, double beta, const double *u, double *out);
+/* solve (alpha*M + beta*A) x = b with DirichletBC.apply rows (heat.py:103-122); b is modified like the reference does */
+int fb_heat_solve(fb_heat *heat, double alpha, double beta, double *b, int64_t nbc, const int64_t *bc_dofs,
+                  const double *bc_vals, double rtol, int maxit, double *x, int *iterations);
+int fb_heat_matrix(fb_heat *heat, int which, fb_mat **out); /* 0 = A */
+
+/* ---- Stokes: replaces flow.stokes.solve (stokes.py:13-148); mixed dofs are passed split (u, p) */
+int fb_stokes_solve(fb_space *W, fb_space *P, double mu, int forcing, const double *f, int64_t n_ubc,
+                    const int64_t *ubc_dofs, const double *ubc_vals, int64_t n_pbc, const int64_t *pbc_dofs,
+                    const double *pbc_vals, double tol, int maxit, double *u, double *p, int *iterations);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWB200_H */

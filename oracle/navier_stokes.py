@@ -19,8 +19,9 @@ class Stepper:
 
     order = {"velocity": 2.0, "pressure": 1.0}
 
-    def __init__(self, mesh, time_step_method="backward euler", rotational=False, chorin=False):
+    def __init__(self, mesh, time_step_method="backward euler", rotational=False, chorin=False, linear="lu"):
         self.mesh = mesh
+        self.linear = linear  # "lu": the reference's Newton+LU; "krylov": C/OpenMP Jacobi-Krylov (CPU timing)
         self.W = fem.Space(mesh, 2, mesh.dim)
         self.P = fem.Space(mesh, 1, 1)
         self.Wn = fem.Space(mesh, 2, 1)
@@ -47,7 +48,8 @@ class Stepper:
                 self.W, self.P, x, u0, p0, load, dt, rho, mu, theta, want_J=want_J
             )
 
-        ui, its = solvers.newton(rj, u0, dofs, vals, atol=tol, maxit=10, report=self.info)
+        newton = solvers.newton if self.linear == "lu" else solvers.newton_krylov
+        ui, its = newton(rj, u0, dofs, vals, atol=tol, maxit=10, report=self.info)
         self.info["newton_its"] = its
         return ui
 
@@ -58,7 +60,8 @@ class Stepper:
             A, b = forms.apply_bc_symmetric(self.A_p, b, p_bc[0], p_bc[1])
             p1, its = solvers.pcg(A, b, tol, 100 * 50)  # reference: maxit 100 with AMG
         else:
-            p1, its = solvers.pcg(self.A_p, b, tol, 1000 * 50)  # reference: maxit 1000 with AMG
+            cg = solvers.pcg if self.linear == "lu" else solvers.c_pcg
+            p1, its = cg(self.A_p, b, tol, 1000 * 50)  # reference: maxit 1000 with AMG
         self.info["pressure_its"] = its
         return p1
 
@@ -66,7 +69,8 @@ class Stepper:
     def velocity_correction(self, ui, p1, p0, u_bc, rho, mu, dt, tol):
         b = forms.correction_rhs(self.W, self.P, ui, p1, p0, dt, rho, mu, self.rotational)
         A, b = forms.apply_bc_symmetric(self.M_vec, b, u_bc[0], u_bc[1])
-        u1, its = solvers.pcg(A, b, tol, 100 * 50)
+        cg = solvers.pcg if self.linear == "lu" else solvers.c_pcg
+        u1, its = cg(A, b, tol, 100 * 50)
         self.info["correction_its"] = its
         return u1
 
@@ -88,8 +92,8 @@ def Chorin(mesh):
     return s
 
 
-def IPCS(mesh, time_step_method="backward euler"):
-    s = Stepper(mesh, time_step_method, rotational=False)
+def IPCS(mesh, time_step_method="backward euler", linear="lu"):
+    s = Stepper(mesh, time_step_method, rotational=False, linear=linear)
     s.order = {"velocity": 2.0, "pressure": 1.0}
     return s
 

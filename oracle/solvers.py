@@ -78,3 +78,104 @@ def newton(residual_jacobian, x0, bc_dofs, bc_vals, atol=1e-10, maxit=10, report
     if report is not None:
         report["newton_residuals"] = hist
     return x, its
+
+
+# ---- "Krylov CPU" variant: the same algorithm the GPU path runs,
+# ---- on the host cores through oracle/_cbaseline.so (C + OpenMP).  Used for CPU timing only.
+_cb = None
+
+
+def cbaseline():
+    global _cb
+    if _cb is None:
+        import ctypes as C
+        import os
+
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_cbaseline.so")
+        lib = C.CDLL(path)
+        pd, pi64, pi32 = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+        lib.cb_pcg.argtypes = [C.c_int64, pi64, pi32, pd, pd, pd, pd, C.c_double, C.c_int]
+        lib.cb_bicgstab.argtypes = [C.c_int64, pi64, pi32, pd, pd, pd, pd, C.c_double, C.c_int]
+        lib.cb_spmv.argtypes = [C.c_int64, pi64, pi32, pd, pd, pd]
+        lib.cb_spmv.restype = None
+        _cb = lib
+    return _cb
+
+
+def _csr_args(A):
+    import ctypes as C
+
+    A = sp.csr_matrix(A)
+    indptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(A.indices, dtype=np.int32)
+    data = np.ascontiguousarray(A.data, dtype=np.float64)
+    keep = (indptr, indices, data)
+    return keep, (A.shape[0], indptr.ctypes.data_as(C.POINTER(C.c_int64)), indices.ctypes.data_as(C.POINTER(C.c_int32)),
+                  data.ctypes.data_as(C.POINTER(C.c_double)))
+
+
+def c_pcg(A, b, rtol, maxit):
+    import ctypes as C
+
+    pd = C.POINTER(C.c_double)
+    keep, args = _csr_args(A)
+    dinv = np.ascontiguousarray(1.0 / A.diagonal())
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros_like(b)
+    its = cbaseline().cb_pcg(*args, dinv.ctypes.data_as(pd), b.ctypes.data_as(pd), x.ctypes.data_as(pd), rtol, maxit)
+    if its < 0:
+        raise ConvergenceError("CG did not converge in %d iterations" % maxit)
+    return x, its
+
+
+def c_bicgstab(A, b, atol, maxit):
+    import ctypes as C
+
+    pd = C.POINTER(C.c_double)
+    keep, args = _csr_args(A)
+    dinv = np.ascontiguousarray(1.0 / A.diagonal())
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros_like(b)
+    its = cbaseline().cb_bicgstab(*args, dinv.ctypes.data_as(pd), b.ctypes.data_as(pd), x.ctypes.data_as(pd), atol, maxit)
+    if its < 0:
+        raise ConvergenceError("BiCGStab did not converge in %d iterations" % maxit)
+    return x, its
+
+
+def newton_krylov(residual_jacobian, x0, bc_dofs, bc_vals, atol=1e-10, maxit=10, report=None):
+    """Same Newton loop as `newton`, linear solves by Jacobi-BiCGStab to 0.1*atol (the GPU path's setting)."""
+    x = x0.copy()
+
+    def eval_F(want_J):
+        F, J = residual_jacobian(x, want_J)
+        F = F.copy()
+        F[bc_dofs] = x[bc_dofs] - bc_vals
+        return F, J
+
+    F, _ = eval_F(False)
+    r = np.linalg.norm(F)
+    its = 0
+    kits = 0
+    while r >= atol:
+        if its >= maxit:
+            raise ConvergenceError("Newton solver did not converge (|F| = %g)" % r)
+        _, J = eval_F(True)
+        mask = np.zeros(x.size, bool)
+        mask[bc_dofs] = True
+        keep = sp.diags((~mask).astype(float))
+        J = (keep @ J + sp.diags(mask.astype(float))).tocsr()
+        # lift the Dirichlet dofs (their update is known exactly); BiCGStab breaks down otherwise
+        dg = np.zeros_like(F)
+        dg[bc_dofs] = F[bc_dofs]
+        b = F - J @ dg
+        b[bc_dofs] = 0.0
+        dx, k = c_bicgstab(J, b, 0.1 * atol, 1000)
+        dx += dg
+        kits += k
+        x -= dx
+        its += 1
+        F, _ = eval_F(False)
+        r = np.linalg.norm(F)
+    if report is not None:
+        report["momentum_its"] = kits
+    return x, its

@@ -1,0 +1,83 @@
+"""Host-side facade logic: Expression parsing, Dirichlet sets, sub-spaces, the numpy data-entry
+helpers (vs the oracle's independent implementations)."""
+import numpy as np
+import pytest
+
+from oracle import fem, forms, util
+
+
+def test_expression_cstring_and_parameters():
+    from flow_b200 import dolfin as d
+
+    e = d.Expression(("sin(x[0] + t)*pow(x[1], 2)", "mu*cos(pi*x[0])"), degree=5, t=0.0, mu=2.0)
+    X = np.array([[0.1, 0.2], [0.3, 0.4]])
+    assert np.allclose(e(X), np.stack([np.sin(X[:, 0]) * X[:, 1] ** 2, 2 * np.cos(np.pi * X[:, 0])], 1))
+    e.t = 0.5
+    assert np.allclose(e(X)[:, 0], np.sin(X[:, 0] + 0.5) * X[:, 1] ** 2)
+    assert e.user_parameters["t"] == 0.5 and e.degree() == 5
+    s = d.Expression("x[0]*x[1]", degree=2)
+    assert s(X).shape == (2,)
+
+
+def test_dirichlet_sets_and_merge():
+    from flow_b200 import dolfin as d
+
+    m = d.UnitSquareMesh(4, 4)
+    W = d.VectorFunctionSpace(m, "CG", 2)
+    om = fem.Mesh(*fem.unit_square_mesh(4, 4))
+    Wo = fem.Space(om, 2, 2)
+    dofs, vals = d.collect_bcs([d.DirichletBC(W, (1.0, 2.0), "on_boundary")], W)
+    assert np.array_equal(dofs, Wo.boundary_dofs())
+    assert np.allclose(vals.reshape(-1, 2), [1.0, 2.0])
+    left = d.DirichletBC(W.sub(0), d.Expression("x[1]", degree=1), lambda x, on: on and x[0] < 1e-12)
+
+    class Top(d.SubDomain):
+        def inside(self, x, on_boundary):
+            return on_boundary and x[1] > 1 - 1e-12
+
+    top = d.DirichletBC(W, d.Constant((3.0, 4.0)), Top())
+    dofs, vals = d.collect_bcs([left, top], W)
+    assert len(np.unique(dofs)) == dofs.size and (np.diff(dofs) > 0).all()
+    X = W.tabulate_dof_coordinates()
+    for k, v in zip(dofs, vals):
+        if X[k, 1] > 1 - 1e-12:
+            assert v == (3.0 if k % 2 == 0 else 4.0)  # later BC wins at the corner
+        else:
+            assert k % 2 == 0 and X[k, 0] < 1e-12 and v == X[k, 1]
+
+
+def test_mixed_space_and_split():
+    from flow_b200 import dolfin as d
+
+    m = d.UnitSquareMesh(3, 3)
+    WP = d.FunctionSpace(m, d.VectorElement("Lagrange", m.ufl_cell(), 2) * d.FiniteElement("Lagrange", m.ufl_cell(), 1))
+    assert WP.dim() == WP.sub(0).dim() + WP.sub(1).dim() == 2 * 49 + 16
+    up = d.Function(WP)
+    up.vector()[:] = np.arange(WP.dim())
+    u, p = up.split(True)
+    assert u.function_space().ncomp == 2 and p.function_space().dim() == 16
+    ux, uy = u.split()
+    assert np.array_equal(ux.vector().get_local(), u.vector().get_local()[0::2])
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_hostfem_matches_oracle(dim):
+    from flow_b200 import dolfin as d, hostfem
+
+    if dim == 2:
+        m, om = d.UnitSquareMesh(3, 4, "crossed"), fem.Mesh(*fem.unit_square_mesh(3, 4, "crossed"))
+        f = lambda X: np.stack([np.sin(X[:, 0] + 2 * X[:, 1]), np.cos(X[:, 0] * X[:, 1])], 1)
+    else:
+        m, om = d.UnitCubeMesh(2, 2, 1), fem.Mesh(*fem.unit_cube_mesh(2, 2, 1))
+        f = lambda X: np.stack([np.sin(X[:, 0] + 2 * X[:, 1]), np.cos(X[:, 0] * X[:, 2]), X[:, 1] ** 3], 1)
+    ns = m.node_space(2)
+    Wo = fem.Space(om, 2, dim)
+    for deg in (0, 1, 2, 5):
+        a = hostfem.load_vector(m.coordinates(), m.cells(), ns.cell_nodes, ns.nnodes, 2, dim, f, deg)
+        b = forms.expression_load_vector(Wo, f, deg)
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-15)
+    uh = np.random.default_rng(0).standard_normal(Wo.ndofs)
+    assert abs(hostfem.errornorm_l2(m.coordinates(), m.cells(), ns.cell_nodes, 2, uh, f) - util.errornorm(Wo, f, uh)) < 1e-12
+    lam, w = hostfem.quadrature(dim, 6)
+    lo, wo = fem.simplex_quadrature(dim, 6)
+    assert np.allclose(np.sort(w), np.sort(wo))

@@ -1,0 +1,128 @@
+"""Pin the oracle: the reference's own acceptance thresholds (tests/test_navier_stokes.py:386-445,
+tests/test_sealed_box.py:134-141), closed-form integrals, Jacobian consistency, golden fixtures."""
+import json
+import os
+
+import numpy as np
+import pytest
+import sympy
+
+import mms_problems as mp
+from oracle import fem, forms, navier_stokes as ons, solvers, util
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("dim,degree", [(1, 5), (2, 2), (2, 5), (2, 8), (3, 2), (3, 5), (3, 7)])
+def test_quadrature_exact(dim, degree):
+    import itertools
+    import math
+
+    lam, w = fem.simplex_quadrature(dim, degree)
+    assert (w > 0).all() and abs(w.sum() - 1) < 1e-14
+    for exps in itertools.product(range(degree + 1), repeat=dim + 1):
+        if sum(exps) > degree:
+            continue
+        exact = math.prod(math.factorial(e) for e in exps) * math.factorial(dim) / math.factorial(sum(exps) + dim)
+        assert abs(np.sum(w * np.prod(lam ** np.array(exps), axis=1)) - exact) < 1e-14
+
+
+def test_p2_mass_closed_form():
+    """int phi_i phi_j over the reference triangle, by sympy."""
+    x, y = sympy.symbols("x y")
+    lam = [1 - x - y, x, y]
+    phi = [l * (2 * l - 1) for l in lam] + [4 * lam[a] * lam[b] for a, b in fem.TRI_EDGES]
+    M = np.array([[float(sympy.integrate(sympy.integrate(pi * pj, (y, 0, 1 - x)), (x, 0, 1))) for pj in phi] for pi in phi])
+    mesh = fem.Mesh(np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]]), np.array([[0, 1, 2]]))
+    sp2 = fem.Space(mesh, 2)
+    Mo = forms.mass_matrix(sp2).toarray()
+    # edge nodes are numbered lexicographically (0,1),(0,2),(1,2); local edges are (1,2),(0,2),(0,1)
+    perm = list(sp2.cell_nodes[0])
+    assert np.allclose(Mo[np.ix_(perm, perm)], M, atol=1e-15)
+
+
+@pytest.mark.parametrize("name", ["tri", "tet"])
+@pytest.mark.parametrize("theta", [1.0, 0.5])
+def test_jacobian_is_derivative_of_residual(name, theta):
+    mesh = fem.Mesh(*(fem.unit_square_mesh(3, 2, "crossed") if name == "tri" else fem.unit_cube_mesh(2, 1, 1)))
+    W, P = fem.Space(mesh, 2, mesh.dim), fem.Space(mesh, 1, 1)
+    rng = np.random.default_rng(0)
+    ui, u0, p0 = rng.standard_normal(W.ndofs), rng.standard_normal(W.ndofs), rng.standard_normal(P.nnodes)
+    z = np.zeros(W.ndofs)
+    F, J = forms.momentum_residual_jacobian(W, P, ui, u0, p0, z, 0.3, 1.2, 0.7, theta)
+    v = rng.standard_normal(W.ndofs)
+    h = 1e-6
+    Fp, _ = forms.momentum_residual_jacobian(W, P, ui + h * v, u0, p0, z, 0.3, 1.2, 0.7, theta, want_J=False)
+    Fm, _ = forms.momentum_residual_jacobian(W, P, ui - h * v, u0, p0, z, 0.3, 1.2, 0.7, theta, want_J=False)
+    fd = (Fp - Fm) / (2 * h)
+    assert np.abs(fd - J @ v).max() / np.abs(fd).max() < 1e-8
+
+
+def test_mms_ipcs_order_and_golden():
+    """test_ipcs of the reference (meshes 8,16,32; Dt 1,0.5; guermond2): u order > 1.9, p order > 0.9."""
+    from golden.make_golden import time_errors
+
+    Dt = [1.0, 0.5]
+    e = time_errors(mp.problem_guermond2, ons.IPCS, [8, 16, 32], Dt)
+    ou = mp.compute_numerical_order_of_convergence(Dt, e["u"].T).T
+    op = mp.compute_numerical_order_of_convergence(Dt, e["p"].T).T
+    assert (ou[:, 0] > 2.0 - 0.1).all() and (op[:, 0] > 1.0 - 0.1).all()
+    gold = json.load(open(os.path.join(HERE, "golden", "mms_ipcs_guermond2.json")))
+    assert np.allclose(e["u"], gold["u"], rtol=1e-8) and np.allclose(e["p"], gold["p"], rtol=1e-8)
+
+
+def test_mms_chorin_order_flat():
+    """test_chorin[problem_flat] of the reference: u order > 0.9, p order > 0.4."""
+    from golden.make_golden import time_errors
+
+    Dt = [1.0e-3, 0.5e-3]
+    e = time_errors(mp.problem_flat, ons.Chorin, [16], Dt)
+    assert mp.compute_numerical_order_of_convergence(Dt, e["u"].T)[0, 0] > 0.9
+    assert mp.compute_numerical_order_of_convergence(Dt, e["p"].T)[0, 0] > 0.4
+
+
+def test_mms_rotational_order():
+    """test_rotational of the reference on the coarser of its two meshes (n=32): u > 1.9, p > 1.4."""
+    from golden.make_golden import time_errors
+
+    Dt = [1.0e-2, 0.5e-2]
+    e = time_errors(mp.problem_guermond1, ons.Rotational, [32], Dt)
+    assert mp.compute_numerical_order_of_convergence(Dt, e["u"].T)[0, 0] > 1.9
+    assert mp.compute_numerical_order_of_convergence(Dt, e["p"].T)[0, 0] > 1.4
+
+
+def test_sealed_box_invariant():
+    """tests/test_sealed_box.py:85-141 on a structured mesh: |u|_inf < 1e-13 after two IPCS steps."""
+    mesh = fem.Mesh(*fem.rectangle_mesh((0.0, 0.0), (0.1, 0.2), 6, 12, "left/right"))
+    st = ons.IPCS(mesh)
+    W, P = st.W, st.P
+    g, rho, mu, dt = -9.81, 998.21, 1.002e-3, 1e-2
+    u, p = np.zeros(W.ndofs), g * P.node_coords[:, 1]
+    bd = W.boundary_dofs()
+    load = forms.expression_load_vector(W, lambda X: np.tile([0.0, g], (X.shape[0], 1)), 0)
+    for _ in range(2):
+        u, p = st.step(dt, u, p, (bd, np.zeros(bd.size)), None, rho, mu, load, load, tol=1e-10)
+    assert np.sqrt((u.reshape(-1, 2) ** 2).sum(1)).max() < 1e-13
+
+
+def test_small_step_golden():
+    from golden.make_golden import small_step_fixture
+
+    gold = json.load(open(os.path.join(HERE, "golden", "rotational_small_step.json")))
+    now = small_step_fixture()
+    for k in gold:
+        for f in ("u1", "p1"):
+            assert np.allclose(now[k][f], gold[k][f], rtol=1e-9, atol=1e-12)
+
+
+def test_krylov_mode_matches_lu():
+    mesh = fem.Mesh(*fem.unit_cube_mesh(3, 3, 3))
+    out = {}
+    for lin in ("lu", "krylov"):
+        st = ons.IPCS(mesh, linear=lin)
+        W = st.W
+        bd = W.boundary_dofs()
+        g = np.zeros((W.nnodes, 3))
+        g[W.node_coords[:, 2] > 1 - 1e-12, 0] = 1.0
+        out[lin] = st.step(1e-2, np.zeros(W.ndofs), np.zeros(st.P.nnodes), (bd, g.reshape(-1)[bd]), None, 1.0, 1e-2, tol=1e-10)
+    assert np.linalg.norm(out["lu"][0] - out["krylov"][0]) / np.linalg.norm(out["lu"][0]) < 1e-8
