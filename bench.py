@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- IPCS time-steps/s on the 3D P2/P1 lid-driven cavity (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n 74]
+
+Workload: UnitCubeMesh(n, n, n), n = 74 -> 10 345 722 dofs
+(9 923 847 velocity + 421 875 pressure), lid u = (1,0,0) on z = 1, no-slip elsewhere,
+p_bcs = [], f = 0, rho = 1, mu = 1e-2 (Re = 100), dt = 1e-2, IPCS / backward Euler,
+tol = 1e-10, starting from rest; every step continues from the previous one.
+
+One JSON line on stdout (rank 0).  `value` = steps/s with the state resident in HBM
+(C ABI called with FB_DEVICE_PTRS); `e2e` = the same steps through the public API
+`flow_b200.navier_stokes.IPCS().step` with pinned host buffers, H2D/D2H inside the timed
+region.  `roofline` = the block-CSR SpMV of the momentum Jacobian (the dominant kernel).
+`cpu_baseline` = the oracle's Krylov variant (numpy assembly + C/OpenMP Jacobi-Krylov) on a
+bounded sample of the same cavity, extrapolated linearly in dofs.  The reference's own stack
+(FEniCS/PETSc) cannot be installed here, so `--impl reference` times that same
+oracle port on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ipcs_timesteps_per_sec_p2p1_3d_cavity"
+UNIT = "steps/s"
+DT, RHO, MU, TOL = 1.0e-2, 1.0, 1.0e-2, 1.0e-10
+
+
+def dof_counts(n):
+    nv = (n + 1) ** 3
+    ne = 3 * n * (n + 1) ** 2 + 3 * n * n * (n + 1) + n ** 3  # axis + face-diagonal + body-diagonal edges
+    return 3 * (nv + ne), nv
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                               "--format=csv,noheader,nounits"], timeout=5).decode().strip()
+                self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=3)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any(s[3 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(sm)}
+
+
+def cavity_bcs(d, W):
+    top = 1.0 - 1e-12
+    walls = d.DirichletBC(W, (0.0, 0.0, 0.0), "on_boundary")
+    lid = d.DirichletBC(W, (1.0, 0.0, 0.0), lambda x, on: x[2] > top)
+    return [walls, lid]  # the lid wins on the shared edges
+
+
+def oracle_cavity_step_time(n, steps, warmup=0):
+    """Seconds per IPCS step of the oracle's Krylov-CPU variant on UnitCubeMesh(n)."""
+    from oracle import fem, navier_stokes as ons, solvers
+
+    om = fem.Mesh(*fem.unit_cube_mesh(n, n, n))
+    st = ons.IPCS(om, linear="krylov")
+    W = st.W
+    bd = W.boundary_dofs()
+    g = np.zeros((W.nnodes, 3))
+    g[W.node_coords[:, 2] > 1 - 1e-12, 0] = 1.0
+    g = g.reshape(-1)[bd]
+    u, p = np.zeros(W.ndofs), np.zeros(st.P.nnodes)
+    times = []
+    for k in range(warmup + steps):
+        t0 = time.perf_counter()
+        u, p = st.step(DT, u, p, (bd, g), None, RHO, MU, None, None, tol=TOL)
+        if k >= warmup:
+            times.append(time.perf_counter() - t0)
+    return float(np.mean(times)), W.ndofs + st.P.nnodes, solvers.cbaseline().cb_num_threads(), dict(st.info)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n_full = args.n
+    nd_full = sum(dof_counts(n_full))
+    sec, nd, threads, info = oracle_cavity_step_time(args.cpu_n, max(1, args.steps), min(args.warmup, 1))
+    value = (1.0 / sec) * (nd / float(nd_full))
+    sample = ("oracle port (numpy assembly + C/OpenMP Jacobi-BiCGStab/CG) of the same cavity on UnitCubeMesh(%d) = %d dofs, "
+              "%.2f s/step measured; steps/s extrapolated linearly in dofs to %d dofs (optimistic for the CPU). "
+              "FEniCS/PETSc itself is not installable here." % (args.cpu_n, nd, sec, nd_full))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "3D lid-driven cavity P2/P1 IPCS, UnitCubeMesh(%d), %d dofs" % (n_full, nd_full)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=74, help="cells per edge of the unit cube (74 -> 10.3 M dofs)")
+    ap.add_argument("--cpu-n", type=int, default=10, help="cube size of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch
+    import torch.distributed as dist
+
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    os.environ["FLOW_B200_DEVICE"] = str(local_rank)
+
+    from flow_b200 import _lib
+    from flow_b200 import dolfin as d
+    from flow_b200 import navier_stokes as nav
+    from flow_b200._lib import lib
+    from flow_b200.navier_stokes.pressure_correction import _engine
+
+    if not _lib.has_device():
+        raise SystemExit("bench.py: no CUDA device; flow_b200 has no CPU path (use --impl reference for the CPU arm)")
+    ctx = _lib.context()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- setup (untimed): mesh, spaces, patterns, constant operators
+    t_setup = time.perf_counter()
+    n = args.n
+    mesh = d.UnitCubeMesh(n, n, n)
+    W = d.VectorFunctionSpace(mesh, "CG", 2)
+    P = d.FunctionSpace(mesh, "CG", 1)
+    bcs = cavity_bcs(d, W)
+    ud, uv = d.collect_bcs(bcs, W)
+    ns = _engine(W, P)
+    nu, npp = W.dim(), P.dim()
+    t_setup = time.perf_counter() - t_setup
+
+    def launches():
+        c = _lib.i64()
+        lib.fb_ctx_launch_count(ctx, C.byref(c))
+        return c.value
+
+    # ---- device-resident stepping (value)
+    dev = torch.device("cuda", local_rank)
+    ua, ub = torch.zeros(nu, dtype=torch.float64, device=dev), torch.zeros(nu, dtype=torch.float64, device=dev)
+    pa, pb = torch.zeros(npp, dtype=torch.float64, device=dev), torch.zeros(npp, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    stats = _lib.NSStats()
+    hist = []
+
+    def dev_step(uin, pin, uout, pout):
+        st = lib.fb_ns_step(ns, DT, RHO, MU, _lib.BACKWARD_EULER, _lib.DEVICE_PTRS, uin.data_ptr(), pin.data_ptr(),
+                            _lib.F_NONE, None, None, ud.size, _lib.as_pi64(ud), _lib.as_pd(uv), 0, None, None, TOL,
+                            uout.data_ptr(), pout.data_ptr(), C.byref(stats))
+        _lib.check(st, ctx, "fb_ns_step")
+        hist.append(stats.as_dict())
+
+    for _ in range(args.warmup):
+        dev_step(ua, pa, ub, pb)
+        ua, ub, pa, pb = ub, ua, pb, pa
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = launches()
+    del hist[:]
+    _lib.check(lib.fb_ctx_timer_start(ctx), ctx)
+    for _ in range(args.steps):
+        dev_step(ua, pa, ub, pb)
+        ua, ub, pa, pb = ub, ua, pb, pa
+    ms = C.c_double()
+    _lib.check(lib.fb_ctx_timer_stop(ctx, C.byref(ms)), ctx)
+    barrier()
+    clocks = sampler.summary()
+    gpu_launches = launches() - l0
+    t = torch.tensor([ms.value], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * args.steps / (ms_total * 1e-3)  # replicas: every rank advances its own cavity
+    timed = list(hist)
+
+    # ---- end-to-end through the public API with pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        u0 = d.Function(W, _lib.pinned_empty(ctx, nu))
+        p0 = d.Function(P, _lib.pinned_empty(ctx, npp))
+        u0._vec[:] = ua.cpu().numpy()
+        p0._vec[:] = pa.cpu().numpy()
+        zero = d.Constant((0.0, 0.0, 0.0))
+        stepper = nav.IPCS()
+        for _ in range(1):
+            u1, p1 = stepper.step(d.Constant(DT), {0: u0}, p0, bcs, [], d.Constant(RHO), d.Constant(MU), {0: zero, 1: zero},
+                                  verbose=False, tol=TOL)
+            u0, p0 = u1, p1
+        barrier()
+        t0 = time.perf_counter()
+        ke = max(2, min(args.steps, 5))
+        for _ in range(ke):
+            u1, p1 = stepper.step(d.Constant(DT), {0: u0}, p0, bcs, [], d.Constant(RHO), d.Constant(MU), {0: zero, 1: zero},
+                                  verbose=False, tol=TOL)
+            u0, p0 = u1, p1
+            _ = float(u1._vec[0])  # the result is on the host
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * ke / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int((nu + npp) * 8 + ud.size * 16),
+               "d2h_bytes_per_step": int((nu + npp) * 8), "steps": ke}
+
+    # ---- roofline of the dominant kernel: block-CSR SpMV of the momentum Jacobian
+    roofline = None
+    extra = {}
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        which = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        h = _lib.vp()
+        lib.fb_ns_matrix(ns, 2, C.byref(h))
+        msv, byt = C.c_double(), C.c_double()
+        _lib.check(lib.fb_mat_bench_spmv(h, 1, 30, C.byref(msv), C.byref(byt)), ctx, "bench_spmv")
+        ach = byt.value / (msv.value * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_bspmv<3,32> (momentum Jacobian SpMV)", "achieved": ach, "peak": peak,
+                    "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": which,
+                    "algorithmic_bytes_per_launch": byt.value, "ms_per_launch": msv.value}
+        for name, idx, nc in (("p1_stiffness_spmv", 0, 1), ("p2_mass_spmm3", 1, 3)):
+            lib.fb_ns_matrix(ns, idx, C.byref(h))
+            lib.fb_mat_bench_spmv(h, nc, 30, C.byref(msv), C.byref(byt))
+            extra[name] = {"ms": msv.value, "GB/s": byt.value / (msv.value * 1e-3) / 1e9}
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same cavity
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sec, nd, threads, info = oracle_cavity_step_time(args.cpu_n, 1, 0)
+        nd_full = nu + npp
+        cpu = {"value": (1.0 / sec) * (nd / float(nd_full)), "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "oracle Krylov-CPU IPCS step on UnitCubeMesh(%d) = %d dofs: %.2f s/step (numpy assembly + C/OpenMP "
+                         "Jacobi-Krylov); extrapolated linearly in dofs to %d" % (args.cpu_n, nd, sec, nd_full)}
+
+    if rank == 0:
+        avg = lambda k: float(np.mean([h[k] for h in timed]))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": "3D lid-driven cavity, P2/P1 IPCS backward Euler, UnitCubeMesh(%d): %d dofs (%d u + %d p), "
+                            "Re=100, dt=1e-2, tol=1e-10" % (n, nu + npp, nu, npp),
+                "parallelism": "single GPU" if world == 1 else "replicas: %d independent cavities (mesh partitioning lands next)" % world,
+                "l2_policy": "working set (Jacobian %.1f GB) far exceeds the 126 MB L2" % (roofline["algorithmic_bytes_per_launch"] / 1e9 if roofline else 0),
+            },
+            "iterations": {"newton": avg("newton_its"), "momentum_krylov": avg("momentum_its"), "pressure_cg": avg("pressure_its"),
+                           "correction_cg": avg("correction_its")},
+            "phase_ms": {"tentative": avg("ms_tentative"), "pressure": avg("ms_pressure"), "correction": avg("ms_correction"),
+                         "assembly_J": avg("ms_assembly_J"), "momentum_solve": avg("ms_momentum_solve")},
+            "setup_s": t_setup, "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
+            "other_kernels": extra, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -86,6 +86,8 @@ SIGNATURES = {
     "fb_ctx_launch_count": (C.c_int, [vp, pi64]),
     "fb_ctx_timer_start": (C.c_int, [vp]),
     "fb_ctx_timer_stop": (C.c_int, [vp, pd]),
+    "fb_host_alloc": (C.c_int, [vp, i64, C.POINTER(vp)]),
+    "fb_host_free": (C.c_int, [vp, vp]),
     "fb_mesh_create": (C.c_int, [vp, C.c_int, i64, pd, i64, pi32, C.POINTER(vp)]),
     "fb_mesh_destroy": (C.c_int, [vp]),
     "fb_mesh_info": (C.c_int, [vp, pi64, pi64, pi64, pi64]),
@@ -205,3 +207,36 @@ def has_device():
         if h is ctx or h.value == ctx.value:
             return dev >= 0
     return False
+
+
+# ---- page-locked host arrays (pooled: cudaMallocHost costs ~10 ms per 100 MB) ----------------
+_pinned_pool = {}
+
+
+class _PinnedBlock(object):
+    def __init__(self, ctx, nbytes):
+        p = vp()
+        check(lib.fb_host_alloc(ctx, nbytes, C.byref(p)), ctx, "fb_host_alloc")
+        self.ptr, self.nbytes = p, nbytes
+        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (p.value, False), "version": 3}
+
+
+def pinned_empty(ctx, n):
+    """float64 numpy array of length n in page-locked memory; returned to a pool when collected."""
+    import weakref
+
+    nbytes = int(n) * 8
+    free = _pinned_pool.setdefault(nbytes, [])
+    blk = free.pop() if free else _PinnedBlock(ctx, nbytes)
+    arr = np.asarray(blk).view(np.float64)
+    weakref.finalize(arr, free.append, blk)
+    return arr
+
+
+def state_array(ctx, n, threshold=1 << 16):
+    """Zero-initialised dof array: pinned when a device is present and the array is large."""
+    if n >= threshold and has_device():
+        a = pinned_empty(ctx, n)
+        a[:] = 0.0
+        return a
+    return np.zeros(n)

@@ -180,6 +180,21 @@ int fb_ctx_timer_stop(fb_ctx *ctx, double *ms) {
   FB_API_END
 }
 
+int fb_host_alloc(fb_ctx *ctx, int64_t bytes, void **out) {
+  FB_NEED_DEVICE(ctx);
+  if (!out || bytes <= 0) return FB_EINVAL;
+  FB_API_BEGIN(ctx)
+  FB_CUDA(cudaMallocHost(out, (size_t)bytes));
+  FB_API_END
+}
+
+int fb_host_free(fb_ctx *ctx, void *ptr) {
+  FB_NEED_DEVICE(ctx);
+  FB_API_BEGIN(ctx)
+  if (ptr) FB_CUDA(cudaFreeHost(ptr));
+  FB_API_END
+}
+
 int fb_mesh_destroy(fb_mesh *m) {
   delete m;
   return FB_OK;

@@ -87,8 +87,9 @@ def _step(dt, u, p0, u_bcs, p_bcs, rho, mu, time_step_method, f, rotational_form
     mode, f0, f1 = _forcing(f, W, theta)
     ud, uv = collect_bcs(u_bcs, W)
     pd_, pv = collect_bcs(p_bcs, P)
-    u1 = Function(W)
-    p1 = Function(P)
+    ctx = W.mesh().ctx
+    u1 = Function(W, _lib.state_array(ctx, W.dim()))
+    p1 = Function(P, _lib.state_array(ctx, P.dim()))
     flags = (_lib.ROTATIONAL if rotational_form else 0) | (_lib.CHORIN if chorin else 0)
     stats = _lib.NSStats()
 

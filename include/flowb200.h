@@ -63,6 +63,11 @@ int fb_ctx_launch_count(fb_ctx *ctx, int64_t *count);
 int fb_ctx_timer_start(fb_ctx *ctx);
 int fb_ctx_timer_stop(fb_ctx *ctx, double *ms);
 
+/* page-locked host buffers for the caller's state vectors (faster H2D/D2H); plain malloc'd
+ * or numpy memory is accepted everywhere as well */
+int fb_host_alloc(fb_ctx *ctx, int64_t bytes, void **out);
+int fb_host_free(fb_ctx *ctx, void *ptr);
+
 /* ---- mesh: replaces dolfin.Mesh / UnitSquareMesh / RectangleMesh / BoxMesh
  * (tests/test_navier_stokes.py:82,144,176; tests/test_sealed_box.py:53).
  * cells: ncells*(gdim+1) vertex indices; they are sorted per cell (UFC order). */

@@ -10,6 +10,11 @@ import scipy.sparse as sp
 from . import fem
 
 
+def _es(*args):
+    """einsum with contraction-order optimisation (BLAS where possible): same sums, ~10x faster."""
+    return np.einsum(*args, optimize=True)
+
+
 def _scatter_matrix(row_dofs, col_dofs, Ke, nrows, ncols):
     nlr = row_dofs.shape[1]
     nlc = col_dofs.shape[1]
@@ -28,7 +33,7 @@ def vector_dofs(cell_nodes, d):
 
 def phys_grads(mesh, dphi):
     """(nc, nq, nl, d) physical gradients from dphi/dlam (nq, nl, d+1)."""
-    return np.einsum("qam,cmk->cqak", dphi, mesh.glam)
+    return _es("qam,cmk->cqak", dphi, mesh.glam)
 
 
 # ---- constant scalar matrices --------------------------------------------
@@ -37,7 +42,7 @@ def mass_matrix(space):
     m = space.mesh
     lam, w = fem.simplex_quadrature(m.dim, 2 * space.degree)
     phi, _ = space.tabulate(lam)
-    Mref = np.einsum("q,qa,qb->ab", w, phi, phi)
+    Mref = _es("q,qa,qb->ab", w, phi, phi)
     Ke = m.vol[:, None, None] * Mref[None]
     return _scatter_matrix(space.cell_nodes, space.cell_nodes, Ke, space.nnodes, space.nnodes)
 
@@ -48,7 +53,7 @@ def stiffness_matrix(space):
     lam, w = fem.simplex_quadrature(m.dim, max(0, 2 * (space.degree - 1)))
     _, dphi = space.tabulate(lam)
     g = phys_grads(m, dphi)
-    Ke = np.einsum("q,cqak,cqbk->cab", w, g, g) * m.vol[:, None, None]
+    Ke = _es("q,cqak,cqbk->cab", w, g, g) * m.vol[:, None, None]
     return _scatter_matrix(space.cell_nodes, space.cell_nodes, Ke, space.nnodes, space.nnodes)
 
 
@@ -64,7 +69,7 @@ def load_vector(space, fq, lam, w):
     """int f.v dx given f at quadrature points: fq (nc, nq, ncomp)."""
     m = space.mesh
     phi, _ = space.tabulate(lam)
-    be = np.einsum("q,cqi,qa,c->cai", w, fq, phi, m.vol)
+    be = _es("q,cqi,qa,c->cai", w, fq, phi, m.vol)
     b = np.zeros(space.nnodes * space.ncomp)
     dofs = vector_dofs(space.cell_nodes, space.ncomp)
     np.add.at(b, dofs.ravel(), be.reshape(m.nc, -1).ravel())
@@ -82,10 +87,10 @@ def expression_load_vector(space, func, degree):
         fq = np.repeat(vals, lam.shape[0], axis=1)
     else:
         al = fem.lattice(m.dim, degree) / float(degree)
-        X = np.einsum("nm,cmk->cnk", al, m.points[m.cells])  # lattice points per cell
+        X = _es("nm,cmk->cnk", al, m.points[m.cells])  # lattice points per cell
         vals = func(X.reshape(-1, m.dim)).reshape(m.nc, al.shape[0], -1)
         psi = fem.tabulate_pk(m.dim, degree, lam)
-        fq = np.einsum("qn,cni->cqi", psi, vals)
+        fq = _es("qn,cni->cqi", psi, vals)
     return load_vector(space, fq, lam, w)
 
 
@@ -121,26 +126,26 @@ def momentum_residual_jacobian(W, P, ui, u0, p0, load, dt, rho, mu, theta, want_
     g = phys_grads(m, dphi)  # (c,q,a,k)
     psi, _ = P.tabulate(lam)
     vol = m.vol
-    p0q = np.einsum("qa,ca->cq", psi, p0[P.cell_nodes])
+    p0q = _es("qa,ca->cq", psi, p0[P.cell_nodes])
 
     def cell_R(u):
         U = u.reshape(-1, d)[W.cell_nodes]  # (c,a,i)
-        uq = np.einsum("qa,cai->cqi", phi, U)
-        gu = np.einsum("cqak,cai->cqik", g, U)  # d u_i / d x_k
-        conv1 = np.einsum("cqik,cqk->cqi", gu, uq)  # (grad u) u
-        ugphi = np.einsum("cqk,cqak->cqa", uq, g)  # u . grad phi_a
+        uq = _es("qa,cai->cqi", phi, U)
+        gu = _es("cqak,cai->cqik", g, U)  # d u_i / d x_k
+        conv1 = _es("cqik,cqk->cqi", gu, uq)  # (grad u) u
+        ugphi = _es("cqk,cqak->cqa", uq, g)  # u . grad phi_a
         eps = 0.5 * (gu + np.swapaxes(gu, 2, 3))
         R = -rho * 0.5 * (
-            np.einsum("q,cqi,qa->cai", w, conv1, phi) - np.einsum("q,cqa,cqi->cai", w, ugphi, uq)
+            _es("q,cqi,qa->cai", w, conv1, phi) - _es("q,cqa,cqi->cai", w, ugphi, uq)
         )
-        R += -2 * mu * np.einsum("q,cqik,cqak->cai", w, eps, g)
-        R += np.einsum("q,cq,cqai->cai", w, p0q, g)  # + p0 div v
+        R += -2 * mu * _es("q,cqik,cqak->cai", w, eps, g)
+        R += _es("q,cq,cqai->cai", w, p0q, g)  # + p0 div v
         return R * vol[:, None, None], (U, uq, gu, ugphi)
 
     Ui = ui.reshape(-1, d)[W.cell_nodes]
     U0 = u0.reshape(-1, d)[W.cell_nodes]
-    Mref = np.einsum("q,qa,qb->ab", w, phi, phi)
-    Fe = np.einsum("ab,cbi,c->cai", Mref, Ui - U0, vol)
+    Mref = _es("q,qa,qb->ab", w, phi, phi)
+    Fe = _es("ab,cbi,c->cai", Mref, Ui - U0, vol)
     ctx = None
     if theta != 0.0:
         Ri, ctx = cell_R(ui)
@@ -169,14 +174,14 @@ def momentum_residual_jacobian(W, P, ui, u0, p0, load, dt, rho, mu, theta, want_
         gl = m.glam[sel]
         # n * |facet| = -grad(lambda_f) * d * vol
         nA = -gl[:, f, :] * (d * vol[sel])[:, None]
-        gf = np.einsum("qam,cmk->cqak", fdphi, gl)
-        p0f = np.einsum("qa,ca->cq", fpsi, p0[P.cell_nodes[sel]])
+        gf = _es("qam,cmk->cqak", fdphi, gl)
+        p0f = _es("qa,ca->cq", fpsi, p0[P.cell_nodes[sel]])
 
         def facet_R(u):
             U = u.reshape(-1, d)[W.cell_nodes[sel]]
-            gu = np.einsum("cqak,cai->cqik", gf, U)
-            gtn = np.einsum("cqki,ck->cqi", gu, nA)  # (grad u)^T n
-            return -np.einsum("q,cq,ci,qa->cai", fw, p0f, nA, fphi) + mu * np.einsum(
+            gu = _es("cqak,cai->cqik", gf, U)
+            gtn = _es("cqki,ck->cqi", gu, nA)  # (grad u)^T n
+            return -_es("q,cq,ci,qa->cai", fw, p0f, nA, fphi) + mu * _es(
                 "q,cqi,qa->cai", fw, gtn, fphi
             )
 
@@ -189,30 +194,30 @@ def momentum_residual_jacobian(W, P, ui, u0, p0, load, dt, rho, mu, theta, want_
         if want_J and theta != 0.0:
             # -theta dt/rho mu ((grad delta)^T n, v)_ds ; delta = phi_b e_j, v = phi_a e_i
             # ((grad delta)^T n)_i = d_i phi_b n_j
-            Jf = -theta * dt / rho * mu * np.einsum("q,qa,cqbi,cj->caibj", fw, fphi, gf, nA)
+            Jf = -theta * dt / rho * mu * _es("q,qa,cqbi,cj->caibj", fw, fphi, gf, nA)
             np.add.at(Je, sel, Jf)
 
     if not want_J:
         return F, None
 
     eye = np.eye(d)
-    Je += np.einsum("ab,ij,c->caibj", Mref, eye, vol)
+    Je += _es("ab,ij,c->caibj", Mref, eye, vol)
     if theta != 0.0:
         U, uq, gu, ugphi = ctx
         c1 = theta * dt * 0.5  # rho cancels
         # ((grad delta) ui, v) - ((grad v) ui, delta): component-diagonal, skew in (a,b)
-        S = np.einsum("q,cqb,qa->cab", w, ugphi, phi)
+        S = _es("q,cqb,qa->cab", w, ugphi, phi)
         S = (S - np.swapaxes(S, 1, 2)) * vol[:, None, None]
-        Je += c1 * np.einsum("cab,ij->caibj", S, eye)
+        Je += c1 * _es("cab,ij->caibj", S, eye)
         # ((grad ui) delta, v): phi_a phi_b d_j ui_i
-        Je += c1 * np.einsum("q,qa,qb,cqij,c->caibj", w, phi, phi, gu, vol)
+        Je += c1 * _es("q,qa,qb,cqij,c->caibj", w, phi, phi, gu, vol)
         # -((grad v) delta, ui): - d_j phi_a phi_b ui_i
-        Je -= c1 * np.einsum("q,cqaj,qb,cqi,c->caibj", w, g, phi, uq, vol)
+        Je -= c1 * _es("q,cqaj,qb,cqi,c->caibj", w, g, phi, uq, vol)
         c2 = theta * dt / rho * mu
         # 2 eps(delta):eps(v) = delta_ij grad phi_a.grad phi_b + d_i phi_b d_j phi_a
-        K = np.einsum("q,cqak,cqbk,c->cab", w, g, g, vol)
-        Je += c2 * np.einsum("cab,ij->caibj", K, eye)
-        Je += c2 * np.einsum("q,cqbi,cqaj,c->caibj", w, g, g, vol)
+        K = _es("q,cqak,cqbk,c->cab", w, g, g, vol)
+        Je += c2 * _es("cab,ij->caibj", K, eye)
+        Je += c2 * _es("q,cqbi,cqaj,c->caibj", w, g, g, vol)
     J = _scatter_matrix(dofs, dofs, Je.reshape(m.nc, nl * d, nl * d), W.nnodes * d, W.nnodes * d)
     return F, J
 
@@ -224,7 +229,7 @@ def divergence_at(W, lam, u):
     _, dphi = W.tabulate(lam)
     g = phys_grads(m, dphi)
     U = u.reshape(-1, m.dim)[W.cell_nodes]
-    return np.einsum("cqai,cai->cq", g, U)
+    return _es("cqai,cai->cq", g, U)
 
 
 def grad_div(W, u):
@@ -233,7 +238,7 @@ def grad_div(W, u):
     H = fem.p2_second_derivs(m.dim)  # (a,m,n)
     U = u.reshape(-1, m.dim)[W.cell_nodes]
     # d_k d_i phi_a = sum_mn H[a,m,n] glam[m,i] glam[n,k]
-    return np.einsum("amn,cmi,cnk,cai->ck", H, m.glam, m.glam, U)
+    return _es("amn,cmi,cnk,cai->ck", H, m.glam, m.glam, U)
 
 
 def pressure_rhs(W, P, ui, p0, dt, rho, mu, rotational, alpha=1.0):
@@ -244,11 +249,11 @@ def pressure_rhs(W, P, ui, p0, dt, rho, mu, rotational, alpha=1.0):
     psi, dpsi = P.tabulate(lam)
     gq = phys_grads(m, dpsi)[:, 0]  # P1 gradients constant: (c,a,k)
     div = divergence_at(W, lam, ui)
-    be = -alpha * rho / dt * np.einsum("q,cq,qa,c->ca", w, div, psi, m.vol)
-    gp0 = np.einsum("cak,ca->ck", gq, p0[P.cell_nodes])
-    be += np.einsum("ck,cak,c->ca", gp0, gq, m.vol)
+    be = -alpha * rho / dt * _es("q,cq,qa,c->ca", w, div, psi, m.vol)
+    gp0 = _es("cak,ca->ck", gq, p0[P.cell_nodes])
+    be += _es("ck,cak,c->ca", gp0, gq, m.vol)
     if rotational:
-        be -= mu * np.einsum("ck,cak,c->ca", grad_div(W, ui), gq, m.vol)
+        be -= mu * _es("ck,cak,c->ca", grad_div(W, ui), gq, m.vol)
     b = np.zeros(P.nnodes)
     np.add.at(b, P.cell_nodes.ravel(), be.ravel())
     return b
@@ -264,12 +269,12 @@ def correction_rhs(W, P, ui, p1, p0, dt, rho, mu, rotational):
     psi, dpsi = P.tabulate(lam)
     gq = phys_grads(m, dpsi)[:, 0]
     U = ui.reshape(-1, d)[W.cell_nodes]
-    Mref = np.einsum("q,qa,qb->ab", w, phi, phi)
-    be = np.einsum("ab,cbi,c->cai", Mref, U, m.vol)
-    gphi = np.einsum("cak,ca->ck", gq, (p1 - p0)[P.cell_nodes])
+    Mref = _es("q,qa,qb->ab", w, phi, phi)
+    be = _es("ab,cbi,c->cai", Mref, U, m.vol)
+    gphi = _es("cak,ca->ck", gq, (p1 - p0)[P.cell_nodes])
     if rotational:
         gphi = gphi + mu * grad_div(W, ui)
-    be -= dt / rho * np.einsum("q,qa,ck,c->cak", w, phi, gphi, m.vol)
+    be -= dt / rho * _es("q,qa,ck,c->cak", w, phi, gphi, m.vol)
     b = np.zeros(W.nnodes * d)
     np.add.at(b, vector_dofs(W.cell_nodes, d).ravel(), be.reshape(m.nc, -1).ravel())
     return b
@@ -282,11 +287,11 @@ def heat_operator(V, W, conv, kappa, rho_cp):
     lam, w = fem.simplex_quadrature(m.dim, 2 + 2 * V.degree - 1)
     phi, dphi = V.tabulate(lam)
     g = phys_grads(m, dphi)
-    Ke = -(kappa / rho_cp) * np.einsum("q,cqak,cqbk->cab", w, g, g)
+    Ke = -(kappa / rho_cp) * _es("q,cqak,cqbk->cab", w, g, g)
     if conv is not None:
         wphi, _ = W.tabulate(lam)
-        cq = np.einsum("qa,cai->cqi", wphi, conv.reshape(-1, m.dim)[W.cell_nodes])
-        Ke -= np.einsum("q,cqk,cqbk,qa->cab", w, cq, g, phi)
+        cq = _es("qa,cai->cqi", wphi, conv.reshape(-1, m.dim)[W.cell_nodes])
+        Ke -= _es("q,cqk,cqbk,qa->cab", w, cq, g, phi)
     Ke *= m.vol[:, None, None]
     return _scatter_matrix(V.cell_nodes, V.cell_nodes, Ke, V.nnodes, V.nnodes)
 
@@ -303,7 +308,7 @@ def stokes_blocks(W, P, mu):
     psi, _ = P.tabulate(lam)
     g = phys_grads(m, dphi)
     # B[q_a, (b,j)] = - int psi_a d_j phi_b
-    Be = -np.einsum("q,qa,cqbj,c->cabj", w, psi, g, m.vol).reshape(m.nc, P.nl, -1)
+    Be = -_es("q,qa,cqbj,c->cabj", w, psi, g, m.vol).reshape(m.nc, P.nl, -1)
     B = _scatter_matrix(P.cell_nodes, vector_dofs(W.cell_nodes, d), Be, P.nnodes, W.nnodes * d)
     Mp = mass_matrix(P)
     A = sp.kron(K, sp.eye(d), format="csr")
