@@ -22,11 +22,17 @@ struct fb_cuda_error : std::runtime_error {
                               std::to_string(__LINE__));                                                \
   } while (0)
 
-// All kernels go through this so the context can report how many of OUR kernels ran.
-#define FB_LAUNCH(ctx, kernel, grid, block, smem, ...)                    \
-  do {                                                                    \
-    kernel<<<(grid), (block), (smem), (ctx)->dev->stream>>>(__VA_ARGS__); \
-    (ctx)->launches++;                                                    \
+// All kernels go through this so the context can report how many of OUR kernels ran.  Every
+// kernel in the library is a grid-stride loop, so the requested grid is clamped to one full
+// wave (resident blocks per SM x SM count, from the occupancy calculator): a grid larger than
+// that only adds a partially filled tail wave.
+int fb_clamp_grid(fb_ctx *ctx, const void *kernel, int grid, int block, size_t smem);
+
+#define FB_LAUNCH(ctx, kernel, grid, block, smem, ...)                                               \
+  do {                                                                                               \
+    const int _fb_g = fb_clamp_grid((ctx), (const void *)(kernel), (grid), (block), (smem));          \
+    kernel<<<_fb_g, (block), (smem), (ctx)->dev->stream>>>(__VA_ARGS__);                             \
+    (ctx)->launches++;                                                                               \
   } while (0)
 
 constexpr int FB_NSLOTS = 16;          // reduction result slots

@@ -10,6 +10,7 @@
 // compressed to one int per block.  SpMV lanes stream each scalar row contiguously
 // (coalesced) and share one x gather between the D rows.
 #include <algorithm>
+#include <unordered_map>
 #include <vector>
 
 #include "fb_element.cuh"
@@ -105,6 +106,23 @@ static void upload_mref() {
   FB_CUDA(cudaMemcpyToSymbol(c_mref2, m2, sizeof(m2)));
   FB_CUDA(cudaMemcpyToSymbol(c_mref3, m3, sizeof(m3)));
   g_mref_uploaded = true;
+}
+
+int fb_clamp_grid(fb_ctx *ctx, const void *kernel, int grid, int block, size_t smem) {
+  static std::unordered_map<const void *, int> cache;  // resident blocks per SM of each kernel
+  const uint64_t key_block = (uint64_t)block;
+  const void *key = (const void *)((uintptr_t)kernel ^ (key_block << 48));
+  auto it = cache.find(key);
+  int per_sm;
+  if (it == cache.end()) {
+    per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    cache[key] = per_sm;
+  } else {
+    per_sm = it->second;
+  }
+  const int wave = per_sm * ctx->dev->sm_count;
+  return grid < wave ? grid : wave;
 }
 
 static inline int grid_for(int64_t work_items, int block, int cap) {
@@ -657,11 +675,17 @@ void jacobi_setup_blocked(fb_ctx *ctx, const DevSpace &sp, int D, const double *
 // =============================================================================
 constexpr int MOM_WARPS = 4;
 
+// Shared-memory working set of the warp-per-cell momentum kernels.  Everything that is
+// indexed with a lane-dependent index lives here (constant memory would serialise, register
+// arrays would spill to local memory).
 template <int D>
 struct MomShared {
   static constexpr int NL = Elem<D>::NL2;
   static constexpr int NQ = Q5<D>::NQ;
-  double phi[NQ][NL];
+  double phi[NQ][NL];       // P2 basis at the quadrature points (cell independent)
+  double qlam[NQ][D + 1];   // quadrature points
+  double qw[NQ];
+  double glam[MOM_WARPS][D + 1][D];
   double U[MOM_WARPS][NL][D];
   double g[MOM_WARPS][NQ][NL][D];
   double uq[MOM_WARPS][NQ][D];
@@ -670,22 +694,46 @@ struct MomShared {
 };
 
 template <int D>
-__device__ __forceinline__ void mom_fill_phi(MomShared<D> &s) {
+__device__ __forceinline__ void mom_fill_tables(MomShared<D> &s) {
   constexpr int NL = Elem<D>::NL2, NQ = Q5<D>::NQ;
+  for (int t = threadIdx.x; t < NQ * (D + 1); t += blockDim.x) s.qlam[t / (D + 1)][t % (D + 1)] = Q5<D>::lam(t / (D + 1), t % (D + 1));
+  for (int t = threadIdx.x; t < NQ; t += blockDim.x) s.qw[t] = Q5<D>::w(t);
+  __syncthreads();
   for (int t = threadIdx.x; t < NQ * NL; t += blockDim.x) {
     const int q = t / NL, a = t - q * NL;
-    double lam[D + 1];
-#pragma unroll
-    for (int m = 0; m <= D; ++m) lam[m] = Q5<D>::lam(q, m);
-    s.phi[q][a] = fb_p2_phi<D>(a, lam);
+    s.phi[q][a] = fb_p2_phi<D>(a, s.qlam[q]);
   }
+  __syncthreads();
 }
 
-// gather the cell's coefficients of `u`, tabulate gradients and evaluate u, grad u at all points
+// geometry of the warp's cell: grad(lambda) to shared memory, returns the volume
+template <int D>
+__device__ __forceinline__ double mom_geometry(MomShared<D> &s, int wid, int lane, const int *__restrict__ cn,
+                                               const double *__restrict__ xyz) {
+  double X[(D + 1) * D];
+#pragma unroll
+  for (int v = 0; v <= D; ++v) {
+    const int64_t node = cn[v];
+#pragma unroll
+    for (int k = 0; k < D; ++k) X[v * D + k] = xyz[node * D + k];
+  }
+  double glam[D + 1][D], vol;
+  fb_geometry<D>(X, glam, vol);
+  if (lane == 0) {
+#pragma unroll
+    for (int m = 0; m <= D; ++m)
+#pragma unroll
+      for (int k = 0; k < D; ++k) s.glam[wid][m][k] = glam[m][k];
+  }
+  __syncwarp();
+  return vol;
+}
+
+// gather the cell's coefficients of `u`, tabulate basis gradients (first call per cell) and
+// evaluate u and grad u at all quadrature points
 template <int D>
 __device__ __forceinline__ void mom_phase_a(MomShared<D> &s, int wid, int lane, const int *__restrict__ cn,
-                                            const double *__restrict__ u, const double glam[D + 1][D], bool first,
-                                            bool need_grad) {
+                                            const double *__restrict__ u, bool first, bool need_grad) {
   constexpr int NL = Elem<D>::NL2, NQ = Q5<D>::NQ;
   if (lane < NL) {
     const int64_t node = cn[lane];
@@ -695,10 +743,8 @@ __device__ __forceinline__ void mom_phase_a(MomShared<D> &s, int wid, int lane, 
   if (first) {
     for (int t = lane; t < NQ * NL; t += 32) {
       const int q = t / NL, a = t - q * NL;
-      double lam[D + 1], g[D];
-#pragma unroll
-      for (int m = 0; m <= D; ++m) lam[m] = Q5<D>::lam(q, m);
-      fb_p2_grad<D>(a, lam, glam, g);
+      double g[D];
+      fb_p2_grad<D>(a, s.qlam[q], s.glam[wid], g);
 #pragma unroll
       for (int k = 0; k < D; ++k) s.g[wid][q][a][k] = g[k];
     }
@@ -736,70 +782,41 @@ __device__ __forceinline__ void cell_geometry(const int *__restrict__ cn, const 
   fb_geometry<D>(X, glam, vol);
 }
 
+// Cell part of one state's contribution to F1 (pressure_correction.py:169-190):
+//   F[(a,i)] += cm (u, phi_a e_i) - cr dt/rho R_cell(u; phi_a e_i)
+// called with (ui, 1, theta) every Newton iteration and with (u0, -1, 1-theta) once per step.
 template <int D>
 __global__ void __launch_bounds__(MOM_WARPS * 32)
-    k_momentum_F(int64_t nc, const int *__restrict__ cell_nodes, const double *__restrict__ xyz, MomentumArgs a,
+    k_momentum_F(int64_t nc, const int *__restrict__ cell_nodes, const double *__restrict__ xyz, double dt, double rho,
+                 double mu, const double *__restrict__ u, const double *__restrict__ p0, double cm, double cr,
                  double *__restrict__ F) {
   constexpr int NL = Elem<D>::NL2, NQ = Q5<D>::NQ;
   __shared__ MomShared<D> s;
-  mom_fill_phi<D>(s);
-  __syncthreads();
+  mom_fill_tables<D>(s);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t warp0 = blockIdx.x * (int64_t)MOM_WARPS + wid;
   const int64_t nwarps = (int64_t)gridDim.x * MOM_WARPS;
-  const double cdt = a.dt / a.rho;
+  const double cdt = cr * dt / rho;
+  const bool need_R = (cr != 0.0);
   for (int64_t c = warp0; c < nc; c += nwarps) {
     const int *cn = cell_nodes + c * NL;
-    double glam[D + 1][D], vol;
-    cell_geometry<D>(cn, xyz, glam, vol);
-    if (lane < NQ) {
+    const double vol = mom_geometry<D>(s, wid, lane, cn, xyz);
+    if (need_R && lane < NQ) {
       double p = 0.0;
 #pragma unroll
-      for (int v = 0; v <= D; ++v) p += a.p0[cn[v]] * Q5<D>::lam(lane, v);
+      for (int v = 0; v <= D; ++v) p += p0[cn[v]] * s.qlam[lane][v];
       s.p0q[wid][lane] = p;
     }
-    const int ta = lane / D, ti = lane - ta * D;
-    const bool active = lane < NL * D;
-    double acc = 0.0;
-    // ---- state ui: + (ui, v) - dt/rho theta R(ui)
-    mom_phase_a<D>(s, wid, lane, cn, a.ui, glam, true, a.theta != 0.0);
-    if (active) {
+    mom_phase_a<D>(s, wid, lane, cn, u, need_R, need_R);
+    if (lane < NL * D) {
+      const int ta = lane / D, ti = lane - ta * D;
+      double acc = 0.0;
       for (int q = 0; q < NQ; ++q) {
-        const double w = Q5<D>::w(q) * vol;
+        const double w = s.qw[q] * vol;
         const double pa = s.phi[q][ta];
-        acc += w * pa * s.uq[wid][q][ti];
-        if (a.theta != 0.0) {
-          double ga[D], u[D], gu[D][D];
-#pragma unroll
-          for (int k = 0; k < D; ++k) {
-            ga[k] = s.g[wid][q][ta][k];
-            u[k] = s.uq[wid][q][k];
-#pragma unroll
-            for (int l = 0; l < D; ++l) gu[k][l] = s.gu[wid][q][k][l];
-          }
-          acc -= cdt * a.theta * w * fb_rhs_point<D>(ti, a.rho, a.mu, pa, ga, u, gu, s.p0q[wid][q]);
-        }
-      }
-    }
-    __syncwarp();
-    // ---- state u0: - (u0, v) - dt/rho (1-theta) R(u0)
-    mom_phase_a<D>(s, wid, lane, cn, a.u0, glam, false, a.theta != 1.0);
-    if (active) {
-      for (int q = 0; q < NQ; ++q) {
-        const double w = Q5<D>::w(q) * vol;
-        const double pa = s.phi[q][ta];
-        acc -= w * pa * s.uq[wid][q][ti];
-        if (a.theta != 1.0) {
-          double ga[D], u[D], gu[D][D];
-#pragma unroll
-          for (int k = 0; k < D; ++k) {
-            ga[k] = s.g[wid][q][ta][k];
-            u[k] = s.uq[wid][q][k];
-#pragma unroll
-            for (int l = 0; l < D; ++l) gu[k][l] = s.gu[wid][q][k][l];
-          }
-          acc -= cdt * (1.0 - a.theta) * w * fb_rhs_point<D>(ti, a.rho, a.mu, pa, ga, u, gu, s.p0q[wid][q]);
-        }
+        acc += cm * w * pa * s.uq[wid][q][ti];
+        if (need_R)  // lane-dependent (a, i): index the shared tables directly
+          acc -= cdt * w * fb_rhs_point<D>(ti, rho, mu, pa, s.g[wid][q][ta], s.uq[wid][q], s.gu[wid][q], s.p0q[wid][q]);
       }
       atomicAdd(&F[(int64_t)cn[ta] * D + ti], acc);
     }
@@ -808,6 +825,7 @@ __global__ void __launch_bounds__(MOM_WARPS * 32)
 }
 
 // boundary-facet part of F: -dt/rho [ -(p0 n, v)_ds + mu ((grad u)^T n, v)_ds ]  (pressure_correction.py:142-143)
+// evaluated for the blended state theta*ui + (1-theta)*u0 (the facet terms are linear in u)
 template <int D>
 __global__ void k_momentum_F_facets(int64_t nbf, const int *__restrict__ bf_cell, const int *__restrict__ bf_local,
                                     const int *__restrict__ cell_nodes, const double *__restrict__ xyz, MomentumArgs a,
@@ -836,17 +854,38 @@ __global__ void k_momentum_F_facets(int64_t nbf, const int *__restrict__ bf_cell
   }
 }
 
-void assemble_momentum_F(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F) {
-  FB_CUDA(cudaMemsetAsync(F, 0, sizeof(double) * W.nnodes * W.dim, ctx->dev->stream));
+template <int D>
+static void momentum_F_cells(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, const double *u, double cm, double cr,
+                             double *F) {
   const int g = grid_for(W.nc * 32, MOM_WARPS * 32, ctx->dev->sm_count * 16);
+  FB_LAUNCH(ctx, k_momentum_F<D>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.xyz.p, a.dt, a.rho, a.mu, u, a.p0, cm, cr, F);
+}
+
+// F += state-u0 part: -(u0, v) - dt/rho (1-theta) R_cell(u0; v).  For backward Euler this is -M u0 and
+// the caller uses the assembled mass matrix instead.
+void assemble_momentum_F_old_state(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F) {
+  if (W.dim == 2)
+    momentum_F_cells<2>(ctx, W, a, a.u0, -1.0, 1.0 - a.theta, F);
+  else
+    momentum_F_cells<3>(ctx, W, a, a.u0, -1.0, 1.0 - a.theta, F);
+}
+
+// F += (ui, v) - dt/rho theta R_cell(ui; v) + boundary-facet terms of the blended state
+void assemble_momentum_F_new_state(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F) {
   const int gf = grid_for(W.nbf * W.nl * W.dim, 128, ctx->dev->sm_count * 16);
   if (W.dim == 2) {
-    FB_LAUNCH(ctx, k_momentum_F<2>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.xyz.p, a, F);
+    momentum_F_cells<2>(ctx, W, a, a.ui, 1.0, a.theta, F);
     if (W.nbf) FB_LAUNCH(ctx, k_momentum_F_facets<2>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.xyz.p, a, F);
   } else {
-    FB_LAUNCH(ctx, k_momentum_F<3>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.xyz.p, a, F);
+    momentum_F_cells<3>(ctx, W, a, a.ui, 1.0, a.theta, F);
     if (W.nbf) FB_LAUNCH(ctx, k_momentum_F_facets<3>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.xyz.p, a, F);
   }
+}
+
+void assemble_momentum_F(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F) {
+  FB_CUDA(cudaMemsetAsync(F, 0, sizeof(double) * W.nnodes * W.dim, ctx->dev->stream));
+  assemble_momentum_F_old_state(ctx, W, a, F);
+  assemble_momentum_F_new_state(ctx, W, a, F);
 }
 
 template <int D>
@@ -855,17 +894,15 @@ __global__ void __launch_bounds__(MOM_WARPS * 32)
                  const int *__restrict__ rowptr, const int *__restrict__ smap, MomentumArgs a, double *__restrict__ val) {
   constexpr int NL = Elem<D>::NL2, NQ = Q5<D>::NQ, NP = NL * NL, R = (NP + 31) / 32;
   __shared__ MomShared<D> s;
-  mom_fill_phi<D>(s);
-  __syncthreads();
+  mom_fill_tables<D>(s);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t warp0 = blockIdx.x * (int64_t)MOM_WARPS + wid;
   const int64_t nwarps = (int64_t)gridDim.x * MOM_WARPS;
   const double c1 = 0.5 * a.theta * a.dt, c2 = a.theta * a.dt * a.mu / a.rho;
   for (int64_t c = warp0; c < nc; c += nwarps) {
     const int *cn = cell_nodes + c * NL;
-    double glam[D + 1][D], vol;
-    cell_geometry<D>(cn, xyz, glam, vol);
-    mom_phase_a<D>(s, wid, lane, cn, a.ui, glam, true, true);
+    const double vol = mom_geometry<D>(s, wid, lane, cn, xyz);
+    mom_phase_a<D>(s, wid, lane, cn, a.ui, true, true);
     double acc[R][D][D];
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -874,7 +911,7 @@ __global__ void __launch_bounds__(MOM_WARPS * 32)
 #pragma unroll
         for (int j = 0; j < D; ++j) acc[r][i][j] = 0.0;
     for (int q = 0; q < NQ; ++q) {
-      const double w = Q5<D>::w(q) * vol;
+      const double w = s.qw[q] * vol;
       double u[D], gu[D][D];
 #pragma unroll
       for (int k = 0; k < D; ++k) {
@@ -947,6 +984,7 @@ __global__ void k_momentum_J_facets(int64_t nbf, const int *__restrict__ bf_cell
       for (int j = 0; j < D; ++j) atomicAdd(base + (int64_t)i * len + j, coef * B[i][j]);
   }
 }
+
 
 void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *Jval) {
   const int D = W.dim;
