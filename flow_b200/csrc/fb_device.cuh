@@ -35,7 +35,7 @@ int fb_clamp_grid(fb_ctx *ctx, const void *kernel, int grid, int block, size_t s
     (ctx)->launches++;                                                                               \
   } while (0)
 
-constexpr int FB_NSLOTS = 16;          // reduction result slots
+constexpr int FB_NSLOTS = 48;          // reduction result slots
 constexpr int FB_MAX_RED_BLOCKS = 2048;  // max blocks of a reducing kernel
 
 struct fb_device_state {

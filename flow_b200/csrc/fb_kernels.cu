@@ -10,6 +10,7 @@
 // compressed to one int per block.  SpMV lanes stream each scalar row contiguously
 // (coalesced) and share one x gather between the D rows.
 #include <algorithm>
+#include <cstdlib>
 #include <unordered_map>
 #include <vector>
 
@@ -414,6 +415,90 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Same product, U independent row chunks per lane in flight (index -> x gather -> values are
+// issued for all chunks before the FMAs) to cover DRAM latency with fewer resident warps.
+template <int D, int T, int DOT, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+    k_bspmv_u(int64_t nrows, const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val,
+              const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, double *partials,
+              unsigned int *counter, double *red, int slot, const int *__restrict__ flag) {
+  if (flag && *flag) return;
+  const int lane = threadIdx.x % T;
+  const int64_t group = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / T;
+  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / T;
+  double d[2] = {0.0, 0.0};
+  const int64_t nrows_pad = ((nrows + ngroups - 1) / ngroups) * ngroups;
+  for (int64_t row = group; row < nrows_pad; row += ngroups) {
+    double acc[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) acc[i] = 0.0;
+    if (row < nrows) {
+      const int r0 = rowptr[row];
+      const int len = (rowptr[row + 1] - r0) * D;
+      const double *v = val + (int64_t)r0 * (D * D);
+      for (int t0 = lane; t0 < len; t0 += T * U) {
+        int c[U];
+        double xv[U], a[U][D];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int t = t0 + u * T;
+          c[u] = (t < len) ? col[r0 + t / D] * D + (t % D) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) xv[u] = (c[u] >= 0) ? x[c[u]] : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int t = t0 + u * T;
+#pragma unroll
+          for (int i = 0; i < D; ++i) a[u][i] = (t < len) ? __ldcs(&v[i * len + t]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int i = 0; i < D; ++i) acc[i] += a[u][i] * xv[u];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int o = T / 2; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    if (row < nrows && lane < D) {
+      double yc = acc[0];
+#pragma unroll
+      for (int i = 1; i < D; ++i)
+        if (lane == i) yc = acc[i];
+      const int64_t dof = row * D + lane;
+      y[dof] = yc;
+      if (DOT >= 1) d[0] += w[dof] * yc;
+      if (DOT >= 2) d[1] += yc * yc;
+    }
+  }
+  if (DOT >= 1) {
+    if (DOT == 1) {
+      double v1[1] = {d[0]};
+      fb_grid_reduce<1>(v1, partials, counter, red, slot);
+    } else {
+      fb_grid_reduce<2>(d, partials, counter, red, slot);
+    }
+  }
+}
+
+template <int D, int T, int U, int MINB>
+static void launch_bspmv_u(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_mode, const double *w, int slot,
+                           const int *flag) {
+  fb_device_state *dv = ctx->dev;
+  const int block = 256;
+  const int64_t rows_per_block = block / T;
+  const int g = grid_for((A.nrows + rows_per_block - 1) / rows_per_block * block, block, dv->sm_count * 8);
+#define FB_BSU(DOT)                                                                                                    \
+  FB_LAUNCH(ctx, (k_bspmv_u<D, T, DOT, U, MINB>), g, block, 0, A.nrows, A.rowptr, A.col, A.val, x, y, w, dv->partials, \
+            dv->counter, dv->red, slot, flag)
+  if (dot_mode == 0) FB_BSU(0);
+  else if (dot_mode == 1) FB_BSU(1);
+  else FB_BSU(2);
+#undef FB_BSU
+}
+
 template <int NC, int T>
 static void launch_spmm(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_mode, const double *w, int slot,
                         const int *flag) {
@@ -448,8 +533,29 @@ static void launch_bspmv(fb_ctx *ctx, const LinOp &A, const double *x, double *y
 
 void spmv(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_mode, const double *w, int slot,
           const int *flag) {
-  if (A.block == 2) return launch_bspmv<2, 16>(ctx, A, x, y, dot_mode, w, slot, flag);
-  if (A.block == 3) return launch_bspmv<3, 32>(ctx, A, x, y, dot_mode, w, slot, flag);
+  if (A.block == 2) return launch_bspmv_u<2, 8, 4, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+  if (A.block == 3) {
+    // tuning knob (kernel variant); measured on B200 at n = 74 (profiles/r1_spmv_variants.txt):
+    // plain 1.76 ms, T=32/U=2 1.37 ms, T=16/U=3 1.28 ms, T=16/U=4 1.25 ms (= 8.2 GB DRAM traffic at 6.5 TB/s)
+    static const int V = getenv("FB_BSPMV_V") ? atoi(getenv("FB_BSPMV_V")) : 9;
+    switch (V) {
+      case 1: return launch_bspmv_u<3, 32, 2, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+      case 2: return launch_bspmv_u<3, 32, 3, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+      case 3: return launch_bspmv_u<3, 32, 2, 6>(ctx, A, x, y, dot_mode, w, slot, flag);
+      case 4: return launch_bspmv_u<3, 32, 3, 5>(ctx, A, x, y, dot_mode, w, slot, flag);
+      case 5: return launch_bspmv_u<3, 32, 1, 8>(ctx, A, x, y, dot_mode, w, slot, flag);
+      case 6: return launch_bspmv_u<3, 16, 3, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+      case 7: return launch_bspmv_u<3, 32, 4, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+      case 8: return launch_bspmv_u<3, 16, 2, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+      case 9: return launch_bspmv_u<3, 16, 4, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+      case 10: return launch_bspmv_u<3, 16, 6, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+      case 11: return launch_bspmv_u<3, 8, 4, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+      case 12: return launch_bspmv_u<3, 8, 6, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+      case 13: return launch_bspmv_u<3, 16, 3, 5>(ctx, A, x, y, dot_mode, w, slot, flag);
+      case 14: return launch_bspmv_u<3, 8, 8, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+      default: return launch_bspmv<3, 32>(ctx, A, x, y, dot_mode, w, slot, flag);
+    }
+  }
   // scalar: pick lanes per row from the average row length
   switch (A.ncomp) {
     case 1:

@@ -43,7 +43,7 @@ __global__ void k_cg_start(int64_t n, const double *__restrict__ b, const double
     const double ref2 = red[1] + ref_extra2;
     red[S_TOL2] = rtol * rtol * ref2;
     *iters = 0;
-    *flag = (ref2 == 0.0) ? 1 : ((ref2 != ref2) ? 2 : 0);
+    *flag = (ref2 == 0.0) ? 1 : ((ref2 != ref2) ? 3 : 0);
   }
 }
 
@@ -68,7 +68,7 @@ __global__ void k_cg_update(int64_t n, int it, const double *__restrict__ dinv, 
   if (last && threadIdx.x == 0) {
     const double zz = red[2 * nxt + 1];
     if (!(pAp > 0.0) || zz != zz) {
-      *flag = 2;
+      *flag = (zz != zz || pAp != pAp) ? 3 : 2;
       *iters = it + 1;
     } else if (zz <= red[S_TOL2]) {
       *flag = 1;
@@ -122,7 +122,7 @@ __global__ void k_bi_start(int64_t n, const double *__restrict__ b, double *r, d
     red[S_BTOL2] = atol * atol;
     *iters = 0;
     const double rr = red[bs(0, 1)];
-    *flag = (rr != rr) ? 2 : (rr <= atol * atol ? 1 : 0);
+    *flag = (rr != rr) ? 3 : (rr <= atol * atol ? 1 : 0);
   }
 }
 
@@ -162,7 +162,7 @@ __global__ void k_bi_half(int64_t nnodes, int it, const double *__restrict__ min
   const double rhv = red[bs(s, 2)];
   if (rhv == 0.0 || rhv != rhv) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-      *flag = 2;
+      *flag = (rhv != rhv) ? 3 : 2;
       *iters = it + 1;
     }
     return;  // every block takes this branch (rhv is grid-uniform)
@@ -203,7 +203,7 @@ __global__ void k_bi_update(int64_t n, int it, const double *__restrict__ phat, 
   if (last && threadIdx.x == 0) {
     const double rr = red[bs(nx, 1)];
     if (rr != rr) {
-      *flag = 2;
+      *flag = 3;
       *iters = it + 1;
     } else if (rr <= red[S_BTOL2]) {
       *flag = 1;
@@ -252,9 +252,11 @@ int krylov_pcg(fb_ctx *ctx, const LinOp &A, const double *dinv, const double *b,
   }
   if (iters) *iters = flag ? done : it;
   if (flag == 1) return FB_OK;
-  if (flag == 2) return FB_ENAN;
+  if (flag >= 2) return FB_ENAN;
   return FB_ENOCONV_KRYLOV;
 }
+
+constexpr int FB_BREAKDOWN = -100;  // internal: recoverable BiCGStab breakdown
 
 template <int D>
 static int bicgstab_impl(fb_ctx *ctx, const LinOp &A, const double *minv, const double *b, double *x, double atol,
@@ -284,13 +286,37 @@ static int bicgstab_impl(fb_ctx *ctx, const LinOp &A, const double *minv, const 
   }
   if (iters) *iters = flag ? done : it;
   if (flag == 1) return FB_OK;
-  if (flag == 2) return FB_ENAN;
+  if (flag == 2) return FB_BREAKDOWN;
+  if (flag == 3) return FB_ENAN;
   return FB_ENOCONV_KRYLOV;
 }
 
-int krylov_bicgstab(fb_ctx *ctx, const LinOp &A, const double *minv, const double *b, double *x, double atol, int maxit,
-                    int check_every, KrylovWork &w, int *iters) {
+static int bicgstab_once(fb_ctx *ctx, const LinOp &A, const double *minv, const double *b, double *x, double atol,
+                         int maxit, int check_every, KrylovWork &w, int *iters) {
   if (A.block == 2) return bicgstab_impl<2>(ctx, A, minv, b, x, atol, maxit, check_every, w, iters);
   if (A.block == 3) return bicgstab_impl<3>(ctx, A, minv, b, x, atol, maxit, check_every, w, iters);
   return bicgstab_impl<1>(ctx, A, minv, b, x, atol, maxit, check_every, w, iters);
+}
+
+// BiCGStab with restarts: on a (recoverable) breakdown the true residual b - A x is formed and the
+// iteration restarted for the correction, the usual remedy for rho ~ 0 / omega ~ 0.
+int krylov_bicgstab(fb_ctx *ctx, const LinOp &A, const double *minv, const double *b, double *x, double atol, int maxit,
+                    int check_every, KrylovWork &w, int *iters) {
+  const int64_t n = A.ndofs();
+  int total = 0, its = 0;
+  int status = bicgstab_once(ctx, A, minv, b, x, atol, maxit, check_every, w, &its);
+  total += its;
+  for (int restart = 0; status == FB_BREAKDOWN && restart < 20 && total < maxit; ++restart) {
+    w.v[7].alloc((size_t)n);
+    w.v[8].alloc((size_t)n);
+    double *rhs = w.v[7].p, *e = w.v[8].p;
+    spmv(ctx, A, x, rhs);
+    vec_axpby(ctx, rhs, 1.0, b, -1.0, rhs, n);  // rhs = b - A x
+    status = bicgstab_once(ctx, A, minv, rhs, e, atol, maxit - total, check_every, w, &its);
+    total += its;
+    vec_axpy(ctx, x, 1.0, e, n);
+  }
+  if (iters) *iters = total;
+  if (status == FB_BREAKDOWN) return FB_ENOCONV_KRYLOV;
+  return status;
 }

@@ -126,3 +126,41 @@ def test_krylov_mode_matches_lu():
         g[W.node_coords[:, 2] > 1 - 1e-12, 0] = 1.0
         out[lin] = st.step(1e-2, np.zeros(W.ndofs), np.zeros(st.P.nnodes), (bd, g.reshape(-1)[bd]), None, 1.0, 1e-2, tol=1e-10)
     assert np.linalg.norm(out["lu"][0] - out["krylov"][0]) / np.linalg.norm(out["lu"][0]) < 1e-8
+
+
+def test_stokes_order_oracle():
+    """tests/test_stokes.py:102-117 on the oracle: spatial orders of u and p exceed 1.9."""
+    from oracle import stokes as ostokes
+
+    pr = mp.stokes_guermond1()
+    hmax, ue, pe = [], [], []
+    for n in (8, 16):
+        mesh = fem.Mesh(*fem.unit_square_mesh(n, n, "left/right"))
+        W, P = fem.Space(mesh, 2, 2), fem.Space(mesh, 1, 1)
+        load = forms.expression_load_vector(W, pr["f"], mp.MAX_DEGREE)
+        ubd, pbd = W.boundary_dofs(), P.boundary_dofs()
+        u, p = ostokes.solve(mesh, pr["mu"], load, (ubd, util.interpolate(W, pr["u"])[ubd]), (pbd, util.interpolate(P, pr["p"])[pbd]))
+        hmax.append(mesh.hmax())
+        ue.append(util.errornorm(W, pr["u"], u))
+        pe.append(util.errornorm(P, pr["p"], p))
+    assert mp.compute_numerical_order_of_convergence(hmax, ue)[0] > 1.9
+    assert mp.compute_numerical_order_of_convergence(hmax, pe)[0] > 1.9
+
+
+def test_heat_lumped_mass_and_maximum_principle():
+    """heat.py:39-45: vertex-lumped mass is diagonal with zero rows at P2 edge nodes; pure diffusion
+    with Dirichlet data between 293 and 320 stays inside that range for P1."""
+    from oracle import heat as oheat
+
+    mesh = fem.Mesh(*fem.unit_square_mesh(6, 6, "crossed"))
+    V2 = fem.Space(mesh, 2, 1)
+    M = forms.lumped_vertex_mass(V2).diagonal()
+    assert (M[: mesh.nv] > 0).all() and (M[mesh.nv:] == 0).all() and abs(M.sum() - 1.0) < 1e-14
+    V1 = fem.Space(mesh, 1, 1)
+    bd = V1.boundary_dofs()
+    vals = np.where(V1.node_coords[bd, 0] < 1e-12, 320.0, 293.0)
+    h = oheat.Heat(mesh, 1, None, 0.6, 1000.0, 4.0, (bd, vals))
+    th = np.full(V1.nnodes, 293.0)
+    for _ in range(3):
+        th = oheat.implicit_euler_step(h, th, 0.0, 10.0)
+    assert th.min() > 293.0 - 1e-9 and th.max() < 320.0 + 1e-9
