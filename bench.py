@@ -266,7 +266,7 @@ def main():
         msv, byt = C.c_double(), C.c_double()
         _lib.check(lib.fb_mat_bench_spmv(h, 1, 30, C.byref(msv), C.byref(byt)), ctx, "bench_spmv")
         ach = byt.value / (msv.value * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_bspmv<3,32> (momentum Jacobian SpMV)", "achieved": ach, "peak": peak,
+        roofline = {"bound": "hbm", "kernel": "k_bspmv_u<3,16,*,4,1> (momentum Jacobian block-CSR SpMV)", "achieved": ach, "peak": peak,
                     "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": which,
                     "algorithmic_bytes_per_launch": byt.value, "ms_per_launch": msv.value}
         for name, idx, nc in (("p1_stiffness_spmv", 0, 1), ("p2_mass_spmm3", 1, 3)):
@@ -299,6 +299,7 @@ def main():
                            "correction_cg": avg("correction_its")},
             "phase_ms": {"tentative": avg("ms_tentative"), "pressure": avg("ms_pressure"), "correction": avg("ms_correction"),
                          "assembly_J": avg("ms_assembly_J"), "momentum_solve": avg("ms_momentum_solve")},
+            "newton_residuals_last_step": timed[-1]["newton_residuals"],
             "setup_s": t_setup, "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
             "other_kernels": extra, "cpu_baseline": cpu,
         }

@@ -73,7 +73,9 @@ class NSStats(C.Structure):
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d["newton_residuals"] = [self.reserved[k] for k in range(min(8, self.newton_its + 1))]
+        return d
 
 
 # every exported symbol of include/flowb200.h with its signature

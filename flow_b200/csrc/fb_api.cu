@@ -644,6 +644,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
   };
   double r = residual();
   int newton = 0;
+  s.reserved[0] = r;  // reserved[k] = |F| after k Newton updates (first 8)
   const int mom_check = o.check_every > 0 ? o.check_every : 2;
   float ms;
   while (!(r < o.newton_atol)) {
@@ -678,6 +679,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     vec_axpy(ctx, ns->ui.p, -1.0, ns->delta.p, nu);
     ++newton;
     r = residual();
+    if (newton < 8) s.reserved[newton] = r;
     FB_CUDA(cudaEventElapsedTime(&ms, dv->ev[4], dv->ev[5]));
     s.ms_assembly_J += ms;
     FB_CUDA(cudaEventElapsedTime(&ms, dv->ev[5], dv->ev[10]));
