@@ -103,6 +103,13 @@ SIGNATURES = {
     "fb_space_node_coords": (C.c_int, [vp, C.POINTER(pd)]),
     "fb_space_boundary_nodes": (C.c_int, [vp, C.POINTER(pu8)]),
     "fb_space_pattern": (C.c_int, [vp, pi64, C.POINTER(pi64), C.POINTER(pi32)]),
+    "fb_mesh_set_boundary_facets": (C.c_int, [vp, i64, pi32, pi32]),
+    "fb_space_create_numbered": (C.c_int, [vp, C.c_int, C.c_int, pi32, i64, C.POINTER(vp)]),
+    "fb_space_set_halo": (C.c_int, [vp, C.c_int, pi32, pi64, pi32, pi64]),
+    "fb_comm_unique_id": (C.c_int, [vp]),
+    "fb_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+    "fb_comm_destroy": (C.c_int, [vp]),
+    "fb_space_halo_exchange": (C.c_int, [vp, C.c_int, pd]),
     "fb_assemble_mass": (C.c_int, [vp, C.POINTER(vp)]),
     "fb_assemble_stiffness": (C.c_int, [vp, C.POINTER(vp)]),
     "fb_assemble_lumped_mass": (C.c_int, [vp, pd]),

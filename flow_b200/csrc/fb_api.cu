@@ -240,6 +240,21 @@ int fb_assemble_lumped_mass(fb_space *space, double *diag_out) {
   FB_API_END
 }
 
+int fb_space_halo_exchange(fb_space *space, int ncomp, double *x) {
+  if (!space || !x || ncomp < 1 || ncomp > 3) return FB_EINVAL;
+  FB_NEED_DEVICE(space->mesh->ctx);
+  FB_API_BEGIN(space->mesh->ctx)
+  DevSpace *sp = dev_space(space);
+  cudaStream_t st = _ctx->dev->stream;
+  const int64_t n = sp->nnodes * ncomp;
+  DBuf<double> dx;
+  dx.upload(x, (size_t)n, st);
+  halo_exchange(_ctx, *sp, dx.p, ncomp);
+  FB_CUDA(cudaMemcpyAsync(x, dx.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(cudaStreamSynchronize(st));
+  FB_API_END
+}
+
 int fb_mat_destroy(fb_mat *mat) {
   delete mat;
   return FB_OK;
@@ -266,11 +281,12 @@ int fb_mat_spmv(fb_mat *mat, int ncomp, const double *x, double *y) {
   if (mat->block == 1 && (ncomp < 1 || ncomp > 3)) return fb_fail(mat->ctx, FB_EINVAL, "fb_mat_spmv: ncomp must be 1..3");
   FB_API_BEGIN(mat->ctx)
   LinOp A = make_linop(*mat, ncomp, nullptr);
-  const int64_t n = A.ndofs();
+  const int64_t n = A.nlocal_dofs();  // x and y are rank-local vectors (owned + ghost); y is valid on owned dofs
   DBuf<double> dx, dy;
   cudaStream_t st = _ctx->dev->stream;
   dx.upload(x, (size_t)n, st);
   dy.alloc((size_t)n);
+  dy.zero(st);
   spmv(_ctx, A, dx.p, dy.p);
   FB_CUDA(cudaMemcpyAsync(y, dy.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   FB_CUDA(cudaStreamSynchronize(st));
@@ -310,11 +326,11 @@ static int solve_cg_masked(fb_ctx *ctx, const fb_mat &M, int ncomp, double *b_de
                            int64_t nbc, const int64_t *bc_dofs_dev, const double *bc_vals_dev, double g2,
                            uint8_t *mask_dev, double *dinv_dev, double *xg_dev, double *tmp_dev, double rtol, int maxit,
                            int check_every, KrylovWork &kw, int *iters) {
-  const int64_t n = M.sp->nnodes * ncomp;
+  const int64_t n = M.sp->n_owned * ncomp;  // owned dofs
   LinOp Afull = make_linop(M, ncomp, nullptr);
   const uint8_t *mask = nullptr;
   if (nbc > 0) {
-    mask_build(ctx, mask_dev, n, bc_dofs_dev, nbc);
+    mask_build(ctx, mask_dev, M.sp->nnodes * ncomp, bc_dofs_dev, nbc);
     mask = mask_dev;
     // lift: b <- b - A xg on free rows, 0 on constrained rows
     vec_fill(ctx, xg_dev, 0.0, n);
@@ -376,7 +392,8 @@ struct fb_ns {
   fb_space *Wh = nullptr, *Ph = nullptr;
   DevSpace *W = nullptr, *P = nullptr;
   int D = 2;
-  int64_t nu = 0, np = 0;
+  int64_t nu = 0, np = 0;      // local sizes (owned + ghost dofs)
+  int64_t nu_o = 0, np_o = 0;  // owned dofs (== local on a single rank)
   fb_ns_opts opts;
   fb_mat Ap, Mu, J;
   DBuf<double> u0, p0, ui, p1, u1, F, Fconst, delta, load, ftmp, bp, bu, dinv_p, dinv_u, binv, tmp_u, tmp_p, xg_u, xg_p, Ap_bc;
@@ -432,7 +449,7 @@ static bool ns_build_load(fb_ns *ns, int forcing, const double *f0, const double
 
 static void ns_assemble_F(fb_ns *ns, const MomentumArgs &a, bool have_load) {
   assemble_momentum_F(ns->ctx, *ns->W, a, ns->F.p);
-  if (have_load) vec_axpy(ns->ctx, ns->F.p, -a.dt / a.rho, ns->load.p, ns->nu);
+  if (have_load) vec_axpy(ns->ctx, ns->F.p, -a.dt / a.rho, ns->load.p, ns->nu_o);
 }
 
 // Part of F1 that does not change during the Newton iteration:
@@ -443,12 +460,12 @@ static void ns_build_Fconst(fb_ns *ns, const MomentumArgs &a, bool have_load) {
   ns->Fconst.alloc((size_t)ns->nu);
   if (a.theta == 1.0) {
     spmv(ctx, make_linop(ns->Mu, ns->D, nullptr), a.u0, ns->tmp_u.p);
-    vec_axpby(ctx, ns->Fconst.p, -1.0, ns->tmp_u.p, 0.0, ns->tmp_u.p, ns->nu);
+    vec_axpby(ctx, ns->Fconst.p, -1.0, ns->tmp_u.p, 0.0, ns->tmp_u.p, ns->nu_o);
   } else {
     ns->Fconst.zero(ctx->dev->stream);
     assemble_momentum_F_old_state(ctx, *ns->W, a, ns->Fconst.p);
   }
-  if (have_load) vec_axpy(ctx, ns->Fconst.p, -a.dt / a.rho, ns->load.p, ns->nu);
+  if (have_load) vec_axpy(ctx, ns->Fconst.p, -a.dt / a.rho, ns->load.p, ns->nu_o);
 }
 
 extern "C" {
@@ -488,6 +505,8 @@ int fb_ns_create(fb_space *Wsp, fb_space *Psp, const fb_ns_opts *opts, fb_ns **o
   ns->D = Wsp->mesh->dim;
   ns->nu = Wsp->nnodes * ns->D;
   ns->np = Psp->nnodes;
+  ns->nu_o = Wsp->n_owned * ns->D;
+  ns->np_o = Psp->n_owned;
   if (opts)
     ns->opts = *opts;
   else
@@ -535,7 +554,7 @@ int fb_ns_residual(fb_ns *ns, double dt, double rho, double mu, double theta, co
   ns_upload(ns, ns->ui, ui, ns->nu, false);
   ns_upload(ns, ns->u0, u0, ns->nu, false);
   ns_upload(ns, ns->p0, p0, ns->np, false);
-  MomentumArgs a{dt, rho, mu, theta, ns->ui.p, ns->u0.p, ns->p0.p};
+  MomentumArgs a{dt, rho, mu, theta, ns->ui.p, ns->u0.p, ns->p0.p, ns->P->cell_nodes.p};
   bool have_load = false;
   if (load) {
     ns_upload(ns, ns->load, load, ns->nu, false);
@@ -570,7 +589,7 @@ int fb_ns_correction_rhs(fb_ns *ns, double dt, double rho, double mu, int rotati
   ns_upload(ns, ns->p0, p0, ns->np, false);
   ns_upload(ns, ns->p1, p1, ns->np, false);
   spmv(_ctx, make_linop(ns->Mu, ns->D, nullptr), ns->ui.p, ns->bu.p);
-  assemble_correction_grad(_ctx, *ns->W, dt, rho, mu, rotational, ns->ui.p, ns->p1.p, ns->p0.p, ns->bu.p);
+  assemble_correction_grad(_ctx, *ns->W, *ns->P, dt, rho, mu, rotational, ns->ui.p, ns->p1.p, ns->p0.p, ns->bu.p);
   FB_CUDA(cudaMemcpyAsync(b_out, ns->bu.p, sizeof(double) * ns->nu, cudaMemcpyDeviceToHost, st));
   FB_CUDA(cudaStreamSynchronize(st));
   FB_API_END
@@ -601,7 +620,8 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
   const int rotational = (flags & FB_ROTATIONAL) ? 1 : 0;
   const double theta = scheme == FB_FORWARD_EULER ? 0.0 : (scheme == FB_BACKWARD_EULER ? 1.0 : 0.5);
   const int D = ns->D;
-  const int64_t nu = ns->nu, np = ns->np;
+  const int64_t nu = ns->nu, np = ns->np;        // local (owned + ghost)
+  const int64_t nu_o = ns->nu_o, np_o = ns->np_o;  // owned: vector kernels and dots run over these
   const fb_ns_opts &o = ns->opts;
   const int64_t launches0 = ctx->launches;
   fb_ns_stats s;
@@ -613,22 +633,29 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     ns->p0.zero(st);  // pressure_correction.py:545
   else
     ns_upload(ns, ns->p0, p0, np, dev);
+  // distributed: refresh the ghost copies of the incoming state (callers need not keep them current)
+  halo_exchange(ctx, *ns->W, ns->u0.p, D);
+  halo_exchange(ctx, *ns->P, ns->p0.p, 1);
   const bool have_load = ns_build_load(ns, forcing, f0, f1, theta, dev);
+  // Dirichlet lists cover all LOCAL dofs (ghost copies included) so that masks and identity rows are
+  // consistent on every rank; the norms below count owned dofs only
   double g2u = 0.0, g2p = 0.0;
   if (n_ubc > 0) {
     ns->ubc_dofs.upload(ubc_dofs, (size_t)n_ubc, st);
     ns->ubc_vals.upload(ubc_vals, (size_t)n_ubc, st);
-    for (int64_t i = 0; i < n_ubc; ++i) g2u += ubc_vals[i] * ubc_vals[i];
+    for (int64_t i = 0; i < n_ubc; ++i)
+      if (ubc_dofs[i] < nu_o) g2u += ubc_vals[i] * ubc_vals[i];
   }
   if (n_pbc > 0) {
     ns->pbc_dofs.upload(pbc_dofs, (size_t)n_pbc, st);
     ns->pbc_vals.upload(pbc_vals, (size_t)n_pbc, st);
-    for (int64_t i = 0; i < n_pbc; ++i) g2p += pbc_vals[i] * pbc_vals[i];
+    for (int64_t i = 0; i < n_pbc; ++i)
+      if (pbc_dofs[i] < np_o) g2p += pbc_vals[i] * pbc_vals[i];
   }
 
   // ---- tentative velocity: Newton on F1(ui) = 0 (pressure_correction.py:147-255)
   FB_CUDA(cudaMemcpyAsync(ns->ui.p, ns->u0.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));  // :220
-  MomentumArgs ma{dt, rho, mu, theta, ns->ui.p, ns->u0.p, ns->p0.p};
+  MomentumArgs ma{dt, rho, mu, theta, ns->ui.p, ns->u0.p, ns->p0.p, ns->P->cell_nodes.p};
   ns_build_Fconst(ns, ma, have_load);
   auto residual = [&]() {
     FB_CUDA(cudaEventRecord(dv->ev[8], st));
@@ -636,7 +663,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     assemble_momentum_F_new_state(ctx, *ns->W, ma, ns->F.p);
     bc_residual(ctx, ns->F.p, ns->ui.p, ns->ubc_dofs.p, ns->ubc_vals.p, n_ubc);
     FB_CUDA(cudaEventRecord(dv->ev[9], st));
-    const double nrm = vec_norm2_sync(ctx, ns->F.p, nu);
+    const double nrm = vec_norm2_sync(ctx, ns->F.p, nu_o);
     float t = 0;
     FB_CUDA(cudaEventElapsedTime(&t, dv->ev[8], dv->ev[9]));
     s.ms_assembly_F += t;
@@ -668,7 +695,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     if (lifted) lift_identity_rows(ctx, Jop, ns->F.p, ns->ubc_dofs.p, n_ubc, ns->xg_u.p, ns->tmp_u.p);
     int status = krylov_bicgstab(ctx, Jop, ns->binv.p, ns->F.p, ns->delta.p, atol_inner, o.momentum_maxit, mom_check,
                                  ns->kw_u, &its);
-    if (lifted) vec_axpy(ctx, ns->delta.p, 1.0, ns->xg_u.p, nu);
+    if (lifted) vec_axpy(ctx, ns->delta.p, 1.0, ns->xg_u.p, nu_o);
     s.momentum_its += its;
     FB_CUDA(cudaEventRecord(dv->ev[10], st));
     if (status != FB_OK) {
@@ -676,7 +703,8 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
       snprintf(buf, sizeof buf, "momentum Krylov solver failed after %d iterations (%s)", its, fb_status_string(status));
       return fb_fail(ctx, status == FB_ENAN ? FB_ENAN : FB_ENOCONV_KRYLOV, buf);
     }
-    vec_axpy(ctx, ns->ui.p, -1.0, ns->delta.p, nu);
+    vec_axpy(ctx, ns->ui.p, -1.0, ns->delta.p, nu_o);
+    halo_exchange(ctx, *ns->W, ns->ui.p, D);  // the next assembly reads ui on ghost nodes
     ++newton;
     r = residual();
     if (newton < 8) s.reserved[newton] = r;
@@ -700,7 +728,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     vec_fill(ctx, ns->xg_p.p, 0.0, np);
     vec_set_at(ctx, ns->xg_p.p, ns->pbc_dofs.p, ns->pbc_vals.p, n_pbc);
     spmv(ctx, make_linop(ns->Ap, 1, nullptr), ns->xg_p.p, ns->tmp_p.p);
-    vec_axpy(ctx, ns->bp.p, -1.0, ns->tmp_p.p, np);
+    vec_axpy(ctx, ns->bp.p, -1.0, ns->tmp_p.p, np_o);
     vec_set_at(ctx, ns->bp.p, ns->pbc_dofs.p, ns->pbc_vals.p, n_pbc);
     FB_CUDA(cudaMemcpyAsync(ns->Ap_bc.p, ns->Ap.val.p, sizeof(double) * ns->P->nnz, cudaMemcpyDeviceToDevice, st));
     bc_symmetric_scalar(ctx, *ns->P, ns->Ap_bc.p, ns->mask_p.p);
@@ -720,11 +748,12 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     snprintf(buf, sizeof buf, "pressure CG failed after %d iterations (%s)", s.pressure_its, fb_status_string(status));
     return fb_fail(ctx, status == FB_ENAN ? FB_ENAN : FB_ENOCONV_KRYLOV, buf);
   }
+  halo_exchange(ctx, *ns->P, ns->p1.p, 1);  // the correction assembly reads p1 on ghost vertices
   FB_CUDA(cudaEventRecord(dv->ev[2], st));
 
   // ---- velocity correction (pressure_correction.py:436-465)
   spmv(ctx, make_linop(ns->Mu, D, nullptr), ns->ui.p, ns->bu.p);
-  assemble_correction_grad(ctx, *ns->W, dt, rho, mu, rotational, ns->ui.p, ns->p1.p, ns->p0.p, ns->bu.p);
+  assemble_correction_grad(ctx, *ns->W, *ns->P, dt, rho, mu, rotational, ns->ui.p, ns->p1.p, ns->p0.p, ns->bu.p);
   status = solve_cg_masked(ctx, ns->Mu, D, ns->bu.p, ns->u1.p, n_ubc, ns->ubc_dofs.p, ns->ubc_vals.p, g2u, ns->mask_u.p,
                            ns->dinv_u.p, ns->xg_u.p, ns->tmp_u.p, tol, o.correction_maxit,
                            o.check_every > 0 ? o.check_every : 10, ns->kw_u, &s.correction_its);
@@ -735,6 +764,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     return fb_fail(ctx, status == FB_ENAN ? FB_ENAN : FB_ENOCONV_KRYLOV, buf);
   }
   (void)g2p;
+  halo_exchange(ctx, *ns->W, ns->u1.p, D);  // hand back a state whose ghost copies are current
   const cudaMemcpyKind back = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   FB_CUDA(cudaMemcpyAsync(u1, ns->u1.p, sizeof(double) * nu, back, st));
   FB_CUDA(cudaMemcpyAsync(p1, ns->p1.p, sizeof(double) * np, back, st));

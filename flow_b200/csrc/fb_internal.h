@@ -8,11 +8,14 @@
 
 struct fb_device_state;  // defined in fb_device.cuh (CUDA units only)
 
+struct fb_comm;  // NCCL communicator state (fb_comm.cu)
+
 struct fb_ctx {
   int device = -1;
   std::string err;
   fb_device_state *dev = nullptr;  // null for host-only contexts
   int64_t launches = 0;
+  fb_comm *comm = nullptr;  // null: single rank
 };
 
 struct fb_mesh {
@@ -37,6 +40,12 @@ struct fb_space {
   std::vector<uint8_t> bnode;       // nnodes
   std::vector<int64_t> indptr;      // node-level pattern, built lazily
   std::vector<int32_t> indices;
+  // distributed runs: nodes [0, n_owned) are owned by this rank, [n_owned, nnodes) are ghosts
+  // grouped by owner; halo plan per neighbour rank
+  int64_t n_owned = 0;
+  std::vector<int32_t> halo_ranks;
+  std::vector<int64_t> halo_send_ptr, halo_recv_ptr;  // nneigh + 1 (recv offsets relative to n_owned)
+  std::vector<int32_t> halo_send_nodes;
   void *dev = nullptr;  // DeviceSpace*
 };
 

@@ -187,12 +187,18 @@ void dev_space_build(fb_space *s, DevSpace &d) {
     throw fb_cuda_error(FB_EINVAL, "pattern too large for one GPU (partition the mesh)");
   d.xyz.upload(m->xyz.data(), m->xyz.size(), st);
   d.cell_nodes.upload(s->cell_nodes.data(), s->cell_nodes.size(), st);
+  d.cells.upload(m->cells.data(), m->cells.size(), st);
   std::vector<int> rp(s->nnodes + 1);
   for (int64_t i = 0; i <= s->nnodes; ++i) rp[i] = (int)s->indptr[i];
   d.rowptr.upload(rp.data(), rp.size(), st);
   d.col.upload(s->indices.data(), s->indices.size(), st);
   d.diag.alloc(s->nnodes);
   d.smap.alloc((size_t)d.nc * d.nl * d.nl);
+  d.n_owned = s->n_owned;
+  d.halo_ranks.assign(s->halo_ranks.begin(), s->halo_ranks.end());
+  d.halo_send_ptr = s->halo_send_ptr;
+  d.halo_recv_ptr = s->halo_recv_ptr;
+  if (!s->halo_send_nodes.empty()) d.halo_send_nodes.upload(s->halo_send_nodes.data(), s->halo_send_nodes.size(), st);
   d.nbf = (int64_t)m->bf_cell.size();
   d.bf_cell.upload(m->bf_cell.data(), m->bf_cell.size(), st);
   d.bf_local.upload(m->bf_local.data(), m->bf_local.size(), st);
@@ -206,7 +212,9 @@ LinOp make_linop(const fb_mat &m, int ncomp, const uint8_t *mask) {
   LinOp A;
   A.block = m.block;
   A.ncomp = m.block > 1 ? 1 : ncomp;
-  A.nrows = m.sp->nnodes;
+  A.nrows = m.sp->n_owned;
+  A.nlocal = m.sp->nnodes;
+  A.halo = (fb_is_distributed(m.ctx) && !m.sp->halo_ranks.empty()) ? m.sp : nullptr;
   A.rowptr = m.sp->rowptr.p;
   A.col = m.sp->col.p;
   A.val = m.val.p;
@@ -218,7 +226,7 @@ LinOp make_linop(const fb_mat &m, int ncomp, const uint8_t *mask) {
 // constant operators: one thread per (cell, a, b)
 // =============================================================================
 template <int D, int DEG, int KIND>
-__global__ void k_assemble_constant(int64_t nc, const int *__restrict__ cell_nodes, const double *__restrict__ xyz,
+__global__ void k_assemble_constant(int64_t nc, const int *__restrict__ cells, const double *__restrict__ xyz,
                                     const int *__restrict__ smap, double *__restrict__ val) {
   constexpr int NL = DEG == 1 ? Elem<D>::NL1 : Elem<D>::NL2;
   const int64_t total = nc * NL * NL;
@@ -229,7 +237,7 @@ __global__ void k_assemble_constant(int64_t nc, const int *__restrict__ cell_nod
     double X[(D + 1) * D];
 #pragma unroll
     for (int v = 0; v <= D; ++v) {
-      const int node = cell_nodes[c * NL + v];
+      const int node = cells[c * (D + 1) + v];
 #pragma unroll
       for (int k = 0; k < D; ++k) X[v * D + k] = xyz[(int64_t)node * D + k];
     }
@@ -269,7 +277,7 @@ void assemble_constant(fb_ctx *ctx, DevSpace &sp, int kind, double *val) {
   FB_CUDA(cudaMemsetAsync(val, 0, sizeof(double) * sp.nnz, ctx->dev->stream));
   const int g = grid_for(sp.nc * sp.nl * sp.nl, 256, 148 * 32);
 #define FB_AC(D, DEG, KIND)                                                                                     \
-  FB_LAUNCH(ctx, (k_assemble_constant<D, DEG, KIND>), g, 256, 0, sp.nc, sp.cell_nodes.p, sp.xyz.p, sp.smap.p, val)
+  FB_LAUNCH(ctx, (k_assemble_constant<D, DEG, KIND>), g, 256, 0, sp.nc, sp.cells.p, sp.xyz.p, sp.smap.p, val)
   if (sp.dim == 2 && sp.degree == 1 && kind == 0) FB_AC(2, 1, 0);
   else if (sp.dim == 2 && sp.degree == 1) FB_AC(2, 1, 1);
   else if (sp.dim == 2 && kind == 0) FB_AC(2, 2, 0);
@@ -282,14 +290,14 @@ void assemble_constant(fb_ctx *ctx, DevSpace &sp, int kind, double *val) {
 }
 
 template <int D>
-__global__ void k_lumped(int64_t nc, int nl, const int *__restrict__ cell_nodes, const double *__restrict__ xyz,
-                         double *__restrict__ diag) {
+__global__ void k_lumped(int64_t nc, int nl, const int *__restrict__ cell_nodes, const int *__restrict__ cells,
+                         const double *__restrict__ xyz, double *__restrict__ diag) {
   for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
     double X[(D + 1) * D];
     int nodes[D + 1];
     for (int v = 0; v <= D; ++v) {
       nodes[v] = cell_nodes[c * nl + v];
-      for (int k = 0; k < D; ++k) X[v * D + k] = xyz[(int64_t)nodes[v] * D + k];
+      for (int k = 0; k < D; ++k) X[v * D + k] = xyz[(int64_t)cells[c * (D + 1) + v] * D + k];
     }
     double glam[D + 1][D], vol;
     fb_geometry<D>(X, glam, vol);
@@ -301,9 +309,9 @@ void assemble_lumped(fb_ctx *ctx, DevSpace &sp, double *diag) {
   FB_CUDA(cudaMemsetAsync(diag, 0, sizeof(double) * sp.nnodes, ctx->dev->stream));
   const int g = grid_for(sp.nc, 256, 148 * 16);
   if (sp.dim == 2)
-    FB_LAUNCH(ctx, k_lumped<2>, g, 256, 0, sp.nc, sp.nl, sp.cell_nodes.p, sp.xyz.p, diag);
+    FB_LAUNCH(ctx, k_lumped<2>, g, 256, 0, sp.nc, sp.nl, sp.cell_nodes.p, sp.cells.p, sp.xyz.p, diag);
   else
-    FB_LAUNCH(ctx, k_lumped<3>, g, 256, 0, sp.nc, sp.nl, sp.cell_nodes.p, sp.xyz.p, diag);
+    FB_LAUNCH(ctx, k_lumped<3>, g, 256, 0, sp.nc, sp.nl, sp.cell_nodes.p, sp.cells.p, sp.xyz.p, diag);
 }
 
 // =============================================================================
@@ -531,8 +539,20 @@ static void launch_bspmv(fb_ctx *ctx, const LinOp &A, const double *x, double *y
 #undef FB_BS
 }
 
+static void spmv_local(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_mode, const double *w, int slot,
+                       const int *flag);
+
 void spmv(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_mode, const double *w, int slot,
           const int *flag) {
+  // distributed: the ghost entries of x are refreshed from their owners first (x is logically const:
+  // only its ghost copies are rewritten), the fused dot products are summed over the ranks afterwards
+  if (A.halo) halo_exchange(ctx, *A.halo, const_cast<double *>(x), A.dofs_per_node());
+  spmv_local(ctx, A, x, y, dot_mode, w, slot, flag);
+  if (dot_mode > 0) fb_allreduce_slots(ctx, slot, dot_mode);
+}
+
+static void spmv_local(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_mode, const double *w, int slot,
+                       const int *flag) {
   if (A.block == 2) return launch_bspmv_u<2, 8, 4, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
   if (A.block == 3) {
     // tuning knob (kernel variant); measured on B200 at n = 74 (profiles/r1_spmv_variants.txt):
@@ -620,6 +640,7 @@ void vec_axpby(fb_ctx *ctx, double *z, double a, const double *x, double b, cons
 void vec_dot(fb_ctx *ctx, const double *x, const double *y, int64_t n, int slot) {
   fb_device_state *dv = ctx->dev;
   FB_LAUNCH(ctx, k_dot, vgrid(ctx, n), 256, 0, x, y, n, dv->partials, dv->counter, dv->red, slot);
+  fb_allreduce_slots(ctx, slot, 1);
 }
 double vec_norm2_sync(fb_ctx *ctx, const double *x, int64_t n) {
   fb_device_state *dv = ctx->dev;
@@ -724,7 +745,7 @@ __global__ void k_jacobi_scalar(int64_t n, int ncomp, const int *__restrict__ di
 }
 
 void jacobi_setup_scalar(fb_ctx *ctx, const DevSpace &sp, const double *val, int ncomp, const uint8_t *mask, double *dinv) {
-  FB_LAUNCH(ctx, k_jacobi_scalar, vgrid(ctx, sp.nnodes * ncomp), 256, 0, sp.nnodes, ncomp, sp.diag.p, val, mask, dinv);
+  FB_LAUNCH(ctx, k_jacobi_scalar, vgrid(ctx, sp.n_owned * ncomp), 256, 0, sp.n_owned, ncomp, sp.diag.p, val, mask, dinv);
 }
 
 template <int D>
@@ -769,11 +790,11 @@ __global__ void k_jacobi_blocked(int64_t n, const int *__restrict__ rowptr, cons
 }
 
 void jacobi_setup_blocked(fb_ctx *ctx, const DevSpace &sp, int D, const double *val, int block_mode, double *binv) {
-  const int g = vgrid(ctx, sp.nnodes);
+  const int g = vgrid(ctx, sp.n_owned);
   if (D == 2)
-    FB_LAUNCH(ctx, k_jacobi_blocked<2>, g, 256, 0, sp.nnodes, sp.rowptr.p, sp.diag.p, val, block_mode, binv);
+    FB_LAUNCH(ctx, k_jacobi_blocked<2>, g, 256, 0, sp.n_owned, sp.rowptr.p, sp.diag.p, val, block_mode, binv);
   else
-    FB_LAUNCH(ctx, k_jacobi_blocked<3>, g, 256, 0, sp.nnodes, sp.rowptr.p, sp.diag.p, val, block_mode, binv);
+    FB_LAUNCH(ctx, k_jacobi_blocked<3>, g, 256, 0, sp.n_owned, sp.rowptr.p, sp.diag.p, val, block_mode, binv);
 }
 
 // =============================================================================
@@ -893,9 +914,9 @@ __device__ __forceinline__ void cell_geometry(const int *__restrict__ cn, const 
 // called with (ui, 1, theta) every Newton iteration and with (u0, -1, 1-theta) once per step.
 template <int D>
 __global__ void __launch_bounds__(MOM_WARPS * 32)
-    k_momentum_F(int64_t nc, const int *__restrict__ cell_nodes, const double *__restrict__ xyz, double dt, double rho,
-                 double mu, const double *__restrict__ u, const double *__restrict__ p0, double cm, double cr,
-                 double *__restrict__ F) {
+    k_momentum_F(int64_t nc, const int *__restrict__ cell_nodes, const int *__restrict__ cells, const double *__restrict__ xyz, double dt, double rho,
+                 double mu, const double *__restrict__ u, const double *__restrict__ p0, const int *__restrict__ pcn, double cm,
+                 double cr, double *__restrict__ F) {
   constexpr int NL = Elem<D>::NL2, NQ = Q5<D>::NQ;
   __shared__ MomShared<D> s;
   mom_fill_tables<D>(s);
@@ -906,11 +927,11 @@ __global__ void __launch_bounds__(MOM_WARPS * 32)
   const bool need_R = (cr != 0.0);
   for (int64_t c = warp0; c < nc; c += nwarps) {
     const int *cn = cell_nodes + c * NL;
-    const double vol = mom_geometry<D>(s, wid, lane, cn, xyz);
+    const double vol = mom_geometry<D>(s, wid, lane, cells + c * (D + 1), xyz);
     if (need_R && lane < NQ) {
       double p = 0.0;
 #pragma unroll
-      for (int v = 0; v <= D; ++v) p += p0[cn[v]] * s.qlam[lane][v];
+      for (int v = 0; v <= D; ++v) p += p0[pcn[c * (D + 1) + v]] * s.qlam[lane][v];
       s.p0q[wid][lane] = p;
     }
     mom_phase_a<D>(s, wid, lane, cn, u, need_R, need_R);
@@ -934,7 +955,7 @@ __global__ void __launch_bounds__(MOM_WARPS * 32)
 // evaluated for the blended state theta*ui + (1-theta)*u0 (the facet terms are linear in u)
 template <int D>
 __global__ void k_momentum_F_facets(int64_t nbf, const int *__restrict__ bf_cell, const int *__restrict__ bf_local,
-                                    const int *__restrict__ cell_nodes, const double *__restrict__ xyz, MomentumArgs a,
+                                    const int *__restrict__ cell_nodes, const int *__restrict__ cells, const double *__restrict__ xyz, MomentumArgs a,
                                     double *__restrict__ F) {
   constexpr int NL = Elem<D>::NL2;
   const int64_t total = nbf * NL * D;
@@ -947,14 +968,14 @@ __global__ void k_momentum_F_facets(int64_t nbf, const int *__restrict__ bf_cell
     const int *cn = cell_nodes + c * NL;
     if (!fb_node_on_facet<D>(ta, f)) continue;
     double glam[D + 1][D], vol;
-    cell_geometry<D>(cn, xyz, glam, vol);
+    cell_geometry<D>(cells + c * (D + 1), xyz, glam, vol);
     double Ue[NL * D], p0e[D + 1];
     for (int b = 0; b < NL; ++b) {
       const int64_t node = cn[b];
       for (int k = 0; k < D; ++k)
         Ue[b * D + k] = a.theta * a.ui[node * D + k] + (1.0 - a.theta) * a.u0[node * D + k];
     }
-    for (int v = 0; v <= D; ++v) p0e[v] = a.p0[cn[v]];
+    for (int v = 0; v <= D; ++v) p0e[v] = a.p0[a.pcn[c * (D + 1) + v]];
     const double acc = fb_facet_F<D>(ta, ti, f, glam, vol, QF<D>::lam_ptr(), QF<D>::w_ptr(), QF<D>::NQ, Ue, p0e, a.mu);
     atomicAdd(&F[(int64_t)cn[ta] * D + ti], -(a.dt / a.rho) * acc);
   }
@@ -964,7 +985,7 @@ template <int D>
 static void momentum_F_cells(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, const double *u, double cm, double cr,
                              double *F) {
   const int g = grid_for(W.nc * 32, MOM_WARPS * 32, ctx->dev->sm_count * 16);
-  FB_LAUNCH(ctx, k_momentum_F<D>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.xyz.p, a.dt, a.rho, a.mu, u, a.p0, cm, cr, F);
+  FB_LAUNCH(ctx, k_momentum_F<D>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, a.dt, a.rho, a.mu, u, a.p0, a.pcn, cm, cr, F);
 }
 
 // F += state-u0 part: -(u0, v) - dt/rho (1-theta) R_cell(u0; v).  For backward Euler this is -M u0 and
@@ -981,10 +1002,10 @@ void assemble_momentum_F_new_state(fb_ctx *ctx, const DevSpace &W, const Momentu
   const int gf = grid_for(W.nbf * W.nl * W.dim, 128, ctx->dev->sm_count * 16);
   if (W.dim == 2) {
     momentum_F_cells<2>(ctx, W, a, a.ui, 1.0, a.theta, F);
-    if (W.nbf) FB_LAUNCH(ctx, k_momentum_F_facets<2>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.xyz.p, a, F);
+    if (W.nbf) FB_LAUNCH(ctx, k_momentum_F_facets<2>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.cells.p, W.xyz.p, a, F);
   } else {
     momentum_F_cells<3>(ctx, W, a, a.ui, 1.0, a.theta, F);
-    if (W.nbf) FB_LAUNCH(ctx, k_momentum_F_facets<3>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.xyz.p, a, F);
+    if (W.nbf) FB_LAUNCH(ctx, k_momentum_F_facets<3>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.cells.p, W.xyz.p, a, F);
   }
 }
 
@@ -996,7 +1017,7 @@ void assemble_momentum_F(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, 
 
 template <int D>
 __global__ void __launch_bounds__(MOM_WARPS * 32)
-    k_momentum_J(int64_t nc, const int *__restrict__ cell_nodes, const double *__restrict__ xyz,
+    k_momentum_J(int64_t nc, const int *__restrict__ cell_nodes, const int *__restrict__ cells, const double *__restrict__ xyz,
                  const int *__restrict__ rowptr, const int *__restrict__ smap, MomentumArgs a, double *__restrict__ val) {
   constexpr int NL = Elem<D>::NL2, NQ = Q5<D>::NQ, NP = NL * NL, R = (NP + 31) / 32;
   __shared__ MomShared<D> s;
@@ -1007,7 +1028,7 @@ __global__ void __launch_bounds__(MOM_WARPS * 32)
   const double c1 = 0.5 * a.theta * a.dt, c2 = a.theta * a.dt * a.mu / a.rho;
   for (int64_t c = warp0; c < nc; c += nwarps) {
     const int *cn = cell_nodes + c * NL;
-    const double vol = mom_geometry<D>(s, wid, lane, cn, xyz);
+    const double vol = mom_geometry<D>(s, wid, lane, cells + c * (D + 1), xyz);
     mom_phase_a<D>(s, wid, lane, cn, a.ui, true, true);
     double acc[R][D][D];
 #pragma unroll
@@ -1063,7 +1084,7 @@ __global__ void __launch_bounds__(MOM_WARPS * 32)
 // boundary-facet part of J: -theta dt/rho mu ((grad delta)^T n, v)_ds
 template <int D>
 __global__ void k_momentum_J_facets(int64_t nbf, const int *__restrict__ bf_cell, const int *__restrict__ bf_local,
-                                    const int *__restrict__ cell_nodes, const double *__restrict__ xyz,
+                                    const int *__restrict__ cell_nodes, const int *__restrict__ cells, const double *__restrict__ xyz,
                                     const int *__restrict__ rowptr, const int *__restrict__ smap, MomentumArgs a,
                                     double *__restrict__ val) {
   constexpr int NL = Elem<D>::NL2, NP = NL * NL;
@@ -1078,7 +1099,7 @@ __global__ void k_momentum_J_facets(int64_t nbf, const int *__restrict__ bf_cell
     const int *cn = cell_nodes + c * NL;
     if (!fb_node_on_facet<D>(ta, f)) continue;
     double glam[D + 1][D], vol;
-    cell_geometry<D>(cn, xyz, glam, vol);
+    cell_geometry<D>(cells + c * (D + 1), xyz, glam, vol);
     double B[D][D];
     fb_facet_J<D>(ta, tb, f, glam, vol, QF<D>::lam_ptr(), QF<D>::w_ptr(), QF<D>::NQ, B);
     const int I = cn[ta];
@@ -1098,14 +1119,14 @@ void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, 
   const int g = grid_for(W.nc * 32, MOM_WARPS * 32, ctx->dev->sm_count * 16);
   const int gf = grid_for(W.nbf * W.nl * W.nl, 128, ctx->dev->sm_count * 16);
   if (D == 2) {
-    FB_LAUNCH(ctx, k_momentum_J<2>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
+    FB_LAUNCH(ctx, k_momentum_J<2>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
     if (W.nbf && a.theta != 0.0)
-      FB_LAUNCH(ctx, k_momentum_J_facets<2>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.xyz.p,
+      FB_LAUNCH(ctx, k_momentum_J_facets<2>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.cells.p, W.xyz.p,
                 W.rowptr.p, W.smap.p, a, Jval);
   } else {
-    FB_LAUNCH(ctx, k_momentum_J<3>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
+    FB_LAUNCH(ctx, k_momentum_J<3>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
     if (W.nbf && a.theta != 0.0)
-      FB_LAUNCH(ctx, k_momentum_J_facets<3>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.xyz.p,
+      FB_LAUNCH(ctx, k_momentum_J_facets<3>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.cells.p, W.xyz.p,
                 W.rowptr.p, W.smap.p, a, Jval);
   }
 }
@@ -1114,20 +1135,21 @@ void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, 
 // pressure / correction right-hand sides: one thread per cell
 // =============================================================================
 template <int D>
-__global__ void k_pressure_rhs(int64_t nc, const int *__restrict__ cell_nodes, const double *__restrict__ xyz, double dt,
+__global__ void k_pressure_rhs(int64_t nc, const int *__restrict__ cell_nodes, const int *__restrict__ cells,
+                               const int *__restrict__ pcn, const double *__restrict__ xyz, double dt,
                                double rho, double mu, int rotational, const double *__restrict__ ui,
                                const double *__restrict__ p0, double *__restrict__ b) {
   constexpr int NL = Elem<D>::NL2;
   for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
     const int *cn = cell_nodes + c * NL;
     double glam[D + 1][D], vol;
-    cell_geometry<D>(cn, xyz, glam, vol);
+    cell_geometry<D>(cells + c * (D + 1), xyz, glam, vol);
     double Ue[NL * D], p0e[D + 1], be[D + 1];
     for (int a = 0; a < NL; ++a)
       for (int i = 0; i < D; ++i) Ue[a * D + i] = ui[(int64_t)cn[a] * D + i];
-    for (int v = 0; v <= D; ++v) p0e[v] = p0[cn[v]];
+    for (int v = 0; v <= D; ++v) p0e[v] = p0[pcn[c * (D + 1) + v]];
     fb_pressure_rhs_cell<D>(glam, vol, Q2<D>::lam_ptr(), Q2<D>::w_ptr(), Q2<D>::NQ, Ue, p0e, dt, rho, mu, rotational, be);
-    for (int v = 0; v <= D; ++v) atomicAdd(&b[cn[v]], be[v]);
+    for (int v = 0; v <= D; ++v) atomicAdd(&b[pcn[c * (D + 1) + v]], be[v]);
   }
 }
 
@@ -1136,25 +1158,26 @@ void assemble_pressure_rhs(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, do
   FB_CUDA(cudaMemsetAsync(b, 0, sizeof(double) * P.nnodes, ctx->dev->stream));
   const int g = grid_for(W.nc, 128, ctx->dev->sm_count * 32);
   if (W.dim == 2)
-    FB_LAUNCH(ctx, k_pressure_rhs<2>, g, 128, 0, W.nc, W.cell_nodes.p, W.xyz.p, dt, rho, mu, rotational, ui, p0, b);
+    FB_LAUNCH(ctx, k_pressure_rhs<2>, g, 128, 0, W.nc, W.cell_nodes.p, W.cells.p, P.cell_nodes.p, W.xyz.p, dt, rho, mu, rotational, ui, p0, b);
   else
-    FB_LAUNCH(ctx, k_pressure_rhs<3>, g, 128, 0, W.nc, W.cell_nodes.p, W.xyz.p, dt, rho, mu, rotational, ui, p0, b);
+    FB_LAUNCH(ctx, k_pressure_rhs<3>, g, 128, 0, W.nc, W.cell_nodes.p, W.cells.p, P.cell_nodes.p, W.xyz.p, dt, rho, mu, rotational, ui, p0, b);
 }
 
 template <int D>
-__global__ void k_correction_grad(int64_t nc, const int *__restrict__ cell_nodes, const double *__restrict__ xyz,
+__global__ void k_correction_grad(int64_t nc, const int *__restrict__ cell_nodes, const int *__restrict__ cells,
+                                  const int *__restrict__ pcn, const double *__restrict__ xyz,
                                   double dt, double rho, double mu, int rotational, const double *__restrict__ ui,
                                   const double *__restrict__ p1, const double *__restrict__ p0, double *__restrict__ b) {
   constexpr int NL = Elem<D>::NL2;
   for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
     const int *cn = cell_nodes + c * NL;
     double glam[D + 1][D], vol;
-    cell_geometry<D>(cn, xyz, glam, vol);
+    cell_geometry<D>(cells + c * (D + 1), xyz, glam, vol);
     double Ue[NL * D], dpe[D + 1], gphi[D];
     if (rotational)
       for (int a = 0; a < NL; ++a)
         for (int i = 0; i < D; ++i) Ue[a * D + i] = ui[(int64_t)cn[a] * D + i];
-    for (int v = 0; v <= D; ++v) dpe[v] = p1[cn[v]] - p0[cn[v]];
+    for (int v = 0; v <= D; ++v) dpe[v] = p1[pcn[c * (D + 1) + v]] - p0[pcn[c * (D + 1) + v]];
     fb_correction_gradphi<D>(glam, Ue, dpe, mu, rotational, gphi);
     const double coef = -dt / rho * vol;
     for (int a = 0; a < NL; ++a) {
@@ -1165,13 +1188,13 @@ __global__ void k_correction_grad(int64_t nc, const int *__restrict__ cell_nodes
   }
 }
 
-void assemble_correction_grad(fb_ctx *ctx, const DevSpace &W, double dt, double rho, double mu, int rotational,
-                              const double *ui, const double *p1, const double *p0, double *b) {
+void assemble_correction_grad(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, double dt, double rho, double mu,
+                              int rotational, const double *ui, const double *p1, const double *p0, double *b) {
   const int g = grid_for(W.nc, 128, ctx->dev->sm_count * 32);
   if (W.dim == 2)
-    FB_LAUNCH(ctx, k_correction_grad<2>, g, 128, 0, W.nc, W.cell_nodes.p, W.xyz.p, dt, rho, mu, rotational, ui, p1, p0, b);
+    FB_LAUNCH(ctx, k_correction_grad<2>, g, 128, 0, W.nc, W.cell_nodes.p, W.cells.p, P.cell_nodes.p, W.xyz.p, dt, rho, mu, rotational, ui, p1, p0, b);
   else
-    FB_LAUNCH(ctx, k_correction_grad<3>, g, 128, 0, W.nc, W.cell_nodes.p, W.xyz.p, dt, rho, mu, rotational, ui, p1, p0, b);
+    FB_LAUNCH(ctx, k_correction_grad<3>, g, 128, 0, W.nc, W.cell_nodes.p, W.cells.p, P.cell_nodes.p, W.xyz.p, dt, rho, mu, rotational, ui, p1, p0, b);
 }
 
 // =============================================================================
@@ -1179,7 +1202,7 @@ void assemble_correction_grad(fb_ctx *ctx, const DevSpace &W, double dt, double 
 // =============================================================================
 template <int D, int DEG>
 __global__ void k_heat(int64_t nc, const int *__restrict__ cell_nodes, const int *__restrict__ wcell_nodes,
-                       const double *__restrict__ xyz, const int *__restrict__ smap, const double *__restrict__ conv,
+                       const int *__restrict__ cells, const double *__restrict__ xyz, const int *__restrict__ smap, const double *__restrict__ conv,
                        double kdiff, double *__restrict__ val) {
   constexpr int NL = DEG == 1 ? Elem<D>::NL1 : Elem<D>::NL2;
   constexpr int NLW = Elem<D>::NL2;
@@ -1190,7 +1213,7 @@ __global__ void k_heat(int64_t nc, const int *__restrict__ cell_nodes, const int
     const int a = r / NL, b = r - a * NL;
     const int *cn = cell_nodes + c * NL;
     double glam[D + 1][D], vol;
-    cell_geometry<D>(cn, xyz, glam, vol);
+    cell_geometry<D>(cells + c * (D + 1), xyz, glam, vol);
     double e = 0.0;
     for (int q = 0; q < Q5<D>::NQ; ++q) {
       double lam[D + 1], ga[D], gb[D];
@@ -1230,7 +1253,7 @@ void assemble_heat(fb_ctx *ctx, const DevSpace &V, const DevSpace *W, const doub
   const int *wcn = W ? W->cell_nodes.p : nullptr;
   if (!W) conv = nullptr;
 #define FB_HT(D, DEG) \
-  FB_LAUNCH(ctx, (k_heat<D, DEG>), g, 128, 0, V.nc, V.cell_nodes.p, wcn, V.xyz.p, V.smap.p, conv, kdiff, val)
+  FB_LAUNCH(ctx, (k_heat<D, DEG>), g, 128, 0, V.nc, V.cell_nodes.p, wcn, V.cells.p, V.xyz.p, V.smap.p, conv, kdiff, val)
   if (V.dim == 2 && V.degree == 1) FB_HT(2, 1);
   else if (V.dim == 2) FB_HT(2, 2);
   else if (V.degree == 1) FB_HT(3, 1);
@@ -1242,13 +1265,14 @@ void assemble_heat(fb_ctx *ctx, const DevSpace &V, const DevSpace *W, const doub
 // Stokes divergence block, matrix-free (stokes.py:40-42):  (B u)_a = -int psi_a div u,  (B^T p)_(b,j) = -int p d_j phi_b
 // =============================================================================
 template <int D, int TRANSPOSE>
-__global__ void k_stokes_div(int64_t nc, const int *__restrict__ cell_nodes, const double *__restrict__ xyz,
+__global__ void k_stokes_div(int64_t nc, const int *__restrict__ cell_nodes, const int *__restrict__ cells,
+                             const int *__restrict__ pcn, const double *__restrict__ xyz,
                              const double *__restrict__ in, double *__restrict__ out) {
   constexpr int NL = Elem<D>::NL2;
   for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
     const int *cn = cell_nodes + c * NL;
     double glam[D + 1][D], vol;
-    cell_geometry<D>(cn, xyz, glam, vol);
+    cell_geometry<D>(cells + c * (D + 1), xyz, glam, vol);
     if (!TRANSPOSE) {
       double be[D + 1];
       for (int v = 0; v <= D; ++v) be[v] = 0.0;
@@ -1263,13 +1287,13 @@ __global__ void k_stokes_div(int64_t nc, const int *__restrict__ cell_nodes, con
         }
         for (int v = 0; v <= D; ++v) be[v] -= Q2<D>::w(q) * vol * div * lam[v];
       }
-      for (int v = 0; v <= D; ++v) atomicAdd(&out[cn[v]], be[v]);
+      for (int v = 0; v <= D; ++v) atomicAdd(&out[pcn[c * (D + 1) + v]], be[v]);
     } else {
       for (int q = 0; q < Q2<D>::NQ; ++q) {
         double lam[D + 1];
         for (int m = 0; m <= D; ++m) lam[m] = Q2<D>::lam(q, m);
         double p = 0.0;
-        for (int v = 0; v <= D; ++v) p += in[cn[v]] * lam[v];
+        for (int v = 0; v <= D; ++v) p += in[pcn[c * (D + 1) + v]] * lam[v];
         const double w = -Q2<D>::w(q) * vol * p;
         for (int a = 0; a < NL; ++a) {
           double g[D];
@@ -1281,17 +1305,17 @@ __global__ void k_stokes_div(int64_t nc, const int *__restrict__ cell_nodes, con
   }
 }
 
-void stokes_div(fb_ctx *ctx, const DevSpace &W, const double *u, double *out_p) {
+void stokes_div(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, const double *u, double *out_p) {
   const int g = grid_for(W.nc, 128, ctx->dev->sm_count * 32);
   if (W.dim == 2)
-    FB_LAUNCH(ctx, (k_stokes_div<2, 0>), g, 128, 0, W.nc, W.cell_nodes.p, W.xyz.p, u, out_p);
+    FB_LAUNCH(ctx, (k_stokes_div<2, 0>), g, 128, 0, W.nc, W.cell_nodes.p, W.cells.p, P.cell_nodes.p, W.xyz.p, u, out_p);
   else
-    FB_LAUNCH(ctx, (k_stokes_div<3, 0>), g, 128, 0, W.nc, W.cell_nodes.p, W.xyz.p, u, out_p);
+    FB_LAUNCH(ctx, (k_stokes_div<3, 0>), g, 128, 0, W.nc, W.cell_nodes.p, W.cells.p, P.cell_nodes.p, W.xyz.p, u, out_p);
 }
-void stokes_grad(fb_ctx *ctx, const DevSpace &W, const double *p, double *out_u) {
+void stokes_grad(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, const double *p, double *out_u) {
   const int g = grid_for(W.nc, 128, ctx->dev->sm_count * 32);
   if (W.dim == 2)
-    FB_LAUNCH(ctx, (k_stokes_div<2, 1>), g, 128, 0, W.nc, W.cell_nodes.p, W.xyz.p, p, out_u);
+    FB_LAUNCH(ctx, (k_stokes_div<2, 1>), g, 128, 0, W.nc, W.cell_nodes.p, W.cells.p, P.cell_nodes.p, W.xyz.p, p, out_u);
   else
-    FB_LAUNCH(ctx, (k_stokes_div<3, 1>), g, 128, 0, W.nc, W.cell_nodes.p, W.xyz.p, p, out_u);
+    FB_LAUNCH(ctx, (k_stokes_div<3, 1>), g, 128, 0, W.nc, W.cell_nodes.p, W.cells.p, P.cell_nodes.p, W.xyz.p, p, out_u);
 }

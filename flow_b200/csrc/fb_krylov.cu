@@ -4,10 +4,13 @@
 // Replaces PETSc KSPCG / the LU solves of the reference (pressure_correction.py:325-339,
 // :414-432, :451-464; Newton's linear solves :224-254; heat.py:117-121).  No host
 // round-trip per iteration: every scalar (alpha, beta, omega, rho) is recomputed inside
-// the kernels from reduction slots that live in device memory; the last block of the
-// reducing kernel evaluates the stopping test and raises a device flag that turns all
-// later kernels of the batch into no-ops, so the result is independent of how many
-// iterations the host enqueues between checks.
+// the kernels from reduction slots that live in device memory; the stopping test runs on
+// the device (in the finishing block of the reducing kernel on one GPU, in a one-thread
+// kernel behind the NCCL all-reduce on several) and raises a flag that turns all later
+// kernels of the batch into no-ops, so the result does not depend on how many iterations
+// the host enqueues between polls.  Multi-GPU: vectors hold owned entries first, ghosts
+// after; all vector kernels and dots run over the owned part, the SpMV wrapper refreshes
+// ghosts, each reducing kernel is followed by ONE all-reduce of its 1-2 slots.
 #include "fb_ops.h"
 
 namespace {
@@ -24,9 +27,28 @@ constexpr int S_PAP = 4, S_TOL2 = 5;
 constexpr int S_BTOL2 = 12;
 
 // ---------------------------------------------------------------- PCG
+__device__ void cg_start_check(double *red, double rtol, int *flag, int *iters) {
+  const double ref2 = red[1];  // ||M^-1 b||^2 (+ squared Dirichlet values, folded in by block 0)
+  red[S_TOL2] = rtol * rtol * ref2;
+  *iters = 0;
+  *flag = (ref2 == 0.0) ? 1 : ((ref2 != ref2) ? 3 : 0);
+}
+
+__device__ void cg_update_check(const double *red, int it, int *flag, int *iters) {
+  const int nxt = (it & 1) ^ 1;
+  const double pAp = red[S_PAP], zz = red[2 * nxt + 1];
+  if (!(pAp > 0.0) || zz != zz) {
+    *flag = (zz != zz || pAp != pAp) ? 3 : 2;
+    *iters = it + 1;
+  } else if (zz <= red[S_TOL2]) {
+    *flag = 1;
+    *iters = it + 1;
+  }
+}
+
 __global__ void k_cg_start(int64_t n, const double *__restrict__ b, const double *__restrict__ dinv, double *r, double *z,
-                           double *p, double *x, double rtol, double ref_extra2, double *partials, unsigned int *counter,
-                           double *red, int *flag, int *iters) {
+                           double *p, double *x, double rtol, double ref_extra2, int dist, double *partials,
+                           unsigned int *counter, double *red, int *flag, int *iters) {
   double d[2] = {0.0, 0.0};
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double ri = b[i];
@@ -38,22 +60,18 @@ __global__ void k_cg_start(int64_t n, const double *__restrict__ b, const double
     d[0] += ri * zi;
     d[1] += zi * zi;
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) d[1] += ref_extra2;
   const bool last = fb_grid_reduce<2>(d, partials, counter, red, 0);
-  if (last && threadIdx.x == 0) {
-    const double ref2 = red[1] + ref_extra2;
-    red[S_TOL2] = rtol * rtol * ref2;
-    *iters = 0;
-    *flag = (ref2 == 0.0) ? 1 : ((ref2 != ref2) ? 3 : 0);
-  }
+  if (last && threadIdx.x == 0 && !dist) cg_start_check(red, rtol, flag, iters);
 }
+__global__ void k_cg_start_check(double *red, double rtol, int *flag, int *iters) { cg_start_check(red, rtol, flag, iters); }
 
 __global__ void k_cg_update(int64_t n, int it, const double *__restrict__ dinv, const double *__restrict__ p,
-                            const double *__restrict__ Ap, double *x, double *r, double *z, double *partials,
+                            const double *__restrict__ Ap, double *x, double *r, double *z, int dist, double *partials,
                             unsigned int *counter, double *red, int *flag, int *iters) {
   if (*flag) return;
   const int par = it & 1, nxt = par ^ 1;
-  const double pAp = red[S_PAP];
-  const double alpha = red[2 * par] / pAp;
+  const double alpha = red[2 * par] / red[S_PAP];
   double d[2] = {0.0, 0.0};
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     x[i] += alpha * p[i];
@@ -65,16 +83,11 @@ __global__ void k_cg_update(int64_t n, int it, const double *__restrict__ dinv, 
     d[1] += zi * zi;
   }
   const bool last = fb_grid_reduce<2>(d, partials, counter, red, 2 * nxt);
-  if (last && threadIdx.x == 0) {
-    const double zz = red[2 * nxt + 1];
-    if (!(pAp > 0.0) || zz != zz) {
-      *flag = (zz != zz || pAp != pAp) ? 3 : 2;
-      *iters = it + 1;
-    } else if (zz <= red[S_TOL2]) {
-      *flag = 1;
-      *iters = it + 1;
-    }
-  }
+  if (last && threadIdx.x == 0 && !dist) cg_update_check(red, it, flag, iters);
+}
+__global__ void k_cg_update_check(const double *red, int it, int *flag, int *iters) {
+  if (*flag) return;
+  cg_update_check(red, it, flag, iters);
 }
 
 __global__ void k_cg_direction(int64_t n, int it, const double *__restrict__ z, double *p, const double *red,
@@ -106,8 +119,32 @@ __device__ __forceinline__ void apply_minv(const double *__restrict__ minv, int6
   }
 }
 
+__device__ void bi_start_check(double *red, double atol, int *flag, int *iters) {
+  red[S_BTOL2] = atol * atol;
+  *iters = 0;
+  const double rr = red[bs(0, 1)];
+  *flag = (rr != rr) ? 3 : (rr <= atol * atol ? 1 : 0);
+}
+
+__device__ void bi_update_check(const double *red, int it, int *flag, int *iters) {
+  const int s = it & 1, nx = s ^ 1;
+  const double tt = red[bs(s, 4)];
+  const double omega = tt > 0.0 ? red[bs(s, 3)] / tt : 0.0;
+  const double rr = red[bs(nx, 1)];
+  if (rr != rr) {
+    *flag = 3;
+    *iters = it + 1;
+  } else if (rr <= red[S_BTOL2]) {
+    *flag = 1;
+    *iters = it + 1;
+  } else if (red[bs(nx, 0)] == 0.0 || omega == 0.0) {
+    *flag = 2;  // breakdown: the host restarts from the true residual
+    *iters = it + 1;
+  }
+}
+
 __global__ void k_bi_start(int64_t n, const double *__restrict__ b, double *r, double *rhat, double *x, double atol,
-                           double *partials, unsigned int *counter, double *red, int *flag, int *iters) {
+                           int dist, double *partials, unsigned int *counter, double *red, int *flag, int *iters) {
   double d[2] = {0.0, 0.0};
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double ri = b[i];
@@ -118,13 +155,9 @@ __global__ void k_bi_start(int64_t n, const double *__restrict__ b, double *r, d
     d[1] += ri * ri;
   }
   const bool last = fb_grid_reduce<2>(d, partials, counter, red, bs(0, 0));
-  if (last && threadIdx.x == 0) {
-    red[S_BTOL2] = atol * atol;
-    *iters = 0;
-    const double rr = red[bs(0, 1)];
-    *flag = (rr != rr) ? 3 : (rr <= atol * atol ? 1 : 0);
-  }
+  if (last && threadIdx.x == 0 && !dist) bi_start_check(red, atol, flag, iters);
 }
+__global__ void k_bi_start_check(double *red, double atol, int *flag, int *iters) { bi_start_check(red, atol, flag, iters); }
 
 // p = r + beta (p - omega v);  phat = Minv p        (one thread per node)
 template <int D>
@@ -165,7 +198,7 @@ __global__ void k_bi_half(int64_t nnodes, int it, const double *__restrict__ min
       *flag = (rhv != rhv) ? 3 : 2;
       *iters = it + 1;
     }
-    return;  // every block takes this branch (rhv is grid-uniform)
+    return;  // every block takes this branch (rhv is grid-uniform and identical on all ranks)
   }
   const double alpha = red[bs(s, 0)] / rhv;
   for (int64_t node = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; node < nnodes; node += (int64_t)gridDim.x * blockDim.x) {
@@ -184,7 +217,7 @@ __global__ void k_bi_half(int64_t nnodes, int it, const double *__restrict__ min
 
 // x += alpha phat + omega shat ; r = s - omega t ; rho_next = rhat.r ; rr = r.r
 __global__ void k_bi_update(int64_t n, int it, const double *__restrict__ phat, const double *__restrict__ shat,
-                            const double *__restrict__ t, const double *__restrict__ rhat, double *x, double *r,
+                            const double *__restrict__ t, const double *__restrict__ rhat, double *x, double *r, int dist,
                             double *partials, unsigned int *counter, double *red, int *flag, int *iters) {
   if (*flag) return;
   const int s = it & 1, nx = s ^ 1;
@@ -200,19 +233,11 @@ __global__ void k_bi_update(int64_t n, int it, const double *__restrict__ phat, 
     d[1] += ri * ri;
   }
   const bool last = fb_grid_reduce<2>(d, partials, counter, red, bs(nx, 0));
-  if (last && threadIdx.x == 0) {
-    const double rr = red[bs(nx, 1)];
-    if (rr != rr) {
-      *flag = 3;
-      *iters = it + 1;
-    } else if (rr <= red[S_BTOL2]) {
-      *flag = 1;
-      *iters = it + 1;
-    } else if (red[bs(nx, 0)] == 0.0 || omega == 0.0) {
-      *flag = 2;  // breakdown
-      *iters = it + 1;
-    }
-  }
+  if (last && threadIdx.x == 0 && !dist) bi_update_check(red, it, flag, iters);
+}
+__global__ void k_bi_update_check(const double *red, int it, int *flag, int *iters) {
+  if (*flag) return;
+  bi_update_check(red, it, flag, iters);
 }
 
 int poll(fb_ctx *ctx, int *flag_out, int *iters_out) {
@@ -232,19 +257,28 @@ int krylov_pcg(fb_ctx *ctx, const LinOp &A, const double *dinv, const double *b,
                int maxit, int check_every, KrylovWork &w, int *iters) {
   fb_device_state *dv = ctx->dev;
   const int64_t n = A.ndofs();
-  w.ensure(4, n);
+  const int dist = fb_is_distributed(ctx) ? 1 : 0;
+  w.ensure(4, A.nlocal_dofs());
   double *r = w.v[0].p, *z = w.v[1].p, *p = w.v[2].p, *Ap = w.v[3].p;
   const int g = vgrid(ctx, n);
-  FB_LAUNCH(ctx, k_cg_start, g, 256, 0, n, b, dinv, r, z, p, x, rtol, ref_extra2, dv->partials, dv->counter, dv->red,
+  FB_LAUNCH(ctx, k_cg_start, g, 256, 0, n, b, dinv, r, z, p, x, rtol, ref_extra2, dist, dv->partials, dv->counter, dv->red,
             dv->flag, dv->iters);
+  if (dist) {
+    fb_allreduce_slots(ctx, 0, 2);
+    FB_LAUNCH(ctx, k_cg_start_check, 1, 1, 0, dv->red, rtol, dv->flag, dv->iters);
+  }
   int flag = 0, done = 0, it = 0;
   if (check_every < 1) check_every = 1;
   while (it < maxit) {
     const int batch = std::min(check_every, maxit - it);
     for (int k = 0; k < batch; ++k, ++it) {
       spmv(ctx, A, p, Ap, 1, p, S_PAP, dv->flag);
-      FB_LAUNCH(ctx, k_cg_update, g, 256, 0, n, it, dinv, p, Ap, x, r, z, dv->partials, dv->counter, dv->red, dv->flag,
-                dv->iters);
+      FB_LAUNCH(ctx, k_cg_update, g, 256, 0, n, it, dinv, p, Ap, x, r, z, dist, dv->partials, dv->counter, dv->red,
+                dv->flag, dv->iters);
+      if (dist) {
+        fb_allreduce_slots(ctx, 2 * ((it & 1) ^ 1), 2);
+        FB_LAUNCH(ctx, k_cg_update_check, 1, 1, 0, dv->red, it, dv->flag, dv->iters);
+      }
       FB_LAUNCH(ctx, k_cg_direction, g, 256, 0, n, it, z, p, dv->red, dv->flag);
     }
     poll(ctx, &flag, &done);
@@ -264,10 +298,16 @@ static int bicgstab_impl(fb_ctx *ctx, const LinOp &A, const double *minv, const 
   fb_device_state *dv = ctx->dev;
   const int64_t n = A.ndofs();
   const int64_t nnodes = n / D;
-  w.ensure(7, n);
+  const int dist = fb_is_distributed(ctx) ? 1 : 0;
+  w.ensure(7, A.nlocal_dofs());
   double *r = w.v[0].p, *rhat = w.v[1].p, *p = w.v[2].p, *v = w.v[3].p, *phat = w.v[4].p, *shat = w.v[5].p, *t = w.v[6].p;
   const int g = vgrid(ctx, n), gn = vgrid(ctx, nnodes);
-  FB_LAUNCH(ctx, k_bi_start, g, 256, 0, n, b, r, rhat, x, atol, dv->partials, dv->counter, dv->red, dv->flag, dv->iters);
+  FB_LAUNCH(ctx, k_bi_start, g, 256, 0, n, b, r, rhat, x, atol, dist, dv->partials, dv->counter, dv->red, dv->flag,
+            dv->iters);
+  if (dist) {
+    fb_allreduce_slots(ctx, 0, 2);
+    FB_LAUNCH(ctx, k_bi_start_check, 1, 1, 0, dv->red, atol, dv->flag, dv->iters);
+  }
   int flag = 0, done = 0, it = 0;
   if (check_every < 1) check_every = 1;
   poll(ctx, &flag, &done);
@@ -279,8 +319,12 @@ static int bicgstab_impl(fb_ctx *ctx, const LinOp &A, const double *minv, const 
       spmv(ctx, A, phat, v, 1, rhat, 6 * s + 2, dv->flag);
       FB_LAUNCH(ctx, k_bi_half<D>, gn, 256, 0, nnodes, it, minv, v, r, shat, dv->red, dv->flag, dv->iters);
       spmv(ctx, A, shat, t, 2, r, 6 * s + 3, dv->flag);
-      FB_LAUNCH(ctx, k_bi_update, g, 256, 0, n, it, phat, shat, t, rhat, x, r, dv->partials, dv->counter, dv->red,
+      FB_LAUNCH(ctx, k_bi_update, g, 256, 0, n, it, phat, shat, t, rhat, x, r, dist, dv->partials, dv->counter, dv->red,
                 dv->flag, dv->iters);
+      if (dist) {
+        fb_allreduce_slots(ctx, 6 * (s ^ 1), 2);
+        FB_LAUNCH(ctx, k_bi_update_check, 1, 1, 0, dv->red, it, dv->flag, dv->iters);
+      }
     }
     poll(ctx, &flag, &done);
   }
@@ -307,8 +351,8 @@ int krylov_bicgstab(fb_ctx *ctx, const LinOp &A, const double *minv, const doubl
   int status = bicgstab_once(ctx, A, minv, b, x, atol, maxit, check_every, w, &its);
   total += its;
   for (int restart = 0; status == FB_BREAKDOWN && restart < 20 && total < maxit; ++restart) {
-    w.v[7].alloc((size_t)n);
-    w.v[8].alloc((size_t)n);
+    w.v[7].alloc((size_t)A.nlocal_dofs());
+    w.v[8].alloc((size_t)A.nlocal_dofs());
     double *rhs = w.v[7].p, *e = w.v[8].p;
     spmv(ctx, A, x, rhs);
     vec_axpby(ctx, rhs, 1.0, b, -1.0, rhs, n);  // rhs = b - A x

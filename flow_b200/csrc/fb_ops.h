@@ -1,5 +1,7 @@
 // Host-callable launchers of the CUDA kernels in fb_kernels.cu / fb_krylov.cu.
 #pragma once
+#include <vector>
+
 #include "fb_device.cuh"
 
 // Device copy of a node space: dof map, node-level CSR pattern, element->slot scatter map.
@@ -8,12 +10,19 @@ struct DevSpace {
   int dim = 0, nl = 0, degree = 0;
   int64_t nnodes = 0, nc = 0, nnz = 0, nbf = 0;
   DBuf<double> xyz;         // vertex coordinates (mesh.nv * dim)
-  DBuf<int> cell_nodes;     // nc * nl
+  DBuf<int> cell_nodes;     // nc * nl, in the space's node numbering
+  DBuf<int> cells;          // nc * (dim+1): mesh vertex connectivity (geometry)
   DBuf<int> rowptr;         // nnodes + 1
   DBuf<int> col;            // nnz
   DBuf<int> diag;           // nnodes: slot of the diagonal entry
   DBuf<int> smap;           // nc * nl * nl: CSR slot of (node_a, node_b)
   DBuf<int> bf_cell, bf_local;
+  // distributed: rows [0, n_owned) are computed here, [n_owned, nnodes) are ghosts (SpMV inputs only)
+  int64_t n_owned = 0;
+  std::vector<int> halo_ranks;
+  std::vector<int64_t> halo_send_ptr, halo_recv_ptr;
+  DBuf<int> halo_send_nodes;
+  DBuf<double> halo_buf;
 };
 
 struct fb_mat {
@@ -28,16 +37,24 @@ struct fb_mat {
 struct LinOp {
   int block = 1;   // 1 or D
   int ncomp = 1;   // interleaved components sharing a scalar matrix (block == 1)
-  int64_t nrows = 0;  // node rows
+  int64_t nrows = 0;   // node rows computed here (owned)
+  int64_t nlocal = 0;  // node columns stored here (owned + ghosts)
+  DevSpace *halo = nullptr;  // non-null: refresh the ghosts of x before multiplying
   const int *rowptr = nullptr;
   const int *col = nullptr;
   const double *val = nullptr;
   const uint8_t *mask = nullptr;  // per dof: 1 -> identity row (Dirichlet); may be null
   int64_t ndofs() const { return nrows * (block > 1 ? block : ncomp); }
+  int64_t nlocal_dofs() const { return nlocal * (block > 1 ? block : ncomp); }
   int dofs_per_node() const { return block > 1 ? block : ncomp; }
 };
 
 LinOp make_linop(const fb_mat &m, int ncomp, const uint8_t *mask);
+
+// ---- multi-GPU (fb_comm.cu): no-ops on a single rank
+bool fb_is_distributed(const fb_ctx *ctx);
+void fb_allreduce_slots(fb_ctx *ctx, int slot0, int count);
+void halo_exchange(fb_ctx *ctx, DevSpace &sp, double *x, int ncomp);
 
 // ---- setup
 void dev_space_build(fb_space *s, DevSpace &d);
@@ -76,6 +93,7 @@ void jacobi_setup_blocked(fb_ctx *ctx, const DevSpace &sp, int D, const double *
 struct MomentumArgs {
   double dt, rho, mu, theta;
   const double *ui, *u0, *p0;
+  const int *pcn;  // cell -> P1 dofs of the pressure space
 };
 void assemble_momentum_F(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F);  // zero + both parts
 void assemble_momentum_F_old_state(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F);  // += u0 part
@@ -84,13 +102,13 @@ void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, 
 void assemble_pressure_rhs(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, double dt, double rho, double mu,
                            int rotational, const double *ui, const double *p0, double *b);
 // adds -dt/rho (grad phi, v) to b (which already holds M ui)
-void assemble_correction_grad(fb_ctx *ctx, const DevSpace &W, double dt, double rho, double mu, int rotational,
-                              const double *ui, const double *p1, const double *p0, double *b);
+void assemble_correction_grad(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, double dt, double rho, double mu,
+                              int rotational, const double *ui, const double *p1, const double *p0, double *b);
 // heat operator A (heat.py:54-58): -(kappa/rho_cp) grad u.grad v - (conv.grad u) v on V's pattern
 void assemble_heat(fb_ctx *ctx, const DevSpace &V, const DevSpace *W, const double *conv, double kdiff, double *val);
 // B x and B^T y for the divergence block of stokes.py:40-42 (matrix-free)
-void stokes_div(fb_ctx *ctx, const DevSpace &W, const double *u, double *out_p);
-void stokes_grad(fb_ctx *ctx, const DevSpace &W, const double *p, double *out_u);
+void stokes_div(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, const double *u, double *out_p);
+void stokes_grad(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, const double *p, double *out_u);
 
 // ---- Krylov (fb_krylov.cu).  All vectors are device pointers; return FB_OK / FB_ENOCONV_KRYLOV / FB_ENAN.
 struct KrylovWork {

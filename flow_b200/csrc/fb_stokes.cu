@@ -54,9 +54,9 @@ struct Stokes {
     cudaStream_t st = ctx->dev->stream;
     LinOp Kop = make_linop(K, D, nullptr);
     spmv(ctx, Kop, x, y);                                   // K x_u (K already carries mu)
-    stokes_grad(ctx, *W, x + nu, y);                        // += B^T x_p
+    stokes_grad(ctx, *W, *P, x + nu, y);                        // += B^T x_p
     FB_CUDA(cudaMemsetAsync(y + nu, 0, sizeof(double) * np, st));
-    stokes_div(ctx, *W, x, y + nu);                         // B x_u
+    stokes_div(ctx, *W, *P, x, y + nu);                         // B x_u
     FB_LAUNCH(ctx, k_mask_zero, vgrid(ctx, n), 256, 0, y, mask.p, n);
   }
 
@@ -178,9 +178,9 @@ extern "C" int fb_stokes_solve(fb_space *Wsp, fb_space *Psp, double mu, int forc
       vec_set_at(ctx, xg.p, ddofs.p, dvals.p, nbc);
       // full operator on x_g (not masked): tmp = A x_g
       spmv(ctx, make_linop(S.K, D, nullptr), xg.p, tmp.p);
-      stokes_grad(ctx, *S.W, xg.p + nu, tmp.p);
+      stokes_grad(ctx, *S.W, *S.P, xg.p + nu, tmp.p);
       FB_CUDA(cudaMemsetAsync(tmp.p + nu, 0, sizeof(double) * np, st));
-      stokes_div(ctx, *S.W, xg.p, tmp.p + nu);
+      stokes_div(ctx, *S.W, *S.P, xg.p, tmp.p + nu);
       vec_axpy(ctx, b.p, -1.0, tmp.p, n);
       vec_zero_at(ctx, b.p, ddofs.p, nbc);
     }

@@ -158,6 +158,30 @@ int fb_mesh_boundary_facets(fb_mesh *m, const int32_t **cell, const int32_t **lo
   return FB_OK;
 }
 
+// Replace the boundary-facet list (and the boundary vertex / edge flags derived from it).  A rank-local
+// sub-mesh of a partitioned domain must not treat its cut faces as domain boundary: the caller passes
+// the facets of the GLOBAL boundary that lie in local cells.  Call before creating spaces.
+int fb_mesh_set_boundary_facets(fb_mesh *m, int64_t n, const int32_t *cell, const int32_t *local_facet) {
+  if (!m || n < 0 || (n > 0 && (!cell || !local_facet))) return FB_EINVAL;
+  const int nvc = m->dim + 1, nle = fb_num_local_edges(m->dim);
+  const int(*LE)[2] = m->dim == 2 ? TRI_EDGES : TET_EDGES;
+  for (int64_t i = 0; i < n; ++i)
+    if (cell[i] < 0 || cell[i] >= m->nc || local_facet[i] < 0 || local_facet[i] >= nvc)
+      return fb_fail(m->ctx, FB_EINVAL, "fb_mesh_set_boundary_facets: facet out of range");
+  m->bf_cell.assign(cell, cell + n);
+  m->bf_local.assign(local_facet, local_facet + n);
+  m->bvert.assign(m->nv, 0);
+  m->bedge.assign(m->ne, 0);
+  for (int64_t i = 0; i < n; ++i) {
+    const int32_t c = cell[i], f = local_facet[i];
+    for (int k = 0; k < nvc; ++k)
+      if (k != f) m->bvert[m->cells[(int64_t)c * nvc + k]] = 1;
+    for (int e = 0; e < nle; ++e)
+      if (LE[e][0] != f && LE[e][1] != f) m->bedge[m->cell_edges[(int64_t)c * nle + e]] = 1;
+  }
+  return FB_OK;
+}
+
 int fb_space_create(fb_mesh *m, int degree, int ncomp, fb_space **out) {
   if (!m || !out) return FB_EINVAL;
   if (degree != 1 && degree != 2) return fb_fail(m->ctx, FB_EINVAL, "fb_space_create: degree must be 1 or 2");
@@ -173,6 +197,7 @@ int fb_space_create(fb_mesh *m, int degree, int ncomp, fb_space **out) {
     s->cell_nodes = m->cells;
     s->coords = m->xyz;
     s->bnode = m->bvert;
+    s->n_owned = s->nnodes;
   } else {
     s->nl = nvc + nle;
     s->nnodes = m->nv + m->ne;
@@ -196,8 +221,65 @@ int fb_space_create(fb_mesh *m, int degree, int ncomp, fb_space **out) {
     s->bnode.resize(s->nnodes);
     std::memcpy(s->bnode.data(), m->bvert.data(), m->nv);
     std::memcpy(s->bnode.data() + m->nv, m->bedge.data(), m->ne);
+    s->n_owned = s->nnodes;
   }
   *out = s;
+  return FB_OK;
+}
+
+// Space with a caller-chosen node numbering: perm[canonical node] = node id used by this space
+// (a bijection on [0, nnodes)).  Distributed runs number the owned nodes first and the ghost
+// nodes after them (grouped by owner); n_owned = number of owned nodes.
+int fb_space_create_numbered(fb_mesh *m, int degree, int ncomp, const int32_t *perm, int64_t n_owned, fb_space **out) {
+  fb_space *s = nullptr;
+  int st = fb_space_create(m, degree, ncomp, &s);
+  if (st != FB_OK) return st;
+  const int64_t nn = s->nnodes;
+  if (n_owned < 0 || n_owned > nn) {
+    delete s;
+    return fb_fail(m->ctx, FB_EINVAL, "fb_space_create_numbered: n_owned out of range");
+  }
+  s->n_owned = n_owned;
+  if (perm) {
+    std::vector<uint8_t> seen(nn, 0);
+    for (int64_t i = 0; i < nn; ++i) {
+      if (perm[i] < 0 || perm[i] >= nn || seen[perm[i]]) {
+        delete s;
+        return fb_fail(m->ctx, FB_EINVAL, "fb_space_create_numbered: perm is not a permutation");
+      }
+      seen[perm[i]] = 1;
+    }
+    const int d = m->dim;
+    for (auto &v : s->cell_nodes) v = perm[v];
+    std::vector<double> coords(s->coords.size());
+    std::vector<uint8_t> bnode(nn);
+    for (int64_t i = 0; i < nn; ++i) {
+      for (int k = 0; k < d; ++k) coords[(int64_t)perm[i] * d + k] = s->coords[i * d + k];
+      bnode[perm[i]] = s->bnode[i];
+    }
+    s->coords.swap(coords);
+    s->bnode.swap(bnode);
+  }
+  *out = s;
+  return FB_OK;
+}
+
+// Halo plan of a distributed space.  Neighbour k sends us the ghost nodes
+// [n_owned + recv_ptr[k], n_owned + recv_ptr[k+1]) and receives our owned nodes
+// send_nodes[send_ptr[k] .. send_ptr[k+1]) in that order.
+int fb_space_set_halo(fb_space *s, int nneigh, const int32_t *ranks, const int64_t *send_ptr, const int32_t *send_nodes,
+                      const int64_t *recv_ptr) {
+  if (!s || nneigh < 0) return FB_EINVAL;
+  if (s->dev) return fb_fail(s->mesh->ctx, FB_EINVAL, "fb_space_set_halo: must be called before the space is used on the device");
+  if (nneigh > 0 && (!ranks || !send_ptr || !recv_ptr || (send_ptr[nneigh] > 0 && !send_nodes))) return FB_EINVAL;
+  s->halo_ranks.assign(ranks, ranks + nneigh);
+  s->halo_send_ptr.assign(send_ptr, send_ptr + nneigh + 1);
+  s->halo_recv_ptr.assign(recv_ptr, recv_ptr + nneigh + 1);
+  s->halo_send_nodes.assign(send_nodes, send_nodes + (nneigh ? send_ptr[nneigh] : 0));
+  if (nneigh && s->n_owned + recv_ptr[nneigh] != s->nnodes)
+    return fb_fail(s->mesh->ctx, FB_EINVAL, "fb_space_set_halo: ghost segments do not cover [n_owned, nnodes)");
+  for (int32_t v : s->halo_send_nodes)
+    if (v < 0 || v >= s->n_owned) return fb_fail(s->mesh->ctx, FB_EINVAL, "fb_space_set_halo: send node is not owned");
   return FB_OK;
 }
 

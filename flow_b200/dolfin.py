@@ -68,6 +68,7 @@ class Mesh(object):
         self.handle = h
         self._spaces = {}
         self._vol = None
+        self.partition = None  # set by flow_b200.parallel.distributed_mesh
 
     def coordinates(self):
         return self._points
@@ -139,9 +140,9 @@ class _NodeSpace(object):
     def __init__(self, mesh, degree):
         self.mesh, self.degree = mesh, degree
         self._vec_handles = {}
-        h = _lib.vp()
-        _lib.check(lib.fb_space_create(mesh.handle, degree, 1, C.byref(h)), mesh.ctx, "fb_space_create")
-        self.handle = h
+        self.plan = mesh.partition.plans[degree] if mesh.partition is not None else None
+        self.handle = self._create(1)
+        h = self.handle
         nn, nd, nl = _lib.i64(), _lib.i64(), C.c_int()
         lib.fb_space_info(h, C.byref(nn), C.byref(nd), C.byref(nl))
         self.nnodes, self.nl = nn.value, nl.value
@@ -156,14 +157,25 @@ class _NodeSpace(object):
         self.on_boundary = np.ctypeslib.as_array(b, shape=(self.nnodes,)).astype(bool)
         self._mass = None
 
+    def _create(self, ncomp):
+        h = _lib.vp()
+        mesh, pl = self.mesh, self.plan
+        if pl is None:
+            _lib.check(lib.fb_space_create(mesh.handle, self.degree, ncomp, C.byref(h)), mesh.ctx, "fb_space_create")
+            return h
+        # distributed: owned-first numbering + halo plan (flow_b200/parallel.py)
+        _lib.check(lib.fb_space_create_numbered(mesh.handle, self.degree, ncomp, _lib.as_pi32(pl.perm), pl.n_owned, C.byref(h)),
+                   mesh.ctx, "fb_space_create_numbered")
+        _lib.check(lib.fb_space_set_halo(h, pl.ranks.size, _lib.as_pi32(pl.ranks), _lib.as_pi64(pl.send_ptr),
+                                         _lib.as_pi32(pl.send_nodes), _lib.as_pi64(pl.recv_ptr)), mesh.ctx, "fb_space_set_halo")
+        return h
+
     def vector_handle(self, ncomp):
         """fb_space handle with `ncomp` interleaved components on the same nodes."""
         if ncomp == 1:
             return self.handle
         if ncomp not in self._vec_handles:
-            h = _lib.vp()
-            _lib.check(lib.fb_space_create(self.mesh.handle, self.degree, ncomp, C.byref(h)), self.mesh.ctx, "fb_space_create")
-            self._vec_handles[ncomp] = h
+            self._vec_handles[ncomp] = self._create(ncomp)
         return self._vec_handles[ncomp]
 
     def mass(self):

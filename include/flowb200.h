@@ -90,6 +90,23 @@ int fb_space_boundary_nodes(fb_space *space, const uint8_t **flags);
 /* node-level CSR sparsity pattern (columns ascending) -- the pattern of assemble() */
 int fb_space_pattern(fb_space *space, int64_t *nnz, const int64_t **indptr, const int32_t **indices);
 
+/* ---- distributed runs (one process per GPU).  The caller partitions the mesh
+ * (flow_b200/parallel.py: recursive coordinate bisection, owner-computes rows, one ghost-cell
+ * layer), creates the rank-local mesh and passes the node numbering "owned first, ghosts grouped
+ * by owner" plus the halo plan.  Replaces DOLFIN's implicit MPI partitioning + PETSc's VecScatter /
+ * MPI_Allreduce [EXT]; the reference tree itself has no MPI-aware code. */
+int fb_mesh_set_boundary_facets(fb_mesh *mesh, int64_t n, const int32_t *cell, const int32_t *local_facet);
+int fb_space_create_numbered(fb_mesh *mesh, int degree, int ncomp, const int32_t *perm, int64_t n_owned,
+                             fb_space **out);
+int fb_space_set_halo(fb_space *space, int nneigh, const int32_t *ranks, const int64_t *send_ptr,
+                      const int32_t *send_nodes, const int64_t *recv_ptr);
+/* 128-byte NCCL unique id (create on rank 0, broadcast by the launcher, e.g. torch.distributed) */
+int fb_comm_unique_id(void *id128);
+int fb_comm_init(fb_ctx *ctx, int rank, int nranks, const void *id128);
+int fb_comm_destroy(fb_ctx *ctx);
+/* refresh the ghost entries of a host vector (ncomp interleaved components) -- test/debug helper */
+int fb_space_halo_exchange(fb_space *space, int ncomp, double *x);
+
 /* ---- assembled operators: replaces dolfin.assemble(a) for the constant forms
  * u*v*dx (pressure_correction.py:442) and dot(grad p, grad q)*dx (:317), plus
  * the vertex-quadrature mass of heat.py:39-45. */
