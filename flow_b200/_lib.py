@@ -50,7 +50,9 @@ class NSOpts(C.Structure):
         ("gmres_restart", C.c_int),
         ("check_every", C.c_int),
         ("chebyshev_degree", C.c_int),
-        ("reserved", C.c_int * 8),
+        ("jacobian_reuse", C.c_int),
+        ("adaptive_forcing", C.c_int),
+        ("reserved", C.c_int * 6),
     ]
 
 
@@ -74,7 +76,8 @@ class NSStats(C.Structure):
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
-        d["newton_residuals"] = [self.reserved[k] for k in range(min(8, self.newton_its + 1))]
+        d["newton_residuals"] = [self.reserved[k] for k in range(min(7, self.newton_its + 1))]
+        d["jacobian_assemblies"] = int(self.reserved[7])
         return d
 
 

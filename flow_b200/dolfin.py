@@ -134,6 +134,12 @@ def UnitCubeMesh(nx, ny, nz):
     return Mesh(*hostfem.structured_box((0.0, 0.0, 0.0), (1.0, 1.0, 1.0), nx, ny, nz))
 
 
+def RectangleWithHoleMesh(p0, p1, nx, ny, center, radius, diagonal="left/right"):
+    """Synthetic replacement of the pygmsh rectangle-with-circular-hole geometries used by the reference's
+    drivers (gmsh is not available); see hostfem.structured_rectangle_with_hole."""
+    return Mesh(*hostfem.structured_rectangle_with_hole((p0[0], p0[1]), (p1[0], p1[1]), nx, ny, center, radius, diagonal))
+
+
 class _NodeSpace(object):
     """fb_space handle of a scalar Lagrange node set (P1 or P2) + host views of its tables."""
 

@@ -221,3 +221,31 @@ def integrate_expression(points, cells, func, degree):
     lam, w = quadrature(dim, max(degree, 1))
     fq = expression_at_quadrature(points, cells, func, degree, lam)[:, :, 0]
     return float(np.einsum("q,cq,c->", w, fq, cell_volumes(points, cells)))
+
+
+def structured_rectangle_with_hole(a, b, nx, ny, center, radius, diagonal="left/right"):
+    """Synthetic stand-in for the gmsh geometries of the reference's drivers (rectangle with a circular
+    hole: tests/test_sealed_box.py:32-53, tests/test_boussinesq.py:25-79, the cylinder of
+    tests/test_karman_vortex_street.py:18-45): a structured triangulation whose vertices near the circle
+    are projected onto it; cells inside the circle are removed.  Returns (points, cells)."""
+    pts, cells = structured_rectangle(a, b, nx, ny, diagonal)
+    c = np.asarray(center, dtype=float)
+    h = max((b[0] - a[0]) / nx, (b[1] - a[1]) / ny)
+    d = pts - c
+    r = np.sqrt((d * d).sum(axis=1))
+    snap = np.abs(r - radius) < 0.5 * h
+    pts = pts.copy()
+    pts[snap] = c + d[snap] * (radius / r[snap])[:, None]
+    r = np.sqrt(((pts - c) ** 2).sum(axis=1))
+    inside_v = r < radius * (1 - 1e-9)
+    cen = pts[cells].mean(axis=1)
+    rc = np.sqrt(((cen - c) ** 2).sum(axis=1))
+    keep = ~(inside_v[cells].any(axis=1) | (rc < radius * 0.98))
+    cells = cells[keep]
+    # drop degenerate cells created by snapping and renumber the used vertices
+    vol = cell_volumes(pts, cells)
+    cells = cells[vol > 1e-3 * h * h]
+    used = np.unique(cells)
+    remap = -np.ones(pts.shape[0], dtype=np.int64)
+    remap[used] = np.arange(used.size)
+    return pts[used], np.sort(remap[cells], axis=1).astype(np.int32)

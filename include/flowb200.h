@@ -146,7 +146,11 @@ typedef struct fb_ns_opts {
   int gmres_restart;     /* 30 (PETSc default) */
   int check_every;       /* Krylov iterations enqueued between host convergence checks */
   int chebyshev_degree;  /* default 4 */
-  int reserved[8];
+  int jacobian_reuse;    /* 1 (default): keep the step's first Jacobian for later Newton iterations while the
+                            residual contracts by > 10x per iteration (chord); 0: re-assemble every iteration */
+  int adaptive_forcing;  /* 1 (default): the first linear solve of a step stops at the nonlinear remainder observed
+                            at the previous step; 0: every linear solve goes to 0.1 * newton_atol */
+  int reserved[6];
 } fb_ns_opts;
 
 typedef struct fb_ns_stats {
@@ -158,7 +162,7 @@ typedef struct fb_ns_stats {
   double ms_tentative, ms_pressure, ms_correction, ms_total; /* CUDA-event times */
   double ms_assembly_J, ms_assembly_F, ms_momentum_solve;
   int64_t launches;
-  double reserved[8];
+  double reserved[8]; /* [0..6]: |F| after k Newton updates; [7]: Jacobian assemblies in this step */
 } fb_ns_stats;
 
 int fb_ns_opts_default(fb_ns_opts *opts);
