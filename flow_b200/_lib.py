@@ -135,6 +135,8 @@ SIGNATURES = {
     "fb_ns_pressure_rhs": (C.c_int, [vp, dbl, dbl, dbl, C.c_int, pd, pd, pd]),
     "fb_ns_correction_rhs": (C.c_int, [vp, dbl, dbl, dbl, C.c_int, pd, pd, pd, pd]),
     "fb_heat_create": (C.c_int, [vp, vp, pd, dbl, dbl, dbl, pd, C.POINTER(vp)]),
+    "fb_heat_create_supg": (C.c_int, [vp, vp, pd, dbl, dbl, dbl, pd, C.c_int, dbl, C.POINTER(vp)]),
+    "fb_heat_supg_mass": (C.c_int, [vp, pd]),
     "fb_heat_destroy": (C.c_int, [vp]),
     "fb_heat_eval": (C.c_int, [vp, dbl, dbl, pd, pd]),
     "fb_heat_solve": (C.c_int, [vp, dbl, dbl, pd, i64, pi64, pd, dbl, C.c_int, pd, C.POINTER(C.c_int)]),

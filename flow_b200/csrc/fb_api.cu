@@ -820,6 +820,7 @@ struct fb_heat {
   DevSpace *V = nullptr;
   fb_mat A;
   DBuf<double> S, mdiag, b, u, Au, out, rhs, x, dinv, bc_vals;
+  DBuf<double> Msupg;  // SUPG part of the mass matrix on V's pattern (empty without stabilisation)
   DBuf<int64_t> bc_dofs;
   DBuf<uint8_t> mask;
   KrylovWork kw;
@@ -829,7 +830,13 @@ extern "C" {
 
 int fb_heat_create(fb_space *Vsp, fb_space *Wsp, const double *conv, double kappa, double rho, double cp,
                    const double *source_load, fb_heat **out) {
+  return fb_heat_create_supg(Vsp, Wsp, conv, kappa, rho, cp, source_load, 0, 0.0, out);
+}
+
+int fb_heat_create_supg(fb_space *Vsp, fb_space *Wsp, const double *conv, double kappa, double rho, double cp,
+                        const double *source_load, int supg, double source_value, fb_heat **out) {
   if (!Vsp || !out) return FB_EINVAL;
+  if (supg && !conv) return fb_fail(Vsp->mesh->ctx, FB_EINVAL, "fb_heat_create_supg: SUPG needs a convection field (heat.py:74)");
   fb_ctx *ctx = Vsp->mesh->ctx;
   FB_NEED_DEVICE(ctx);
   if (Vsp->ncomp != 1) return fb_fail(ctx, FB_EINVAL, "fb_heat_create: V must be scalar");
@@ -856,6 +863,12 @@ int fb_heat_create(fb_space *Vsp, fb_space *Wsp, const double *conv, double kapp
     FB_CUDA(cudaMemcpyAsync(h->b.p, source_load, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   else
     h->b.zero(st);
+  if (supg) {
+    h->Msupg.alloc((size_t)h->V->nnz);
+    h->Msupg.zero(st);
+    if (assemble_heat_supg(ctx, *h->V, *W, dconv.p, kappa, rho * cp, source_value, h->A.val.p, h->Msupg.p, h->b.p))
+      return fb_fail(ctx, FB_EINVAL, "fb_heat_create_supg: SUPG tau > 1e3 (stabilization.py:132-140 throws here)");
+  }
   for (DBuf<double> *v : {&h->u, &h->Au, &h->out, &h->rhs, &h->x, &h->dinv}) v->alloc((size_t)n);
   h->S.alloc((size_t)h->V->nnz);
   h->mask.alloc((size_t)n);
@@ -875,6 +888,14 @@ int fb_heat_matrix(fb_heat *h, int which, fb_mat **out) {
   return FB_OK;
 }
 
+int fb_heat_supg_mass(fb_heat *h, double *values_out) {
+  if (!h || !values_out || !h->Msupg.p) return FB_EINVAL;
+  FB_API_BEGIN(h->ctx)
+  FB_CUDA(cudaMemcpyAsync(values_out, h->Msupg.p, sizeof(double) * h->V->nnz, cudaMemcpyDeviceToHost, _ctx->dev->stream));
+  FB_CUDA(cudaStreamSynchronize(_ctx->dev->stream));
+  FB_API_END
+}
+
 int fb_heat_eval(fb_heat *h, double alpha, double beta, const double *u, double *out) {
   if (!h || !u || !out) return FB_EINVAL;
   FB_API_BEGIN(h->ctx)
@@ -883,6 +904,12 @@ int fb_heat_eval(fb_heat *h, double alpha, double beta, const double *u, double 
   FB_CUDA(cudaMemcpyAsync(h->u.p, u, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   spmv(_ctx, make_linop(h->A, 1, nullptr), h->u.p, h->Au.p);
   FB_LAUNCH(_ctx, k_heat_eval, vgrid(_ctx, n), 256, 0, n, alpha, beta, h->mdiag.p, h->u.p, h->Au.p, h->b.p, h->out.p);
+  if (h->Msupg.p) {
+    LinOp Ms = make_linop(h->A, 1, nullptr);
+    Ms.val = h->Msupg.p;
+    spmv(_ctx, Ms, h->u.p, h->Au.p);
+    vec_axpy(_ctx, h->out.p, alpha, h->Au.p, n);
+  }
   FB_CUDA(cudaMemcpyAsync(out, h->out.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   FB_CUDA(cudaStreamSynchronize(st));
   FB_API_END
@@ -903,6 +930,7 @@ int fb_heat_solve(fb_heat *h, double alpha, double beta, double *b, int64_t nbc,
   // S = alpha M + beta A   (heat.py:106)
   FB_LAUNCH(_ctx, k_scale_add_diag, vgrid(_ctx, nnz), 256, 0, nnz, n, beta, h->A.val.p, alpha, h->mdiag.p, h->V->diag.p, h->S.p);
   FB_LAUNCH(_ctx, k_add_diag, vgrid(_ctx, n), 256, 0, n, alpha, h->mdiag.p, h->V->diag.p, h->S.p);
+  if (h->Msupg.p) vec_axpy(_ctx, h->S.p, alpha, h->Msupg.p, nnz);
   if (nbc > 0) {
     h->bc_dofs.upload(bc_dofs, (size_t)nbc, st);
     mask_build(_ctx, h->mask.p, n, h->bc_dofs.p, nbc);

@@ -5,6 +5,7 @@
 // very same routines for the CPU-only unit tests; the shipped library only ever
 // calls them from CUDA kernels.
 #pragma once
+#include <math.h>
 
 #if defined(__CUDACC__)
 #define FB_HD __host__ __device__ __forceinline__
@@ -276,4 +277,29 @@ FB_HD void fb_correction_gradphi(const double glam[D + 1][D], const double *Ue, 
         for (int i = 0; i < D; ++i) gphi[k] += mu * Ue[a * D + i] * H[i][k];
     }
   }
+}
+
+// ---- SUPG stabilisation parameter (flow/stabilization.py:50-143, triangles only) -------------
+// tau = h^2/(4 eps p) xi(Pe),  h = element diameter in the direction of the convection v
+// (:74-111), Pe = |v| h / (2 p eps), xi = (coth Pe - 1/Pe)/Pe with its Taylor branch (:123-125).
+// X: the 3 vertex coordinates (x0,y0,x1,y1,x2,y2).  Returns a negative value if tau > 1e3,
+// where the reference throws (:132-140).
+FB_HD double fb_supg_tau(const double *X, const double v[2], double eps, int p) {
+  const double conv_norm = sqrt(v[0] * v[0] + v[1] * v[1]);
+  if (conv_norm < 1.0e-10) return 0.0;  // :64-68
+  const double ax = X[2] - X[0], ay = X[3] - X[1], bx = X[4] - X[0], by = X[5] - X[1];
+  const double det = ax * by - bx * ay;
+  const double area = 0.5 * (det < 0 ? -det : det);
+  double sum = 0.0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = i + 1; j < 3; ++j) {
+      const double e0 = X[2 * i] - X[2 * j], e1 = X[2 * i + 1] - X[2 * j + 1];
+      const double t = e1 * v[0] - e0 * v[1];
+      sum += t < 0 ? -t : t;
+    }
+  const double h = 4.0 * conv_norm * area / sum;
+  const double Pe = 0.5 * conv_norm * h / (p * eps);
+  const double xi = Pe > 1.0e-5 ? (1.0 / tanh(Pe) - 1.0 / Pe) / Pe : 1.0 / 3.0 - Pe * Pe / 45.0 + 2.0 / 945.0 * Pe * Pe * Pe * Pe;
+  const double tau = h * h / 4.0 / eps / p * xi;
+  return tau > 1.0e3 ? -1.0 : tau;
 }

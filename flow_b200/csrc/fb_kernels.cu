@@ -1345,6 +1345,100 @@ void assemble_heat(fb_ctx *ctx, const DevSpace &V, const DevSpace *W, const doub
 #undef FB_HT
 }
 
+// SUPG terms of the heat operator (heat.py:60-86), triangles only like the reference's SupgStab:
+//   Msupg[a][b] = int phi_b tau (conv.grad phi_a)
+//   A[a][b]    += int [ kappa Lap(phi_b)/rho_cp - conv.grad phi_b ] tau (conv.grad phi_a)
+//   b[a]       += int source/rho_cp tau (conv.grad phi_a)
+// tau is the degree-1 Expression of stabilization.py: evaluated at the cell's vertices (with the
+// nodal convection there) and interpolated linearly.  Degree-7 rule (tau P1 * conv P2 * P1 * P2 * P1).
+template <int DEG>
+__global__ void k_heat_supg(int64_t nc, const int *__restrict__ cell_nodes, const int *__restrict__ wcell_nodes,
+                            const int *__restrict__ cells, const double *__restrict__ xyz, const int *__restrict__ smap,
+                            const double *__restrict__ conv, double kappa, double rho_cp, double source, int pdeg,
+                            double *__restrict__ Aval, double *__restrict__ Mval, double *__restrict__ bvec, int *err) {
+  constexpr int D = 2;
+  constexpr int NL = DEG == 1 ? Elem<D>::NL1 : Elem<D>::NL2;
+  constexpr int NLW = Elem<D>::NL2;
+  const int64_t total = nc * NL * NL;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = t / (NL * NL);
+    const int r = (int)(t - c * NL * NL);
+    const int a = r / NL, b = r - a * NL;
+    const int *cv = cells + c * 3;
+    const int *wn = wcell_nodes + c * NLW;
+    double X[6];
+    for (int v = 0; v < 3; ++v)
+      for (int k = 0; k < 2; ++k) X[v * 2 + k] = xyz[(int64_t)cv[v] * 2 + k];
+    double glam[3][2], vol;
+    fb_geometry<2>(X, glam, vol);
+    double tauv[3];
+    for (int v = 0; v < 3; ++v) {
+      const double cvv[2] = {conv[(int64_t)wn[v] * 2], conv[(int64_t)wn[v] * 2 + 1]};
+      tauv[v] = fb_supg_tau(X, cvv, kappa, pdeg);
+      if (tauv[v] < 0.0) {
+        *err = 1;
+        tauv[v] = 0.0;
+      }
+    }
+    double lap_b = 0.0;  // Laplacian of phi_b (constant per cell; zero for P1)
+    if (DEG == 2) {
+      double H[2][2];
+      fb_p2_hess<2>(b, glam, H);
+      lap_b = H[0][0] + H[1][1];
+    }
+    double em = 0.0, ea = 0.0, eb = 0.0;
+    for (int q = 0; q < dq::TRI_D7_NQ; ++q) {
+      double lam[3], ga[2], gb[2];
+      for (int m = 0; m < 3; ++m) lam[m] = dq::TRI_D7_LAM[q][m];
+      double pb;
+      if (DEG == 1) {
+        pb = lam[b];
+        for (int k = 0; k < 2; ++k) {
+          ga[k] = glam[a][k];
+          gb[k] = glam[b][k];
+        }
+      } else {
+        pb = fb_p2_phi<2>(b, lam);
+        fb_p2_grad<2>(a, lam, glam, ga);
+        fb_p2_grad<2>(b, lam, glam, gb);
+      }
+      double cq[2] = {0.0, 0.0};
+      for (int n = 0; n < NLW; ++n) {
+        const double pn = fb_p2_phi<2>(n, lam);
+        cq[0] += pn * conv[(int64_t)wn[n] * 2];
+        cq[1] += pn * conv[(int64_t)wn[n] * 2 + 1];
+      }
+      const double tau = tauv[0] * lam[0] + tauv[1] * lam[1] + tauv[2] * lam[2];
+      const double test = tau * (cq[0] * ga[0] + cq[1] * ga[1]) * dq::TRI_D7_W[q];
+      em += pb * test;
+      ea += (kappa * lap_b / rho_cp - (cq[0] * gb[0] + cq[1] * gb[1])) * test;
+      if (b == 0) eb += source / rho_cp * test;
+    }
+    atomicAdd(&Mval[smap[t]], em * vol);
+    atomicAdd(&Aval[smap[t]], ea * vol);
+    if (b == 0 && source != 0.0) atomicAdd(&bvec[cell_nodes[c * NL + a]], eb * vol);
+  }
+}
+
+int assemble_heat_supg(fb_ctx *ctx, const DevSpace &V, const DevSpace &W, const double *conv, double kappa, double rho_cp,
+                       double source, double *Aval, double *Mval, double *bvec) {
+  if (V.dim != 2) throw fb_cuda_error(FB_EINVAL, "SUPG stabilisation is defined for triangles only (stabilization.py:84-92)");
+  int *err = ctx->dev->flag;
+  FB_CUDA(cudaMemsetAsync(err, 0, sizeof(int), ctx->dev->stream));
+  const int g = grid_for(V.nc * V.nl * V.nl, 128, ctx->dev->sm_count * 32);
+  if (V.degree == 1)
+    FB_LAUNCH(ctx, k_heat_supg<1>, g, 128, 0, V.nc, V.cell_nodes.p, W.cell_nodes.p, V.cells.p, V.xyz.p, V.smap.p, conv, kappa,
+              rho_cp, source, 1, Aval, Mval, bvec, err);
+  else
+    FB_LAUNCH(ctx, k_heat_supg<2>, g, 128, 0, V.nc, V.cell_nodes.p, W.cell_nodes.p, V.cells.p, V.xyz.p, V.smap.p, conv, kappa,
+              rho_cp, source, 2, Aval, Mval, bvec, err);
+  int h = 0;
+  FB_CUDA(cudaMemcpyAsync(&h, err, sizeof(int), cudaMemcpyDeviceToHost, ctx->dev->stream));
+  FB_CUDA(cudaStreamSynchronize(ctx->dev->stream));
+  FB_CUDA(cudaMemsetAsync(err, 0, sizeof(int), ctx->dev->stream));
+  return h;
+}
+
 // =============================================================================
 // Stokes divergence block, matrix-free (stokes.py:40-42):  (B u)_a = -int psi_a div u,  (B^T p)_(b,j) = -int p d_j phi_b
 // =============================================================================

@@ -106,6 +106,9 @@ void assemble_correction_grad(fb_ctx *ctx, const DevSpace &W, const DevSpace &P,
                               int rotational, const double *ui, const double *p1, const double *p0, double *b);
 // heat operator A (heat.py:54-58): -(kappa/rho_cp) grad u.grad v - (conv.grad u) v on V's pattern
 void assemble_heat(fb_ctx *ctx, const DevSpace &V, const DevSpace *W, const double *conv, double kdiff, double *val);
+// SUPG additions (heat.py:60-86): returns non-zero if tau exceeded 1e3 somewhere (the reference throws)
+int assemble_heat_supg(fb_ctx *ctx, const DevSpace &V, const DevSpace &W, const double *conv, double kappa, double rho_cp,
+                       double source, double *Aval, double *Mval, double *bvec);
 // B x and B^T y for the divergence block of stokes.py:40-42 (matrix-free)
 void stokes_div(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, const double *u, double *out_p);
 void stokes_grad(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, const double *p, double *out_u);

@@ -14,7 +14,9 @@ class Heat(object):
 
     def __init__(self, V, conv, kappa, rho, cp, bcs, source, supg_stabilization=False):
         if supg_stabilization:
-            raise NotImplementedError("SUPG stabilisation (stabilization.py) is a next-tier row (SURVEY.md 8f)")
+            assert conv is not None  # heat.py:74
+            if source is not None and not isinstance(source, (Constant, float, int)):
+                raise NotImplementedError("SUPG with a non-constant source term")
         self.V = V
         self.bcs = bcs
         mesh, ns = V.mesh(), V.nodes
@@ -27,8 +29,9 @@ class Heat(object):
         h = _lib.vp()
         Wh = conv.function_space().handle() if conv is not None else None
         cv = _lib.as_pd(_lib.f64(conv._vec)) if conv is not None else None
-        _lib.check(lib.fb_heat_create(V.handle(), Wh, cv, float(kappa), float(rho), float(cp),
-                                      _lib.as_pd(src) if src is not None else None, C.byref(h)), mesh.ctx, "Heat")
+        _lib.check(lib.fb_heat_create_supg(V.handle(), Wh, cv, float(kappa), float(rho), float(cp),
+                                           _lib.as_pd(src) if src is not None else None, 1 if supg_stabilization else 0,
+                                           float(source) if source is not None else 0.0, C.byref(h)), mesh.ctx, "Heat")
         self._h = h
 
     def __del__(self):

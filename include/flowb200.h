@@ -193,6 +193,11 @@ int fb_ns_correction_rhs(fb_ns *ns, double dt, double rho, double mu, int rotati
 /* ---- heat: replaces flow.heat.Heat (heat.py:20-122).  V scalar P1/P2, W vector P2 (conv) or NULL */
 int fb_heat_create(fb_space *V, fb_space *W, const double *conv, double kappa, double rho, double cp,
                    const double *source_load, fb_heat **out);
+/* with SUPG stabilisation (heat.py:60-86 + stabilization.py:13-152; triangles only like the reference);
+ * source_value: the constant source entering the SUPG residual term */
+int fb_heat_create_supg(fb_space *V, fb_space *W, const double *conv, double kappa, double rho, double cp,
+                        const double *source_load, int supg, double source_value, fb_heat **out);
+int fb_heat_supg_mass(fb_heat *heat, double *values_out); /* parity getter: SUPG part of M on V's pattern */
 int fb_heat_destroy(fb_heat *heat);
 /* alpha*M*u + beta*(A*u + b)   (heat.py:92-101) */
 int fb_heat_eval(fb_heat *heat, double alpha, double beta, const double *u, double *out);

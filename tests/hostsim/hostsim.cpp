@@ -139,6 +139,7 @@ static void rhs(int64_t nc, const int *cell_nodes, const double *xyz, double dt,
 }
 
 extern "C" {
+double hs_supg_tau(const double *X, const double *v, double eps, int p) { return fb_supg_tau(X, v, eps, p); }
 int hs_momentum(int dim, int64_t nc, const int *cell_nodes, const double *xyz, int64_t nbf, const int *bf_cell,
                 const int *bf_local, double dt, double rho, double mu, double theta, const double *ui, const double *u0,
                 const double *p0, int64_t ndofs, double *F, double *J) {

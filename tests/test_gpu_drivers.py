@@ -204,3 +204,13 @@ def test_boussinesq(gpu_ctx):
     assert 0.0 < d.norm(u1, "L2") < 1e-3         # buoyancy has started a (slow) flow
     assert abs(d.norm(theta1, "L2") - 293.0 * np.sqrt(theta1.function_space().mesh().volumes().sum())) < 0.5
     assert len(stats["banach"]) >= 3 and max(stats["banach"]) <= 10
+
+
+def test_boussinesq_with_supg(gpu_ctx):
+    """tests/test_boussinesq.py:91-97: the same run with supg_stabilization=True; with the tiny velocities of
+    the first instants the SUPG terms barely change the result (the reference's goldens differ by 1e-7 relative)."""
+    u0, _, th0, _ = compute_boussinesq(target_time=0.06, nx=8, supg=False)
+    u1, _, th1, _ = compute_boussinesq(target_time=0.06, nx=8, supg=True)
+    assert np.isfinite(th1.vector().get_local()).all()
+    assert np.abs(th1.vector().get_local() - th0.vector().get_local()).max() < 1e-3
+    assert np.abs(u1.vector().get_local() - u0.vector().get_local()).max() < 1e-6

@@ -98,3 +98,45 @@ def test_stokes_order(gpu_ctx):
         pe.append(d.errornorm(p_sol, p))
     assert mp.compute_numerical_order_of_convergence(hmax, ue)[0] > 1.9
     assert mp.compute_numerical_order_of_convergence(hmax, pe)[0] > 1.9
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_heat_supg(gpu_ctx, degree):
+    """supg_stabilization=True (heat.py:60-86 with the tau of stabilization.py): operator, SUPG mass part,
+    eval and an implicit Euler step against the oracle."""
+    from flow_b200 import _lib, dolfin as d, heat, stabilization
+    from flow_b200._lib import lib
+
+    om = oracle_mesh("tri_crossed")
+    m = facade_mesh(om)
+    Q = d.FunctionSpace(m, "Lagrange", degree)
+    W = d.VectorFunctionSpace(m, "CG", 2)
+    Wo = fem.Space(om, 2, 2)
+    X = Wo.node_coords
+    conv = np.stack([2.0 + np.sin(3 * X[:, 1]), -1.0 + X[:, 0] ** 2], 1).reshape(-1)   # convection dominated
+    kappa, rho, cp = 1e-3, 1.0, 1.0
+    Vo = fem.Space(om, degree, 1)
+    bd = Vo.boundary_dofs()
+    vals = 300.0 + 20.0 * Vo.node_coords[bd, 1]
+    oh = oheat.Heat(om, degree, conv, kappa, rho, cp, (bd, vals), supg=True, source=0.7,
+                    source_load=forms.expression_load_vector(Vo, lambda Y: np.full((Y.shape[0], 1), 0.7), 0))
+    bc = d.DirichletBC(Q, d.Expression("300.0 + 20.0*x[1]", degree=1), "on_boundary")
+    h = heat.Heat(Q, d.Function(W, conv.copy()), kappa, rho, cp, [bc], d.Constant(0.7), supg_stabilization=True)
+    mh = _lib.vp()
+    lib.fb_heat_matrix(h._h, 0, C.byref(mh))
+    A = mat_to_csr(mh, Q.nodes, 1)
+    assert abs(A - oh.A).max() / abs(oh.A).max() < 1e-12
+    ms = np.zeros(A.nnz)
+    _lib.check(lib.fb_heat_supg_mass(h._h, _lib.as_pd(ms)), gpu_ctx, "supg mass")
+    Ms = (oh.M - forms.lumped_vertex_mass(Vo)).tocsr()
+    import scipy.sparse as sp
+    got = sp.csr_matrix((ms, A.indices, A.indptr), shape=A.shape)
+    assert abs(got - Ms).max() / abs(Ms).max() < 1e-12
+    tau = stabilization.supg(m, d.Function(W, conv.copy()), kappa, degree).vertex_values()
+    assert np.allclose(tau, oheat.supg_tau(om, Wo, conv, kappa, degree), rtol=1e-13)
+    theta0 = 300.0 + np.random.default_rng(1).standard_normal(Vo.nnodes)
+    out = h.eval_alpha_M_beta_F(1.0, -0.3, d.Function(Q, theta0.copy()), 0.0)
+    assert rel(out.a, oh.eval_alpha_M_beta_F(1.0, -0.3, theta0)) < 1e-12
+    th1 = heat.ImplicitEuler(h).step(d.Function(Q, theta0.copy()), 0.0, 0.02)
+    th1o = oheat.implicit_euler_step(oh, theta0, 0.0, 0.02)
+    assert np.linalg.norm(th1._vec - th1o) / np.linalg.norm(th1o) < 1e-9

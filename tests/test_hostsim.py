@@ -48,3 +48,22 @@ def test_rhs_element_math(hostsim, name, rotational):
     assert rel(bp, forms.pressure_rhs(W, P, ui, p0, dt, rho, mu, bool(rotational))) < 1e-13
     Mv = sp.kron(forms.mass_matrix(fem.Space(om, 2, 1)), sp.eye(om.dim))
     assert rel(bu, forms.correction_rhs(W, P, ui, p1, p0, dt, rho, mu, bool(rotational)) - Mv @ ui) < 1e-12
+
+
+def test_supg_tau_device_routine(hostsim):
+    """fb_supg_tau (the routine k_heat_supg calls) vs the oracle's restatement of stabilization.py:50-143,
+    including the |b| ~ 0 early return and the small-Peclet Taylor branch."""
+    from oracle import heat as oheat
+
+    hostsim.hs_supg_tau.restype = C.c_double
+    om = oracle_mesh("tri_leftright")
+    W = fem.Space(om, 2, 2)
+    rng = np.random.default_rng(0)
+    for scale, eps in ((1.0, 0.6), (1e-7, 0.6), (1e-12, 0.6), (50.0, 1e-3)):
+        conv = scale * rng.standard_normal(W.ndofs)
+        ref = oheat.supg_tau(om, W, conv, eps, 2)
+        V = conv.reshape(-1, 2)[W.cell_nodes[:, :3]]
+        X = np.ascontiguousarray(om.points[om.cells].reshape(om.nc, 6))
+        got = np.array([[hostsim.hs_supg_tau(_pd(X[c]), _pd(np.ascontiguousarray(V[c, v])), C.c_double(eps), 2) for v in range(3)]
+                        for c in range(om.nc)])
+        assert np.allclose(got, ref, rtol=1e-12, atol=1e-300)
