@@ -140,6 +140,11 @@ def RectangleWithHoleMesh(p0, p1, nx, ny, center, radius, diagonal="left/right")
     return Mesh(*hostfem.structured_rectangle_with_hole((p0[0], p0[1]), (p1[0], p1[1]), nx, ny, center, radius, diagonal))
 
 
+def MshMesh(path_or_text):
+    """Mesh from a gmsh MSH 2.x ASCII file (or its text)."""
+    return Mesh(*hostfem.read_msh(path_or_text))
+
+
 class _NodeSpace(object):
     """fb_space handle of a scalar Lagrange node set (P1 or P2) + host views of its tables."""
 

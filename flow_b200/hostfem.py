@@ -249,3 +249,52 @@ def structured_rectangle_with_hole(a, b, nx, ny, center, radius, diagonal="left/
     remap = -np.ones(pts.shape[0], dtype=np.int64)
     remap[used] = np.arange(used.size)
     return pts[used], np.sort(remap[cells], axis=1).astype(np.int32)
+
+
+def read_msh(path_or_text):
+    """Minimal gmsh MSH 2.x ASCII reader: returns (points, cells) of the highest-dimensional
+    simplices (type 4 tetrahedra, else type 2 triangles).  Enough to load the meshes the reference's drivers
+    generate with pygmsh (tests/test_sealed_box.py:32-53) when a .msh file is at hand; gmsh itself is not needed."""
+    import os
+
+    text = open(path_or_text).read() if os.path.exists(str(path_or_text)) else str(path_or_text)
+    lines = text.splitlines()
+
+    def section(name):
+        i = lines.index("$" + name)
+        j = lines.index("$End" + name)
+        return lines[i + 1:j]
+
+    fmt = section("MeshFormat")[0].split()
+    if not fmt[0].startswith("2") or fmt[1] != "0":
+        raise ValueError("only MSH 2.x ASCII files are supported (got %r)" % (fmt,))
+    nodes = section("Nodes")
+    n = int(nodes[0])
+    ids = np.empty(n, dtype=np.int64)
+    xyz = np.empty((n, 3))
+    for k, ln in enumerate(nodes[1:n + 1]):
+        t = ln.split()
+        ids[k] = int(t[0])
+        xyz[k] = [float(t[1]), float(t[2]), float(t[3])]
+    elems = section("Elements")
+    tris, tets = [], []
+    for ln in elems[1:int(elems[0]) + 1]:
+        t = ln.split()
+        etype, ntags = int(t[1]), int(t[2])
+        conn = [int(v) for v in t[3 + ntags:]]
+        if etype == 2:
+            tris.append(conn)
+        elif etype == 4:
+            tets.append(conn)
+    cells = np.array(tets if tets else tris, dtype=np.int64)
+    if cells.size == 0:
+        raise ValueError("no triangles or tetrahedra in the file")
+    lookup = -np.ones(ids.max() + 1, dtype=np.int64)
+    lookup[ids] = np.arange(n)
+    cells = lookup[cells]
+    dim = 3 if tets else (2 if np.abs(xyz[:, 2]).max() == 0.0 else 3)
+    used = np.unique(cells)
+    remap = -np.ones(n, dtype=np.int64)
+    remap[used] = np.arange(used.size)
+    pts = xyz[used][:, :2] if (dim == 2 and not tets) else xyz[used]
+    return np.ascontiguousarray(pts), np.sort(remap[cells], axis=1).astype(np.int32)

@@ -81,3 +81,39 @@ def test_hostfem_matches_oracle(dim):
     lam, w = hostfem.quadrature(dim, 6)
     lo, wo = fem.simplex_quadrature(dim, 6)
     assert np.allclose(np.sort(w), np.sort(wo))
+
+
+MSH = """$MeshFormat
+2.2 0 8
+$EndMeshFormat
+$Nodes
+5
+1 0 0 0
+2 1 0 0
+3 1 1 0
+4 0 1 0
+7 0.5 0.5 0
+$EndNodes
+$Elements
+6
+1 15 2 0 1 1
+2 1 2 0 1 1 2
+3 2 2 0 5 1 2 7
+4 2 2 0 5 2 3 7
+5 2 2 0 5 3 4 7
+6 2 2 0 5 4 1 7
+$EndElements
+"""
+
+
+def test_msh_reader(tmp_path):
+    from flow_b200 import dolfin as d
+
+    m = d.MshMesh(MSH)
+    assert m.num_vertices() == 5 and m.num_cells() == 4 and m.dim == 2
+    assert abs(m.volumes().sum() - 1.0) < 1e-15
+    f = tmp_path / "unit.msh"
+    f.write_text(MSH)
+    m2 = d.MshMesh(str(f))
+    assert np.array_equal(m.cells(), m2.cells())
+    assert m.node_space(2).nnodes == 5 + 8 and m.node_space(1).on_boundary.sum() == 4
