@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(256)
   const int lane = threadIdx.x % T;
   const int64_t group = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / T;
   const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / T;
-  double d[2] = {0.0, 0.0};
+  double d[3] = {0.0, 0.0, 0.0};
   const int64_t nrows_pad = ((nrows + ngroups - 1) / ngroups) * ngroups;  // keep shuffles convergent
   for (int64_t row = group; row < nrows_pad; row += ngroups) {
     double acc[NC];
@@ -356,16 +356,25 @@ __global__ void __launch_bounds__(256)
       const int64_t dof = row * NC + lane;
       if (mask && mask[dof]) yc = x[dof];
       y[dof] = yc;
-      if (DOT >= 1) d[0] += w[dof] * yc;
-      if (DOT >= 2) d[1] += yc * yc;
+      if (DOT == 1 || DOT == 2) d[0] += w[dof] * yc;
+      if (DOT == 2) d[1] += yc * yc;
+      if (DOT == 3) {  // single-reduction CG: (w.x, y.x, x.x) with x the multiplied vector
+        const double xd = x[dof];
+        d[0] += w[dof] * xd;
+        d[1] += yc * xd;
+        d[2] += xd * xd;
+      }
     }
   }
   if (DOT >= 1) {
     if (DOT == 1) {
       double v1[1] = {d[0]};
       fb_grid_reduce<1>(v1, partials, counter, red, slot);
+    } else if (DOT == 2) {
+      double v2[2] = {d[0], d[1]};
+      fb_grid_reduce<2>(v2, partials, counter, red, slot);
     } else {
-      fb_grid_reduce<2>(d, partials, counter, red, slot);
+      fb_grid_reduce<3>(d, partials, counter, red, slot);
     }
   }
 }
@@ -519,7 +528,8 @@ static void launch_spmm(fb_ctx *ctx, const LinOp &A, const double *x, double *y,
             dv->counter, dv->red, slot, flag)
   if (dot_mode == 0) FB_SP(0);
   else if (dot_mode == 1) FB_SP(1);
-  else FB_SP(2);
+  else if (dot_mode == 2) FB_SP(2);
+  else FB_SP(3);
 #undef FB_SP
 }
 

@@ -11,6 +11,8 @@
 // the host enqueues between polls.  Multi-GPU: vectors hold owned entries first, ghosts
 // after; all vector kernels and dots run over the owned part, the SpMV wrapper refreshes
 // ghosts, each reducing kernel is followed by ONE all-reduce of its 1-2 slots.
+#include <cstdlib>
+
 #include "fb_ops.h"
 
 namespace {
@@ -253,8 +255,18 @@ int poll(fb_ctx *ctx, int *flag_out, int *iters_out) {
 
 }  // namespace
 
+int krylov_pcg_single_reduction(fb_ctx *ctx, const LinOp &A, const double *dinv, const double *b, double *x, double rtol,
+                                double ref_extra2, int maxit, int check_every, KrylovWork &w, int *iters);
+
 int krylov_pcg(fb_ctx *ctx, const LinOp &A, const double *dinv, const double *b, double *x, double rtol, double ref_extra2,
                int maxit, int check_every, KrylovWork &w, int *iters) {
+  // -1 (default): single-reduction CG where the iteration is latency bound (small systems, or several ranks:
+  // one all-reduce instead of two), classic PCG where it is bandwidth bound (measured at n = 74: P2 mass x 3,
+  // 9.9 M dofs: 0.81 vs 0.98 ms per iteration); 0 / 1 force one of them
+  static const int knob = getenv("FB_CG") ? atoi(getenv("FB_CG")) : -1;
+  const int variant = knob >= 0 ? knob : ((fb_is_distributed(ctx) || A.ndofs() < (int64_t(1) << 21)) ? 1 : 0);
+  if (variant == 1 && A.block == 1)
+    return krylov_pcg_single_reduction(ctx, A, dinv, b, x, rtol, ref_extra2, maxit, check_every, w, iters);
   fb_device_state *dv = ctx->dev;
   const int64_t n = A.ndofs();
   const int dist = fb_is_distributed(ctx) ? 1 : 0;
@@ -285,6 +297,106 @@ int krylov_pcg(fb_ctx *ctx, const LinOp &A, const double *dinv, const double *b,
     if (flag) break;
   }
   if (iters) *iters = flag ? done : it;
+  if (flag == 1) return FB_OK;
+  if (flag >= 2) return FB_ENAN;
+  return FB_ENOCONV_KRYLOV;
+}
+
+// ---------------------------------------------------------------- single-reduction PCG
+// Chronopoulos-Gear CG: per iteration ONE SpMV (with the three dot products gamma = r.u, delta = w.u,
+// |u|^2 fused into its epilogue), ONE all-reduce of those three numbers and ONE fused vector kernel.
+// Same Krylov space and stopping test as krylov_pcg; used where the iteration is latency bound
+// (pressure Poisson: 560 iterations of ~20 us kernels, and every NCCL call costs ~10 us).
+namespace {
+constexpr int S_CG3 = 20;   // gamma, delta, |u|^2 of the current iterate
+constexpr int S_CGST = 24;  // state[2][3]: alpha, gamma, tol2 per parity
+
+__global__ void k_cg3_start(int64_t n, const double *__restrict__ b, const double *__restrict__ dinv, double *r, double *u,
+                            double *p, double *s, double *x) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ri = b[i];
+    r[i] = ri;
+    u[i] = dinv[i] * ri;
+    p[i] = 0.0;
+    s[i] = 0.0;
+    x[i] = 0.0;
+  }
+}
+
+// it: iteration being applied (0-based).  red[S_CG3..] holds gamma_it, delta_it, |u_it|^2 (all-reduced).
+__global__ void k_cg3_update(int64_t n, int it, double rtol, double ref_extra2, const double *__restrict__ dinv,
+                             const double *__restrict__ w, double *u, double *r, double *p, double *s, double *x,
+                             double *red, int *flag, int *iters) {
+  if (*flag) return;
+  const int par = it & 1, prv = par ^ 1;
+  const double gamma = red[S_CG3], delta = red[S_CG3 + 1], zz = red[S_CG3 + 2];
+  double *st = red + S_CGST;
+  const double tol2 = (it == 0) ? rtol * rtol * (zz + ref_extra2) : st[3 * prv + 2];
+  // every thread evaluates the stopping test on the same all-reduced numbers: uniform decision
+  const bool bad = (zz != zz) || (gamma != gamma) || (delta != delta);
+  const bool conv = (it == 0) ? (zz + ref_extra2 == 0.0) : (zz <= tol2);
+  double alpha, beta;
+  if (it == 0) {
+    beta = 0.0;
+    alpha = gamma / delta;
+  } else {
+    const double alpha_old = st[3 * prv], gamma_old = st[3 * prv + 1];
+    beta = gamma / gamma_old;
+    alpha = gamma / (delta - beta * gamma / alpha_old);
+  }
+  const bool breakdown = !bad && !conv && !(alpha > 0.0);  // (p, A p) <= 0
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st[3 * par] = alpha;
+    st[3 * par + 1] = gamma;
+    st[3 * par + 2] = tol2;
+    if (bad || conv || breakdown) {
+      *flag = bad ? 3 : (conv ? 1 : 2);
+      *iters = it;
+    }
+  }
+  if (bad || conv || breakdown) return;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double pi = u[i] + beta * p[i];
+    const double si = w[i] + beta * s[i];
+    p[i] = pi;
+    s[i] = si;
+    x[i] += alpha * pi;
+    const double ri = r[i] - alpha * si;
+    r[i] = ri;
+    u[i] = dinv[i] * ri;
+  }
+}
+}  // namespace
+
+int krylov_pcg_single_reduction(fb_ctx *ctx, const LinOp &A, const double *dinv, const double *b, double *x, double rtol,
+                                double ref_extra2, int maxit, int check_every, KrylovWork &w, int *iters) {
+  fb_device_state *dv = ctx->dev;
+  const int64_t n = A.ndofs();
+  w.ensure(5, A.nlocal_dofs());
+  double *r = w.v[0].p, *u = w.v[1].p, *wv = w.v[2].p, *p = w.v[3].p, *s = w.v[4].p;
+  const int g = vgrid(ctx, n);
+  if (fb_is_distributed(ctx)) {  // the squared Dirichlet values entering the reference norm are a global sum
+    FB_CUDA(cudaMemcpyAsync(dv->red + S_CG3 + 3, &ref_extra2, sizeof(double), cudaMemcpyHostToDevice, dv->stream));
+    fb_allreduce_slots(ctx, S_CG3 + 3, 1);
+    FB_CUDA(cudaMemcpyAsync(dv->host_pinned, dv->red + S_CG3 + 3, sizeof(double), cudaMemcpyDeviceToHost, dv->stream));
+    FB_CUDA(cudaStreamSynchronize(dv->stream));
+    ref_extra2 = dv->host_pinned[0];
+  }
+  FB_CUDA(cudaMemsetAsync(dv->flag, 0, sizeof(int), dv->stream));
+  FB_CUDA(cudaMemsetAsync(dv->iters, 0, sizeof(int), dv->stream));
+  FB_LAUNCH(ctx, k_cg3_start, g, 256, 0, n, b, dinv, r, u, p, s, x);
+  int flag = 0, done = 0, it = 0;
+  if (check_every < 1) check_every = 1;
+  while (it <= maxit) {
+    const int batch = std::min(check_every, maxit + 1 - it);
+    for (int k = 0; k < batch; ++k, ++it) {
+      spmv(ctx, A, u, wv, 3, r, S_CG3, dv->flag);  // w = A u; gamma, delta, |u|^2 -> one all-reduce
+      FB_LAUNCH(ctx, k_cg3_update, g, 256, 0, n, it, rtol, ref_extra2, dinv, wv, u, r, p, s, x, dv->red, dv->flag, dv->iters);
+    }
+    poll(ctx, &flag, &done);
+    if (flag) break;
+  }
+  if (iters) *iters = flag ? done : maxit;
   if (flag == 1) return FB_OK;
   if (flag >= 2) return FB_ENAN;
   return FB_ENOCONV_KRYLOV;
