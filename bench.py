@@ -82,24 +82,21 @@ def cavity_bcs(d, W):
 
 
 def oracle_cavity_step_time(n, steps, warmup=0):
-    """Seconds per IPCS step of the oracle's Krylov-CPU variant on UnitCubeMesh(n)."""
-    from oracle import fem, navier_stokes as ons, solvers
+    """Seconds per IPCS step of the CPU port on UnitCubeMesh(n): oracle/_cstep.so (C++/OpenMP assembly with
+    the shared element routines + Jacobi-BiCGStab/CG on all host threads; validated against the numpy oracle in
+    tests/test_oracle.py).  Patterns and constant matrices come from the numpy oracle (set-up, untimed)."""
+    from oracle import cstep
 
-    om = fem.Mesh(*fem.unit_cube_mesh(n, n, n))
-    st = ons.IPCS(om, linear="krylov")
-    W = st.W
-    bd = W.boundary_dofs()
-    g = np.zeros((W.nnodes, 3))
-    g[W.node_coords[:, 2] > 1 - 1e-12, 0] = 1.0
-    g = g.reshape(-1)[bd]
-    u, p = np.zeros(W.ndofs), np.zeros(st.P.nnodes)
-    times = []
+    cv = cstep.CavityCPU(n)
+    u, p = np.zeros(cv.W.ndofs), np.zeros(cv.P.nnodes)
+    times, stats = [], None
     for k in range(warmup + steps):
         t0 = time.perf_counter()
-        u, p = st.step(DT, u, p, (bd, g), None, RHO, MU, None, None, tol=TOL)
+        u, p, stats = cv.step(u, p, DT, RHO, MU, TOL)
         if k >= warmup:
             times.append(time.perf_counter() - t0)
-    return float(np.mean(times)), W.ndofs + st.P.nnodes, solvers.cbaseline().cb_num_threads(), dict(st.info)
+    info = dict(zip(("newton_its", "momentum_its", "pressure_its", "correction_its"), stats))
+    return float(np.mean(times)), cv.ndofs, cv.threads(), info
 
 
 def run_reference(args, rank):
@@ -109,9 +106,10 @@ def run_reference(args, rank):
     nd_full = sum(dof_counts(n_full))
     sec, nd, threads, info = oracle_cavity_step_time(args.cpu_n, max(1, args.steps), min(args.warmup, 1))
     value = (1.0 / sec) * (nd / float(nd_full))
-    sample = ("oracle port (numpy assembly + C/OpenMP Jacobi-BiCGStab/CG) of the same cavity on UnitCubeMesh(%d) = %d dofs, "
-              "%.2f s/step measured; steps/s extrapolated linearly in dofs to %d dofs (optimistic for the CPU). "
-              "FEniCS/PETSc itself is not installable here." % (args.cpu_n, nd, sec, nd_full))
+    sample = ("CPU port oracle/_cstep.so (C++/OpenMP assembly + Jacobi-BiCGStab/CG, same algorithm as the GPU path) of the "
+              "same cavity on UnitCubeMesh(%d) = %d dofs, %.2f s/step measured on %d threads (iterations %s); steps/s "
+              "extrapolated linearly in dofs to %d dofs (optimistic for the CPU: Krylov counts grow with the mesh). "
+              "FEniCS/PETSc itself is not installable here." % (args.cpu_n, nd, sec, threads, info, nd_full))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -131,7 +129,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=74, help="cells per edge of the unit cube (74 -> 10.3 M dofs)")
-    ap.add_argument("--cpu-n", type=int, default=10, help="cube size of the bounded CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=32, help="cube size of the bounded CPU sample (32 -> 0.86 M dofs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -285,11 +283,11 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same cavity
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sec, nd, threads, info = oracle_cavity_step_time(args.cpu_n, 1, 0)
+        sec, nd, threads, info = oracle_cavity_step_time(args.cpu_n, 2, 1)
         nd_full = nu_global + np_global
         cpu = {"value": (1.0 / sec) * (nd / float(nd_full)), "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "oracle Krylov-CPU IPCS step on UnitCubeMesh(%d) = %d dofs: %.2f s/step (numpy assembly + C/OpenMP "
-                         "Jacobi-Krylov); extrapolated linearly in dofs to %d" % (args.cpu_n, nd, sec, nd_full)}
+               "sample": "CPU port oracle/_cstep.so (C++/OpenMP, same algorithm) on UnitCubeMesh(%d) = %d dofs: %.2f s/step on %d "
+                         "threads, iterations %s; extrapolated linearly in dofs to %d" % (args.cpu_n, nd, sec, threads, info, nd_full)}
 
     if rank == 0:
         avg = lambda k: float(np.mean([h[k] for h in timed]))

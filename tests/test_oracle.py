@@ -164,3 +164,19 @@ def test_heat_lumped_mass_and_maximum_principle():
     for _ in range(3):
         th = oheat.implicit_euler_step(h, th, 0.0, 10.0)
     assert th.min() > 293.0 - 1e-9 and th.max() < 320.0 + 1e-9
+
+
+def test_compiled_cpu_baseline_matches_numpy_oracle():
+    """oracle/_cstep.so (bench.py's CPU arm) vs the numpy oracle: two cavity steps, 1e-8."""
+    from oracle import cstep
+
+    cv = cstep.CavityCPU(4)
+    ost = ons.IPCS(cv.mesh)
+    uo, po = np.zeros(cv.W.ndofs), np.zeros(cv.P.nnodes)
+    uc, pc = uo.copy(), po.copy()
+    for _ in range(2):
+        uo, po = ost.step(1e-2, uo, po, cv.bc, None, 1.0, 1e-2, None, None, tol=1e-10)
+        uc, pc, stats = cv.step(uc, pc)
+    assert np.linalg.norm(uc - uo) / np.linalg.norm(uo) < 1e-8
+    assert np.linalg.norm((pc - pc.mean()) - (po - po.mean())) / np.linalg.norm(po - po.mean()) < 1e-7
+    assert stats[0] <= 3
