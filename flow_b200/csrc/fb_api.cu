@@ -399,6 +399,7 @@ struct fb_ns {
   int64_t nu_o = 0, np_o = 0;  // owned dofs (== local on a single rank)
   fb_ns_opts opts;
   fb_mat Ap, Mu, J;
+  DBuf<double> qstate;  // u, grad u of the current Newton iterate at the cell quadrature points (F kernel -> J kernel)
   DBuf<double> u0, p0, ui, p1, u1, F, Fconst, delta, load, ftmp, bp, bu, dinv_p, dinv_u, binv, tmp_u, tmp_p, xg_u, xg_p, Ap_bc;
   DBuf<uint8_t> mask_u, mask_p;
   DBuf<int64_t> ubc_dofs, pbc_dofs;
@@ -451,8 +452,17 @@ static bool ns_build_load(fb_ns *ns, int forcing, const double *f0, const double
   return true;
 }
 
+static double *ns_qstate(fb_ns *ns) {
+  const int D = ns->D;
+  const int64_t nq = D == 2 ? 7 : 14;
+  ns->qstate.alloc((size_t)(ns->W->nc * nq * D * (D + 1)));
+  return ns->qstate.p;
+}
+
 static void ns_assemble_F(fb_ns *ns, const MomentumArgs &a, bool have_load) {
-  assemble_momentum_F(ns->ctx, *ns->W, a, ns->F.p);
+  FB_CUDA(cudaMemsetAsync(ns->F.p, 0, sizeof(double) * ns->nu, ns->ctx->dev->stream));
+  assemble_momentum_F_old_state(ns->ctx, *ns->W, a, ns->F.p);
+  assemble_momentum_F_new_state(ns->ctx, *ns->W, a, ns->F.p, ns_qstate(ns));
   if (have_load) vec_axpy(ns->ctx, ns->F.p, -a.dt / a.rho, ns->load.p, ns->nu_o);
 }
 
@@ -567,7 +577,7 @@ int fb_ns_residual(fb_ns *ns, double dt, double rho, double mu, double theta, co
     have_load = true;
   }
   ns_assemble_F(ns, a, have_load);
-  if (want_J) assemble_momentum_J(_ctx, *ns->W, a, ns->J.val.p);
+  if (want_J) assemble_momentum_J(_ctx, *ns->W, a, ns->J.val.p, ns->qstate.p);
   FB_CUDA(cudaMemcpyAsync(F_out, ns->F.p, sizeof(double) * ns->nu, cudaMemcpyDeviceToHost, st));
   FB_CUDA(cudaStreamSynchronize(st));
   FB_API_END
@@ -666,7 +676,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
   auto residual = [&]() {
     FB_CUDA(cudaEventRecord(dv->ev[8], st));
     FB_CUDA(cudaMemcpyAsync(ns->F.p, ns->Fconst.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
-    assemble_momentum_F_new_state(ctx, *ns->W, ma, ns->F.p);
+    assemble_momentum_F_new_state(ctx, *ns->W, ma, ns->F.p, ns_qstate(ns));
     bc_residual(ctx, ns->F.p, ns->ui.p, ns->ubc_dofs.p, ns->ubc_vals.p, n_ubc);
     FB_CUDA(cudaEventRecord(dv->ev[9], st));
     const double nrm = vec_norm2_sync(ctx, ns->F.p, nu_o);
@@ -693,7 +703,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     // (chord iteration) as long as the previous update contracted the residual well -- the convergence
     // test on |F| is unchanged, only the path to it is cheaper (opts.jacobian_reuse = 0: plain Newton).
     if (!have_J || !o.jacobian_reuse || !reuse_ok) {
-      assemble_momentum_J(ctx, *ns->W, ma, ns->J.val.p);
+      assemble_momentum_J(ctx, *ns->W, ma, ns->J.val.p, ns->qstate.p);
       bc_rows_identity_blocked(ctx, *ns->W, D, ns->J.val.p, ns->ubc_dofs.p, n_ubc);
       jacobi_setup_blocked(ctx, *ns->W, D, ns->J.val.p, o.momentum_precond == FB_BLOCK_JACOBI ? 1 : 0, ns->binv.p);
       have_J = true;
