@@ -25,7 +25,7 @@ FORWARD_EULER, BACKWARD_EULER, CRANK_NICOLSON = 0, 1, 2
 DEVICE_PTRS, ROTATIONAL, CHORIN = 1, 2, 4
 F_NONE, F_CONSTANT, F_NODAL, F_LOAD = 0, 1, 2, 3
 BICGSTAB, GMRES, CG = 0, 1, 2
-JACOBI, BLOCK_JACOBI, CHEBYSHEV = 0, 1, 2
+JACOBI, BLOCK_JACOBI, CHEBYSHEV, AMG = 0, 1, 2, 3
 
 vp = C.c_void_p
 i64 = C.c_int64
@@ -52,7 +52,10 @@ class NSOpts(C.Structure):
         ("chebyshev_degree", C.c_int),
         ("jacobian_reuse", C.c_int),
         ("adaptive_forcing", C.c_int),
-        ("reserved", C.c_int * 6),
+        ("jacobian_across_steps", C.c_int),
+        ("warm_start", C.c_int),
+        ("jacobian_fp32", C.c_int),
+        ("reserved", C.c_int * 3),
     ]
 
 
@@ -125,6 +128,7 @@ SIGNATURES = {
     "fb_ns_opts_default": (C.c_int, [C.POINTER(NSOpts)]),
     "fb_ns_create": (C.c_int, [vp, vp, C.POINTER(NSOpts), C.POINTER(vp)]),
     "fb_ns_destroy": (C.c_int, [vp]),
+    "fb_ns_amg_info": (C.c_int, [vp, C.POINTER(C.c_int), pd, C.POINTER(C.c_int), C.c_int]),
     "fb_ns_step": (
         C.c_int,
         [vp, dbl, dbl, dbl, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, i64, pi64, pd, i64, pi64, pd, dbl, vp, vp,

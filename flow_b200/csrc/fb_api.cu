@@ -328,7 +328,7 @@ int fb_mat_bench_spmv(fb_mat *mat, int ncomp, int reps, double *ms_avg, double *
 static int solve_cg_masked(fb_ctx *ctx, const fb_mat &M, int ncomp, double *b_dev /* modified */, double *x_dev,
                            int64_t nbc, const int64_t *bc_dofs_dev, const double *bc_vals_dev, double g2,
                            uint8_t *mask_dev, double *dinv_dev, double *xg_dev, double *tmp_dev, double rtol, int maxit,
-                           int check_every, KrylovWork &kw, int *iters) {
+                           int check_every, KrylovWork &kw, int *iters, bool warm = false) {
   const int64_t n = M.sp->n_owned * ncomp;  // owned dofs
   LinOp Afull = make_linop(M, ncomp, nullptr);
   const uint8_t *mask = nullptr;
@@ -344,7 +344,7 @@ static int solve_cg_masked(fb_ctx *ctx, const fb_mat &M, int ncomp, double *b_de
   }
   jacobi_setup_scalar(ctx, *M.sp, M.val.p, ncomp, mask, dinv_dev);
   LinOp A = make_linop(M, ncomp, mask);
-  int st = krylov_pcg(ctx, A, dinv_dev, b_dev, x_dev, rtol, g2, maxit, check_every, kw, iters);
+  int st = krylov_pcg(ctx, A, dinv_dev, b_dev, x_dev, rtol, g2, maxit, check_every, kw, iters, nullptr, warm);
   if (nbc > 0) vec_axpy(ctx, x_dev, 1.0, xg_dev, n);
   return st;
 }
@@ -406,7 +406,34 @@ struct fb_ns {
   DBuf<double> ubc_vals, pbc_vals;
   KrylovWork kw_u, kw_p;
   double contraction = 0.0;  // |F| after / before the first Newton update of the previous step
+  // chord Jacobian carried across steps: valid for (dt, rho, mu, theta, constrained set) of its assembly
+  bool J_valid = false;
+  double J_key[4] = {0, 0, 0, 0};
+  uint64_t J_bc_hash = 0;
+  int J_age = 0;             // steps since the assembly
+  int newton_fresh = 0;      // Newton iterations of the last step that started with a fresh Jacobian
+  int newton_last = 0;
+  DBuf<float> J32;           // fp32 copy of J for the Krylov solves (opts.jacobian_fp32)
+  fb_amg *amg_p = nullptr;      // AMG hierarchy of the P1 stiffness (pure Neumann variant)
+  fb_amg *amg_pbc = nullptr;    // ... of the Dirichlet-eliminated matrix, rebuilt when the constrained set changes
+  std::vector<int64_t> amg_pbc_dofs;
+  ~fb_ns() {
+    if (amg_p) amg_destroy(amg_p);
+    if (amg_pbc) amg_destroy(amg_pbc);
+  }
 };
+
+// AMG hierarchy of a P1 matrix living on ns->P's pattern (values on the device)
+static fb_amg *ns_build_amg(fb_ns *ns, const double *val_dev) {
+  fb_space *Ph = ns->Ph;
+  fb_space_build_pattern(Ph);
+  const int64_t nn = Ph->nnodes, nnz = (int64_t)Ph->indices.size();
+  std::vector<int> rp(nn + 1);
+  for (int64_t i = 0; i <= nn; ++i) rp[i] = (int)Ph->indptr[i];
+  std::vector<double> val((size_t)nnz);
+  FB_CUDA(cudaMemcpy(val.data(), val_dev, sizeof(double) * nnz, cudaMemcpyDeviceToHost));
+  return amg_setup(ns->ctx, (int)Ph->n_owned, rp.data(), Ph->indices.data(), val.data());
+}
 
 static void ns_upload(fb_ns *ns, DBuf<double> &dst, const double *src, int64_t n, bool dev) {
   cudaStream_t st = ns->ctx->dev->stream;
@@ -489,7 +516,7 @@ int fb_ns_opts_default(fb_ns_opts *o) {
   std::memset(o, 0, sizeof(*o));
   o->momentum_solver = FB_BICGSTAB;
   o->momentum_precond = FB_BLOCK_JACOBI;
-  o->pressure_precond = FB_JACOBI;
+  o->pressure_precond = FB_AMG;
   o->newton_maxit = 10;
   o->newton_atol = 1e-10;
   o->momentum_rtol = 1e-12;
@@ -501,6 +528,9 @@ int fb_ns_opts_default(fb_ns_opts *o) {
   o->chebyshev_degree = 4;
   o->jacobian_reuse = 1;
   o->adaptive_forcing = 1;
+  o->jacobian_across_steps = 1;
+  o->warm_start = 1;
+  o->jacobian_fp32 = 0;
   return FB_OK;
 }
 
@@ -547,8 +577,20 @@ int fb_ns_create(fb_space *Wsp, fb_space *Psp, const fb_ns_opts *opts, fb_ns **o
   ns->mask_u.alloc((size_t)ns->nu);
   ns->mask_p.alloc((size_t)ns->np);
   FB_CUDA(cudaStreamSynchronize(ctx->dev->stream));
+  // tiny systems: the hierarchy would have one level and Jacobi-CG's kernels are cheaper than a V-cycle's
+  if (ns->opts.pressure_precond == FB_AMG && ns->np_o < 4096) ns->opts.pressure_precond = FB_JACOBI;
+  if (ns->opts.pressure_precond == FB_AMG) ns->amg_p = ns_build_amg(ns.get(), ns->Ap.val.p);
   *out = ns.release();
   FB_API_END
+}
+
+int fb_ns_amg_info(fb_ns *ns, int *levels, double *complexity, int *sizes, int max_sizes) {
+  if (!ns || !ns->amg_p) return FB_EINVAL;
+  const int nl = amg_num_levels(ns->amg_p);
+  if (levels) *levels = nl;
+  if (complexity) *complexity = amg_complexity(ns->amg_p);
+  for (int l = 0; sizes && l < nl && l < max_sizes; ++l) sizes[l] = amg_level_size(ns->amg_p, l);
+  return FB_OK;
 }
 
 int fb_ns_destroy(fb_ns *ns) {
@@ -687,7 +729,16 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
   };
   double r = residual();
   int newton = 0;
-  bool have_J = false, reuse_ok = true;
+  // A Jacobian from an earlier step is kept as the chord operator while nothing it depends on (other than the
+  // linearisation point) changed and it still contracts as well as a fresh one did
+  uint64_t bc_hash = 1469598103934665603ull;
+  for (int64_t i = 0; i < n_ubc; ++i) bc_hash = (bc_hash ^ (uint64_t)ubc_dofs[i]) * 1099511628211ull;
+  const double J_key[4] = {dt, rho, mu, theta};
+  bool have_J = o.jacobian_reuse && o.jacobian_across_steps && ns->J_valid && bc_hash == ns->J_bc_hash &&
+                std::memcmp(J_key, ns->J_key, sizeof(J_key)) == 0 && ns->contraction > 0.0 && ns->contraction < 1e-2 &&
+                ns->newton_last <= ns->newton_fresh;
+  const bool started_stale = have_J;
+  bool reuse_ok = true;
   s.reserved[0] = r;  // reserved[k] = |F| after k Newton updates (first 8)
   const int mom_check = o.check_every > 0 ? o.check_every : 2;
   float ms;
@@ -706,7 +757,15 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
       assemble_momentum_J(ctx, *ns->W, ma, ns->J.val.p, ns->qstate.p);
       bc_rows_identity_blocked(ctx, *ns->W, D, ns->J.val.p, ns->ubc_dofs.p, n_ubc);
       jacobi_setup_blocked(ctx, *ns->W, D, ns->J.val.p, o.momentum_precond == FB_BLOCK_JACOBI ? 1 : 0, ns->binv.p);
+      if (o.jacobian_fp32) {
+        ns->J32.alloc(ns->J.val.n);
+        vec_to_float(ctx, ns->J32.p, ns->J.val.p, (int64_t)ns->J.val.n);
+      }
       have_J = true;
+      ns->J_valid = true;
+      std::memcpy(ns->J_key, J_key, sizeof(J_key));
+      ns->J_bc_hash = bc_hash;
+      ns->J_age = 0;
       s.reserved[7] += 1.0;  // number of Jacobian assemblies
     }
     FB_CUDA(cudaEventRecord(dv->ev[5], st));
@@ -721,7 +780,8 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
         atol_inner = std::max(atol_inner, 0.5 * predicted);
     }
     int its = 0;
-    const LinOp Jop = make_linop(ns->J, 1, nullptr);
+    LinOp Jop = make_linop(ns->J, 1, nullptr);
+    if (o.jacobian_fp32) Jop.val32 = ns->J32.p;
     // Only the first Newton update moves the Dirichlet dofs (delta = ui - g there); lift them so
     // that the Krylov space lives on the free dofs (BiCGStab breaks down otherwise).
     const bool lifted = (newton == 0 && n_ubc > 0);
@@ -752,6 +812,9 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
   }
   s.newton_its = newton;
   s.newton_residual = r;
+  ns->newton_last = newton;
+  if (!started_stale) ns->newton_fresh = newton;
+  ns->J_age++;
   FB_CUDA(cudaEventRecord(dv->ev[1], st));
 
   // ---- pressure Poisson (pressure_correction.py:258-433)
@@ -772,13 +835,31 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     jacobi_setup_scalar(ctx, *ns->P, ns->Ap_bc.p, 1, nullptr, ns->dinv_p.p);
     LinOp A = make_linop(ns->Ap, 1, nullptr);
     A.val = ns->Ap_bc.p;
-    status = krylov_pcg(ctx, A, ns->dinv_p.p, ns->bp.p, ns->p1.p, tol, 0.0, o.pressure_maxit, p_check, ns->kw_p,
-                        &s.pressure_its);
+    fb_amg *amg = nullptr;
+    if (o.pressure_precond == FB_AMG) {
+      std::vector<int64_t> key(pbc_dofs, pbc_dofs + n_pbc);
+      if (!ns->amg_pbc || key != ns->amg_pbc_dofs) {  // hierarchy depends on the constrained set only
+        if (ns->amg_pbc) amg_destroy(ns->amg_pbc);
+        FB_CUDA(cudaStreamSynchronize(st));
+        ns->amg_pbc = ns_build_amg(ns, ns->Ap_bc.p);
+        ns->amg_pbc_dofs.swap(key);
+      }
+      amg = ns->amg_pbc;
+    }
+    const bool warm = o.warm_start && !(flags & FB_CHORIN);
+    if (warm) {  // x0 = p0 with the boundary values imposed
+      FB_CUDA(cudaMemcpyAsync(ns->p1.p, ns->p0.p, sizeof(double) * np, cudaMemcpyDeviceToDevice, st));
+      vec_set_at(ctx, ns->p1.p, ns->pbc_dofs.p, ns->pbc_vals.p, n_pbc);
+    }
+    status = krylov_pcg(ctx, A, ns->dinv_p.p, ns->bp.p, ns->p1.p, tol, 0.0, o.pressure_maxit, amg ? 4 : p_check, ns->kw_p,
+                        &s.pressure_its, amg, warm);
   } else {
     // pure Neumann: CG on the singular, consistent system from x0 = 0 (:340-432)
     jacobi_setup_scalar(ctx, *ns->P, ns->Ap.val.p, 1, nullptr, ns->dinv_p.p);
+    const bool warm = o.warm_start && !(flags & FB_CHORIN);
+    if (warm) FB_CUDA(cudaMemcpyAsync(ns->p1.p, ns->p0.p, sizeof(double) * np, cudaMemcpyDeviceToDevice, st));
     status = krylov_pcg(ctx, make_linop(ns->Ap, 1, nullptr), ns->dinv_p.p, ns->bp.p, ns->p1.p, tol, 0.0,
-                        o.pressure_maxit, p_check, ns->kw_p, &s.pressure_its);
+                        o.pressure_maxit, ns->amg_p ? 4 : p_check, ns->kw_p, &s.pressure_its, ns->amg_p, warm);
   }
   if (status != FB_OK) {
     char buf[160];
@@ -791,9 +872,13 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
   // ---- velocity correction (pressure_correction.py:436-465)
   spmv(ctx, make_linop(ns->Mu, D, nullptr), ns->ui.p, ns->bu.p);
   assemble_correction_grad(ctx, *ns->W, *ns->P, dt, rho, mu, rotational, ns->ui.p, ns->p1.p, ns->p0.p, ns->bu.p);
+  if (o.warm_start) {  // x0 = ui on the free dofs (the lifted unknown vanishes on the constrained ones)
+    FB_CUDA(cudaMemcpyAsync(ns->u1.p, ns->ui.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
+    vec_zero_at(ctx, ns->u1.p, ns->ubc_dofs.p, n_ubc);
+  }
   status = solve_cg_masked(ctx, ns->Mu, D, ns->bu.p, ns->u1.p, n_ubc, ns->ubc_dofs.p, ns->ubc_vals.p, g2u, ns->mask_u.p,
                            ns->dinv_u.p, ns->xg_u.p, ns->tmp_u.p, tol, o.correction_maxit,
-                           o.check_every > 0 ? o.check_every : 10, ns->kw_u, &s.correction_its);
+                           o.check_every > 0 ? o.check_every : 10, ns->kw_u, &s.correction_its, o.warm_start != 0);
   if (status != FB_OK) {
     char buf[160];
     snprintf(buf, sizeof buf, "velocity-correction CG failed after %d iterations (%s)", s.correction_its,

@@ -379,6 +379,112 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Same product with U row chunks per lane in flight (all index / value / x loads of a row are issued before the
+// FMAs) and, if CHUNKED, a contiguous range of rows per block instead of a grid-stride walk: neighbouring rows
+// share most of their columns, so a block that sweeps consecutive rows finds its x gathers in L1.
+template <int NC, int T, int DOT, int U, int CHUNKED, int PAIR = 0>
+__global__ void __launch_bounds__(256)
+    k_spmm_u(int64_t nrows, const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val,
+             const uint8_t *__restrict__ mask, const double *__restrict__ x, double *__restrict__ y,
+             const double *__restrict__ w, double *partials, unsigned int *counter, double *red, int slot,
+             const int *__restrict__ flag, int64_t xlen) {
+  if (flag && *flag) return;
+  const int lane = threadIdx.x % T;
+  constexpr int RPB = 256 / T;  // rows per block per sweep
+  const int64_t per_block = (((nrows + gridDim.x - 1) / gridDim.x + RPB - 1) / RPB) * RPB;
+  int64_t row, row_end, stride;
+  if (CHUNKED) {
+    row = blockIdx.x * per_block + threadIdx.x / T;
+    row_end = (blockIdx.x + 1) * per_block;  // padded: all groups of the block run the same trip count
+    stride = RPB;
+  } else {
+    const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / T;
+    row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / T;
+    row_end = ((nrows + ngroups - 1) / ngroups) * ngroups;
+    stride = ngroups;
+  }
+  double d[3] = {0.0, 0.0, 0.0};
+  for (; row < row_end; row += stride) {
+    double acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+    if (row < nrows) {
+      const int r0 = rowptr[row], r1 = rowptr[row + 1];
+      for (int k0 = r0 + lane; k0 < r1; k0 += T * U) {
+        int64_t j[U];
+        double a[U], xv[U][NC];
+#pragma unroll
+        for (int u = 0; u < U; ++u) j[u] = (k0 + u * T < r1) ? col[k0 + u * T] : -1;
+        if (PAIR && NC == 3) {
+          // the three values of node j sit at doubles 3j .. 3j+2: two aligned 16-byte loads cover them for either
+          // parity of j (instead of three 8-byte loads; the gather is bound by L1 wavefronts, not by bytes)
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (j[u] >= 0) {
+              const int64_t e = 3 * j[u];
+              const double2 lo = *reinterpret_cast<const double2 *>(x + (e & ~int64_t(1)));
+              double2 hi;
+              if ((e | 1) + 3 <= xlen)
+                hi = *reinterpret_cast<const double2 *>(x + (e & ~int64_t(1)) + 2);
+              else
+                hi = make_double2(x[e + 2], 0.0);  // last node of an odd-sized vector: stay inside the array
+              const bool odd = e & 1;
+              xv[u][0] = odd ? lo.y : lo.x;
+              xv[u][1] = odd ? hi.x : lo.y;
+              xv[u][2] = odd ? hi.y : hi.x;
+            } else {
+              xv[u][0] = xv[u][1] = xv[u][2] = 0.0;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) xv[u][c] = (j[u] >= 0) ? x[j[u] * NC + c] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) a[u] = (j[u] >= 0) ? __ldcs(&val[k0 + u * T]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) acc[c] += a[u] * xv[u][c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int o = T / 2; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    if (row < nrows && lane < NC) {
+      double yc = acc[0];
+#pragma unroll
+      for (int c = 1; c < NC; ++c)
+        if (lane == c) yc = acc[c];
+      const int64_t dof = row * NC + lane;
+      if (mask && mask[dof]) yc = x[dof];
+      y[dof] = yc;
+      if (DOT == 1 || DOT == 2) d[0] += w[dof] * yc;
+      if (DOT == 2) d[1] += yc * yc;
+      if (DOT == 3) {
+        const double xd = x[dof];
+        d[0] += w[dof] * xd;
+        d[1] += yc * xd;
+        d[2] += xd * xd;
+      }
+    }
+  }
+  if (DOT >= 1) {
+    if (DOT == 1) {
+      double v1[1] = {d[0]};
+      fb_grid_reduce<1>(v1, partials, counter, red, slot);
+    } else if (DOT == 2) {
+      double v2[2] = {d[0], d[1]};
+      fb_grid_reduce<2>(v2, partials, counter, red, slot);
+    } else {
+      fb_grid_reduce<3>(d, partials, counter, red, slot);
+    }
+  }
+}
+
 // D x D row-planar block CSR; one warp (T = 32) or half warp per block row.
 template <int D, int T, int DOT>
 __global__ void __launch_bounds__(256)
@@ -434,28 +540,39 @@ __global__ void __launch_bounds__(256)
 
 // Same product, U independent row chunks per lane in flight (index -> x gather -> values are
 // issued for all chunks before the FMAs) to cover DRAM latency with fewer resident warps.
-template <int D, int T, int DOT, int U, int MINB>
+template <int D, int T, int DOT, int U, int MINB, typename VT = double, int CHUNKED = 0>
 __global__ void __launch_bounds__(256, MINB)
-    k_bspmv_u(int64_t nrows, const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val,
+    k_bspmv_u(int64_t nrows, const int *__restrict__ rowptr, const int *__restrict__ col, const VT *__restrict__ val,
               const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, double *partials,
               unsigned int *counter, double *red, int slot, const int *__restrict__ flag) {
   if (flag && *flag) return;
   const int lane = threadIdx.x % T;
-  const int64_t group = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / T;
-  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / T;
   double d[2] = {0.0, 0.0};
-  const int64_t nrows_pad = ((nrows + ngroups - 1) / ngroups) * ngroups;
-  for (int64_t row = group; row < nrows_pad; row += ngroups) {
+  int64_t row, nrows_pad, stride;
+  if (CHUNKED) {  // a contiguous range of rows per block (see k_spmm_u)
+    constexpr int RPB = 256 / T;
+    const int64_t per_block = (((nrows + gridDim.x - 1) / gridDim.x + RPB - 1) / RPB) * RPB;
+    row = blockIdx.x * per_block + threadIdx.x / T;
+    nrows_pad = (blockIdx.x + 1) * per_block;
+    stride = RPB;
+  } else {
+    const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / T;
+    row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / T;
+    nrows_pad = ((nrows + ngroups - 1) / ngroups) * ngroups;
+    stride = ngroups;
+  }
+  for (; row < nrows_pad; row += stride) {
     double acc[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) acc[i] = 0.0;
     if (row < nrows) {
       const int r0 = rowptr[row];
       const int len = (rowptr[row + 1] - r0) * D;
-      const double *v = val + (int64_t)r0 * (D * D);
+      const VT *v = val + (int64_t)r0 * (D * D);
       for (int t0 = lane; t0 < len; t0 += T * U) {
         int c[U];
-        double xv[U], a[U][D];
+        double xv[U];
+        VT a[U][D];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int t = t0 + u * T;
@@ -467,12 +584,12 @@ __global__ void __launch_bounds__(256, MINB)
         for (int u = 0; u < U; ++u) {
           const int t = t0 + u * T;
 #pragma unroll
-          for (int i = 0; i < D; ++i) a[u][i] = (t < len) ? __ldcs(&v[i * len + t]) : 0.0;
+          for (int i = 0; i < D; ++i) a[u][i] = (t < len) ? __ldcs(&v[i * len + t]) : VT(0);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
-          for (int i = 0; i < D; ++i) acc[i] += a[u][i] * xv[u];
+          for (int i = 0; i < D; ++i) acc[i] += (double)a[u][i] * xv[u];
       }
     }
 #pragma unroll
@@ -510,10 +627,31 @@ static void launch_bspmv_u(fb_ctx *ctx, const LinOp &A, const double *x, double 
 #define FB_BSU(DOT)                                                                                                    \
   FB_LAUNCH(ctx, (k_bspmv_u<D, T, DOT, U, MINB>), g, block, 0, A.nrows, A.rowptr, A.col, A.val, x, y, w, dv->partials, \
             dv->counter, dv->red, slot, flag)
+#define FB_BSUC(DOT)                                                                                                    \
+  FB_LAUNCH(ctx, (k_bspmv_u<D, T, DOT, U, MINB, double, 1>), g, block, 0, A.nrows, A.rowptr, A.col, A.val, x, y, w,      \
+            dv->partials, dv->counter, dv->red, slot, flag)
+#define FB_BSU32(DOT)                                                                                                   \
+  FB_LAUNCH(ctx, (k_bspmv_u<D, T, DOT, U, MINB, float>), g, block, 0, A.nrows, A.rowptr, A.col, A.val32, x, y, w,        \
+            dv->partials, dv->counter, dv->red, slot, flag)
+  if (A.val32) {  // fp32-stored operator (mixed-precision chord Jacobian); accumulation stays fp64
+    if (dot_mode == 0) FB_BSU32(0);
+    else if (dot_mode == 1) FB_BSU32(1);
+    else FB_BSU32(2);
+    return;
+  }
+  static const int chunked = getenv("FB_BSPMV_CHUNK") ? atoi(getenv("FB_BSPMV_CHUNK")) : 0;
+  if (chunked) {
+    if (dot_mode == 0) FB_BSUC(0);
+    else if (dot_mode == 1) FB_BSUC(1);
+    else FB_BSUC(2);
+    return;
+  }
   if (dot_mode == 0) FB_BSU(0);
   else if (dot_mode == 1) FB_BSU(1);
   else FB_BSU(2);
 #undef FB_BSU
+#undef FB_BSUC
+#undef FB_BSU32
 }
 
 template <int NC, int T>
@@ -531,6 +669,23 @@ static void launch_spmm(fb_ctx *ctx, const LinOp &A, const double *x, double *y,
   else if (dot_mode == 2) FB_SP(2);
   else FB_SP(3);
 #undef FB_SP
+}
+
+template <int NC, int T, int U, int CHUNKED, int PAIR = 0>
+static void launch_spmm_u(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_mode, const double *w, int slot,
+                          const int *flag) {
+  fb_device_state *dv = ctx->dev;
+  const int block = 256;
+  const int64_t rows_per_block = block / T;
+  const int g = grid_for((A.nrows + rows_per_block - 1) / rows_per_block * block, block, dv->sm_count * 8);
+#define FB_SPU(DOT)                                                                                                      \
+  FB_LAUNCH(ctx, (k_spmm_u<NC, T, DOT, U, CHUNKED, PAIR>), g, block, 0, A.nrows, A.rowptr, A.col, A.val, A.mask, x, y, w,        \
+            dv->partials, dv->counter, dv->red, slot, flag, A.nlocal * NC)
+  if (dot_mode == 0) FB_SPU(0);
+  else if (dot_mode == 1) FB_SPU(1);
+  else if (dot_mode == 2) FB_SPU(2);
+  else FB_SPU(3);
+#undef FB_SPU
 }
 
 template <int D, int T>
@@ -592,8 +747,25 @@ static void spmv_local(fb_ctx *ctx, const LinOp &A, const double *x, double *y, 
       return launch_spmm<1, 8>(ctx, A, x, y, dot_mode, w, slot, flag);
     case 2:
       return launch_spmm<2, 8>(ctx, A, x, y, dot_mode, w, slot, flag);
-    case 3:
-      return launch_spmm<3, 16>(ctx, A, x, y, dot_mode, w, slot, flag);
+    case 3: {
+      static const int V = getenv("FB_SPMM_V") ? atoi(getenv("FB_SPMM_V")) : 0;
+      switch (V) {
+        case 1: return launch_spmm_u<3, 16, 2, 0>(ctx, A, x, y, dot_mode, w, slot, flag);
+        case 2: return launch_spmm_u<3, 16, 2, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+        case 3: return launch_spmm_u<3, 8, 4, 0>(ctx, A, x, y, dot_mode, w, slot, flag);
+        case 4: return launch_spmm_u<3, 8, 4, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+        case 5: return launch_spmm_u<3, 16, 1, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+        case 6: return launch_spmm_u<3, 32, 1, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+        case 7: return launch_spmm_u<3, 8, 2, 0>(ctx, A, x, y, dot_mode, w, slot, flag);
+        case 8: return launch_spmm_u<3, 4, 8, 0>(ctx, A, x, y, dot_mode, w, slot, flag);
+        case 9: return launch_spmm_u<3, 8, 4, 0, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+        case 10: return launch_spmm_u<3, 16, 2, 0, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+        case 11: return launch_spmm_u<3, 4, 8, 0, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+        case 12: return launch_spmm_u<3, 4, 4, 0, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+        case 13: return launch_spmm_u<3, 8, 3, 0, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+        default: return launch_spmm<3, 16>(ctx, A, x, y, dot_mode, w, slot, flag);
+      }
+    }
     default:
       throw fb_cuda_error(FB_EINVAL, "spmv: ncomp must be 1..3");
   }
@@ -608,6 +780,10 @@ __global__ void k_fill(double *x, double a, int64_t n) {
 __global__ void k_axpy(double *y, double a, const double *__restrict__ x, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] += a * x[i];
+}
+__global__ void k_to_float(float *__restrict__ dst, const double *__restrict__ src, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = (float)src[i];
 }
 __global__ void k_axpby(double *z, double a, const double *x, double b, const double *y, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -643,6 +819,9 @@ static inline int vgrid(fb_ctx *ctx, int64_t n) { return grid_for(n, 256, ctx->d
 void vec_fill(fb_ctx *ctx, double *x, double a, int64_t n) { FB_LAUNCH(ctx, k_fill, vgrid(ctx, n), 256, 0, x, a, n); }
 void vec_axpy(fb_ctx *ctx, double *y, double a, const double *x, int64_t n) {
   FB_LAUNCH(ctx, k_axpy, vgrid(ctx, n), 256, 0, y, a, x, n);
+}
+void vec_to_float(fb_ctx *ctx, float *dst, const double *src, int64_t n) {
+  FB_LAUNCH(ctx, k_to_float, vgrid(ctx, n), 256, 0, dst, src, n);
 }
 void vec_axpby(fb_ctx *ctx, double *z, double a, const double *x, double b, const double *y, int64_t n) {
   FB_LAUNCH(ctx, k_axpby, vgrid(ctx, n), 256, 0, z, a, x, b, y, n);

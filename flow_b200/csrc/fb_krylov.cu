@@ -27,13 +27,16 @@ inline int vgrid(fb_ctx *ctx, int64_t n) {
 
 constexpr int S_PAP = 4, S_TOL2 = 5;
 constexpr int S_BTOL2 = 12;
+constexpr int S_REF = 40;  // warm starts: ||M^-1 b||^2 of the ORIGINAL right-hand side (the iteration runs on r0)
 
 // ---------------------------------------------------------------- PCG
-__device__ void cg_start_check(double *red, double rtol, int *flag, int *iters) {
-  const double ref2 = red[1];  // ||M^-1 b||^2 (+ squared Dirichlet values, folded in by block 0)
+__device__ void cg_start_check(double *red, double rtol, double warm_extra2, int warm, int *flag, int *iters) {
+  // cold: red[1] = ||M^-1 b||^2 (+ squared Dirichlet values, folded in by block 0)
+  // warm: red[1] = ||M^-1 r0||^2, the reference norm comes from the original b
+  const double ref2 = warm ? red[S_REF] + warm_extra2 : red[1];
   red[S_TOL2] = rtol * rtol * ref2;
   *iters = 0;
-  *flag = (ref2 == 0.0) ? 1 : ((ref2 != ref2) ? 3 : 0);
+  *flag = (ref2 == 0.0) ? 1 : ((ref2 != ref2 || red[1] != red[1]) ? 3 : ((warm && red[1] <= red[S_TOL2]) ? 1 : 0));
 }
 
 __device__ void cg_update_check(const double *red, int it, int *flag, int *iters) {
@@ -49,7 +52,7 @@ __device__ void cg_update_check(const double *red, int it, int *flag, int *iters
 }
 
 __global__ void k_cg_start(int64_t n, const double *__restrict__ b, const double *__restrict__ dinv, double *r, double *z,
-                           double *p, double *x, double rtol, double ref_extra2, int dist, double *partials,
+                           double *p, double *x, double rtol, double ref_extra2, int warm, int dist, double *partials,
                            unsigned int *counter, double *red, int *flag, int *iters) {
   double d[2] = {0.0, 0.0};
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -58,15 +61,28 @@ __global__ void k_cg_start(int64_t n, const double *__restrict__ b, const double
     r[i] = ri;
     z[i] = zi;
     p[i] = zi;
-    x[i] = 0.0;
+    if (!warm) x[i] = 0.0;  // warm: x holds the initial guess and b its residual
     d[0] += ri * zi;
     d[1] += zi * zi;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) d[1] += ref_extra2;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && !warm) d[1] += ref_extra2;
   const bool last = fb_grid_reduce<2>(d, partials, counter, red, 0);
-  if (last && threadIdx.x == 0 && !dist) cg_start_check(red, rtol, flag, iters);
+  if (last && threadIdx.x == 0 && !dist) cg_start_check(red, rtol, ref_extra2, warm, flag, iters);
 }
-__global__ void k_cg_start_check(double *red, double rtol, int *flag, int *iters) { cg_start_check(red, rtol, flag, iters); }
+__global__ void k_cg_start_check(double *red, double rtol, double warm_extra2, int warm, int *flag, int *iters) {
+  cg_start_check(red, rtol, warm_extra2, warm, flag, iters);
+}
+
+// red[S_REF] = || M^-1 b ||^2 with M^-1 = diag(dinv), or || zb ||^2 if dinv == null (zb = AMG cycle applied to b)
+__global__ void k_cg_ref2(int64_t n, const double *__restrict__ b, const double *__restrict__ dinv, double *partials,
+                          unsigned int *counter, double *red) {
+  double d[1] = {0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double zi = dinv ? dinv[i] * b[i] : b[i];
+    d[0] += zi * zi;
+  }
+  fb_grid_reduce<1>(d, partials, counter, red, S_REF);
+}
 
 __global__ void k_cg_update(int64_t n, int it, const double *__restrict__ dinv, const double *__restrict__ p,
                             const double *__restrict__ Ap, double *x, double *r, double *z, int dist, double *partials,
@@ -256,28 +272,49 @@ int poll(fb_ctx *ctx, int *flag_out, int *iters_out) {
 }  // namespace
 
 int krylov_pcg_single_reduction(fb_ctx *ctx, const LinOp &A, const double *dinv, const double *b, double *x, double rtol,
-                                double ref_extra2, int maxit, int check_every, KrylovWork &w, int *iters);
+                                double ref_extra2, int maxit, int check_every, KrylovWork &w, int *iters, fb_amg *amg, int warm);
 
 int krylov_pcg(fb_ctx *ctx, const LinOp &A, const double *dinv, const double *b, double *x, double rtol, double ref_extra2,
-               int maxit, int check_every, KrylovWork &w, int *iters) {
+               int maxit, int check_every, KrylovWork &w, int *iters, fb_amg *amg, bool warm_start) {
+  const int warm = warm_start ? 1 : 0;
+  if (warm) {
+    // x holds an initial guess: iterate on r0 = b - A x with the SAME stopping test as a cold start
+    // (||M^-1 r|| <= rtol ||M^-1 b||, PETSc's default also for a non-zero guess); only the starting point differs.
+    fb_device_state *dv = ctx->dev;
+    const int64_t n = A.ndofs();
+    w.ensure(7, A.nlocal_dofs());
+    double *r0 = w.v[5].p, *zb = w.v[6].p;
+    const int g = std::min(vgrid(ctx, n), FB_MAX_RED_BLOCKS);
+    if (amg) {
+      amg_apply(amg, b, zb);
+      FB_LAUNCH(ctx, k_cg_ref2, g, 256, 0, n, zb, (const double *)nullptr, dv->partials, dv->counter, dv->red);
+    } else {
+      FB_LAUNCH(ctx, k_cg_ref2, g, 256, 0, n, b, dinv, dv->partials, dv->counter, dv->red);
+    }
+    if (fb_is_distributed(ctx)) fb_allreduce_slots(ctx, S_REF, 1);
+    spmv(ctx, A, x, r0);
+    vec_axpby(ctx, r0, 1.0, b, -1.0, r0, n);
+    b = r0;
+  }
+  if (amg) return krylov_pcg_single_reduction(ctx, A, dinv, b, x, rtol, ref_extra2, maxit, check_every, w, iters, amg, warm);
   // -1 (default): single-reduction CG where the iteration is latency bound (small systems, or several ranks:
   // one all-reduce instead of two), classic PCG where it is bandwidth bound (measured at n = 74: P2 mass x 3,
   // 9.9 M dofs: 0.81 vs 0.98 ms per iteration); 0 / 1 force one of them
   static const int knob = getenv("FB_CG") ? atoi(getenv("FB_CG")) : -1;
   const int variant = knob >= 0 ? knob : ((fb_is_distributed(ctx) || A.ndofs() < (int64_t(1) << 21)) ? 1 : 0);
   if (variant == 1 && A.block == 1)
-    return krylov_pcg_single_reduction(ctx, A, dinv, b, x, rtol, ref_extra2, maxit, check_every, w, iters);
+    return krylov_pcg_single_reduction(ctx, A, dinv, b, x, rtol, ref_extra2, maxit, check_every, w, iters, nullptr, warm);
   fb_device_state *dv = ctx->dev;
   const int64_t n = A.ndofs();
   const int dist = fb_is_distributed(ctx) ? 1 : 0;
   w.ensure(4, A.nlocal_dofs());
   double *r = w.v[0].p, *z = w.v[1].p, *p = w.v[2].p, *Ap = w.v[3].p;
   const int g = vgrid(ctx, n);
-  FB_LAUNCH(ctx, k_cg_start, g, 256, 0, n, b, dinv, r, z, p, x, rtol, ref_extra2, dist, dv->partials, dv->counter, dv->red,
-            dv->flag, dv->iters);
+  FB_LAUNCH(ctx, k_cg_start, g, 256, 0, n, b, dinv, r, z, p, x, rtol, ref_extra2, warm, dist, dv->partials, dv->counter,
+            dv->red, dv->flag, dv->iters);
   if (dist) {
     fb_allreduce_slots(ctx, 0, 2);
-    FB_LAUNCH(ctx, k_cg_start_check, 1, 1, 0, dv->red, rtol, dv->flag, dv->iters);
+    FB_LAUNCH(ctx, k_cg_start_check, 1, 1, 0, dv->red, rtol, ref_extra2, warm, dv->flag, dv->iters);
   }
   int flag = 0, done = 0, it = 0;
   if (check_every < 1) check_every = 1;
@@ -312,29 +349,30 @@ constexpr int S_CG3 = 20;   // gamma, delta, |u|^2 of the current iterate
 constexpr int S_CGST = 24;  // state[2][3]: alpha, gamma, tol2 per parity
 
 __global__ void k_cg3_start(int64_t n, const double *__restrict__ b, const double *__restrict__ dinv, double *r, double *u,
-                            double *p, double *s, double *x) {
+                            double *p, double *s, double *x, int warm) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double ri = b[i];
     r[i] = ri;
-    u[i] = dinv[i] * ri;
+    if (dinv) u[i] = dinv[i] * ri;  // null: the caller applies the AMG cycle to r
     p[i] = 0.0;
     s[i] = 0.0;
-    x[i] = 0.0;
+    if (!warm) x[i] = 0.0;  // warm: x holds the initial guess and b its residual
   }
 }
 
 // it: iteration being applied (0-based).  red[S_CG3..] holds gamma_it, delta_it, |u_it|^2 (all-reduced).
-__global__ void k_cg3_update(int64_t n, int it, double rtol, double ref_extra2, const double *__restrict__ dinv,
+__global__ void k_cg3_update(int64_t n, int it, double rtol, double ref_extra2, int warm, const double *__restrict__ dinv,
                              const double *__restrict__ w, double *u, double *r, double *p, double *s, double *x,
                              double *red, int *flag, int *iters) {
   if (*flag) return;
   const int par = it & 1, prv = par ^ 1;
   const double gamma = red[S_CG3], delta = red[S_CG3 + 1], zz = red[S_CG3 + 2];
   double *st = red + S_CGST;
-  const double tol2 = (it == 0) ? rtol * rtol * (zz + ref_extra2) : st[3 * prv + 2];
+  const double ref2 = (warm ? red[S_REF] : zz) + ref_extra2;  // warm: norm of the original right-hand side
+  const double tol2 = (it == 0) ? rtol * rtol * ref2 : st[3 * prv + 2];
   // every thread evaluates the stopping test on the same all-reduced numbers: uniform decision
   const bool bad = (zz != zz) || (gamma != gamma) || (delta != delta);
-  const bool conv = (it == 0) ? (zz + ref_extra2 == 0.0) : (zz <= tol2);
+  const bool conv = (it == 0) ? (ref2 == 0.0 || (warm && zz <= tol2)) : (zz <= tol2);
   double alpha, beta;
   if (it == 0) {
     beta = 0.0;
@@ -363,14 +401,15 @@ __global__ void k_cg3_update(int64_t n, int it, double rtol, double ref_extra2, 
     x[i] += alpha * pi;
     const double ri = r[i] - alpha * si;
     r[i] = ri;
-    u[i] = dinv[i] * ri;
+    if (dinv) u[i] = dinv[i] * ri;
   }
 }
 }  // namespace
 
 int krylov_pcg_single_reduction(fb_ctx *ctx, const LinOp &A, const double *dinv, const double *b, double *x, double rtol,
-                                double ref_extra2, int maxit, int check_every, KrylovWork &w, int *iters) {
+                                double ref_extra2, int maxit, int check_every, KrylovWork &w, int *iters, fb_amg *amg, int warm) {
   fb_device_state *dv = ctx->dev;
+  if (amg) dinv = nullptr;
   const int64_t n = A.ndofs();
   w.ensure(5, A.nlocal_dofs());
   double *r = w.v[0].p, *u = w.v[1].p, *wv = w.v[2].p, *p = w.v[3].p, *s = w.v[4].p;
@@ -384,14 +423,17 @@ int krylov_pcg_single_reduction(fb_ctx *ctx, const LinOp &A, const double *dinv,
   }
   FB_CUDA(cudaMemsetAsync(dv->flag, 0, sizeof(int), dv->stream));
   FB_CUDA(cudaMemsetAsync(dv->iters, 0, sizeof(int), dv->stream));
-  FB_LAUNCH(ctx, k_cg3_start, g, 256, 0, n, b, dinv, r, u, p, s, x);
+  FB_LAUNCH(ctx, k_cg3_start, g, 256, 0, n, b, dinv, r, u, p, s, x, warm);
+  if (amg) amg_apply(amg, r, u);
   int flag = 0, done = 0, it = 0;
   if (check_every < 1) check_every = 1;
   while (it <= maxit) {
     const int batch = std::min(check_every, maxit + 1 - it);
     for (int k = 0; k < batch; ++k, ++it) {
       spmv(ctx, A, u, wv, 3, r, S_CG3, dv->flag);  // w = A u; gamma, delta, |u|^2 -> one all-reduce
-      FB_LAUNCH(ctx, k_cg3_update, g, 256, 0, n, it, rtol, ref_extra2, dinv, wv, u, r, p, s, x, dv->red, dv->flag, dv->iters);
+      FB_LAUNCH(ctx, k_cg3_update, g, 256, 0, n, it, rtol, ref_extra2, warm, dinv, wv, u, r, p, s, x, dv->red, dv->flag,
+                dv->iters);
+      if (amg) amg_apply(amg, r, u);  // u = M^-1 r (runs unconditionally; harmless once the flag is up)
     }
     poll(ctx, &flag, &done);
     if (flag) break;

@@ -43,6 +43,7 @@ struct LinOp {
   const int *rowptr = nullptr;
   const int *col = nullptr;
   const double *val = nullptr;
+  const float *val32 = nullptr;   // block > 1 only: fp32 copy of val; when set the product streams this one
   const uint8_t *mask = nullptr;  // per dof: 1 -> identity row (Dirichlet); may be null
   int64_t ndofs() const { return nrows * (block > 1 ? block : ncomp); }
   int64_t nlocal_dofs() const { return nlocal * (block > 1 ? block : ncomp); }
@@ -70,6 +71,7 @@ void spmv(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_mode 
 void vec_fill(fb_ctx *ctx, double *x, double a, int64_t n);
 void vec_axpy(fb_ctx *ctx, double *y, double a, const double *x, int64_t n);          // y += a x
 void vec_axpby(fb_ctx *ctx, double *z, double a, const double *x, double b, const double *y, int64_t n);  // z = a x + b y
+void vec_to_float(fb_ctx *ctx, float *dst, const double *src, int64_t n);
 void vec_dot(fb_ctx *ctx, const double *x, const double *y, int64_t n, int slot);     // red[slot] = x.y
 double vec_norm2_sync(fb_ctx *ctx, const double *x, int64_t n);                       // host-synchronous
 void mask_build(fb_ctx *ctx, uint8_t *mask, int64_t ndofs, const int64_t *dofs, int64_t nbc);
@@ -121,9 +123,19 @@ struct KrylovWork {
     for (int i = 0; i < count; ++i) v[i].alloc((size_t)n);
   }
 };
-// Jacobi-PCG, stopping test ||M^-1 r|| <= rtol * ref  (ref <= 0: ref = ||M^-1 b||)
+// smoothed-aggregation AMG (fb_amg.cu): hierarchy of the n x n leading (owned) block of a host CSR matrix
+struct fb_amg;
+fb_amg *amg_setup(fb_ctx *ctx, int n, const int *rowptr, const int *col, const double *val);
+void amg_apply(fb_amg *amg, const double *r, double *z);  // z = V(1,1)-cycle applied to r (device vectors)
+void amg_destroy(fb_amg *amg);
+int amg_num_levels(const fb_amg *amg);
+double amg_complexity(const fb_amg *amg);
+int amg_level_size(const fb_amg *amg, int l);
+
+// PCG, stopping test ||M^-1 r|| <= rtol * ||M^-1 b|| (PETSc default); M^-1 = Jacobi (dinv) or, if amg != null, the
+// AMG V-cycle (then dinv is ignored).  warm_start: x holds an initial guess on entry (the test is unchanged).
 int krylov_pcg(fb_ctx *ctx, const LinOp &A, const double *dinv, const double *b, double *x, double rtol, double ref_extra2,
-               int maxit, int check_every, KrylovWork &w, int *iters);
+               int maxit, int check_every, KrylovWork &w, int *iters, fb_amg *amg = nullptr, bool warm_start = false);
 // right-preconditioned BiCGStab with D x D block inverse (A.block > 1) or diagonal dinv (A.block == 1);
 // stops when ||r||_2 <= atol
 int krylov_bicgstab(fb_ctx *ctx, const LinOp &A, const double *minv, const double *b, double *x, double atol, int maxit,

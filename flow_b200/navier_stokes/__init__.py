@@ -1,1 +1,1 @@
-from .pressure_correction import Chorin, IPCS, Rotational, last_stats  # noqa: F401
+from .pressure_correction import Chorin, IPCS, Rotational, last_stats, set_options, reset_options  # noqa: F401

@@ -21,6 +21,24 @@ _SCHEMES = {"forward euler": _lib.FORWARD_EULER, "backward euler": _lib.BACKWARD
             "crank-nicolson": _lib.CRANK_NICOLSON}
 
 _last_stats = {}
+_options = {}
+_PRECONDS = {"jacobi": _lib.JACOBI, "amg": _lib.AMG}
+
+
+def set_options(**kw):
+    """Solver options of the engines created from now on (fields of ``fb_ns_opts``, include/flowb200.h):
+    pressure_precond ("amg" | "jacobi"), jacobian_reuse, jacobian_across_steps, warm_start, jacobian_fp32,
+    adaptive_forcing, momentum_maxit, pressure_maxit, correction_maxit, check_every.  The reference's counterpart
+    is its hard-wired ``solver_parameters`` dicts (pressure_correction.py:228-253, :328-339, :453-464)."""
+    known = {name for name, _ in _lib.NSOpts._fields_}
+    for k, v in kw.items():
+        if k not in known or k == "reserved":
+            raise KeyError("unknown option %r" % (k,))
+        _options[k] = _PRECONDS[v] if k == "pressure_precond" and isinstance(v, str) else v
+
+
+def reset_options():
+    _options.clear()
 
 
 def last_stats():
@@ -34,9 +52,14 @@ def _scalar(c):
 
 def _engine(W, P, opts=None):
     """fb_ns handle for the (W, P) pair; created on first use and kept on W's node space."""
-    key = ("ns", id(P.nodes))
+    key = ("ns", id(P.nodes), tuple(sorted(_options.items())))
     cache = W.nodes.__dict__.setdefault("_engines", {})
     if key not in cache:
+        if opts is None and _options:
+            opts = _lib.NSOpts()
+            lib.fb_ns_opts_default(C.byref(opts))
+            for k, v in _options.items():
+                setattr(opts, k, v)
         h = _lib.vp()
         _lib.check(lib.fb_ns_create(W.handle(), P.handle(), C.byref(opts) if opts is not None else None, C.byref(h)),
                    W.mesh().ctx, "fb_ns_create")

@@ -49,7 +49,7 @@ enum fb_scheme { FB_FORWARD_EULER = 0, FB_BACKWARD_EULER = 1, FB_CRANK_NICOLSON 
 enum fb_flags { FB_DEVICE_PTRS = 1, FB_ROTATIONAL = 2, FB_CHORIN = 4 };
 enum fb_forcing { FB_F_NONE = 0, FB_F_CONSTANT = 1, FB_F_NODAL = 2, FB_F_LOAD = 3 };
 enum fb_krylov { FB_BICGSTAB = 0, FB_GMRES = 1, FB_CG = 2 };
-enum fb_precond { FB_JACOBI = 0, FB_BLOCK_JACOBI = 1, FB_CHEBYSHEV = 2 };
+enum fb_precond { FB_JACOBI = 0, FB_BLOCK_JACOBI = 1, FB_CHEBYSHEV = 2, FB_AMG = 3 };
 
 /* ---- context ---------------------------------------------------------- */
 int fb_version(void);
@@ -136,7 +136,9 @@ int fb_mat_bench_spmv(fb_mat *mat, int ncomp, int reps, double *ms_avg, double *
 typedef struct fb_ns_opts {
   int momentum_solver;   /* fb_krylov: FB_BICGSTAB (default) or FB_GMRES */
   int momentum_precond;  /* FB_JACOBI or FB_BLOCK_JACOBI (default) */
-  int pressure_precond;  /* FB_JACOBI (default) or FB_CHEBYSHEV */
+  int pressure_precond;  /* FB_AMG (default; smoothed aggregation, V(1,1), dense pseudo-inverse on the coarsest level;
+                            replaces hypre BoomerAMG of pressure_correction.py:331,:414-419; systems of fewer than
+                            4096 unknowns fall back to Jacobi) or FB_JACOBI */
   int newton_maxit;      /* 10, pressure_correction.py:232 */
   double newton_atol;    /* 1e-10, pressure_correction.py:499 */
   double momentum_rtol;  /* inner Krylov tolerance relative to |F| (inexact Newton), default 1e-6 */
@@ -150,7 +152,15 @@ typedef struct fb_ns_opts {
                             residual contracts by > 10x per iteration (chord); 0: re-assemble every iteration */
   int adaptive_forcing;  /* 1 (default): the first linear solve of a step stops at the nonlinear remainder observed
                             at the previous step; 0: every linear solve goes to 0.1 * newton_atol */
-  int reserved[6];
+  int jacobian_across_steps; /* 1 (default): the chord Jacobian also survives from one step to the next while dt, rho,
+                            mu, the scheme and the constrained dofs are unchanged and the first update of the previous
+                            step contracted |F| by > 100x; 0: re-assemble at every step */
+  int warm_start;        /* 1 (default): the Poisson / correction CG iterations start from p0 / ui instead of 0; the
+                            stopping test (relative to the preconditioned norm of b) is the reference's */
+  int jacobian_fp32;     /* 0 (default).  1: the chord Jacobian used INSIDE the Krylov solves is stored in fp32 (half the
+                            SpMV bytes); residuals, vectors, dots and the Newton test |F| < atol stay fp64, so the
+                            accepted solution satisfies the same fp64 criterion (mixed-precision inexact Newton) */
+  int reserved[3];
 } fb_ns_opts;
 
 typedef struct fb_ns_stats {
@@ -169,6 +179,8 @@ int fb_ns_opts_default(fb_ns_opts *opts);
 /* W: vector P2 space (ncomp == gdim), P: scalar P1 space on the same mesh. */
 int fb_ns_create(fb_space *W, fb_space *P, const fb_ns_opts *opts, fb_ns **out);
 int fb_ns_destroy(fb_ns *ns);
+/* AMG hierarchy of the pressure operator: number of levels, operator complexity, rows per level */
+int fb_ns_amg_info(fb_ns *ns, int *levels, double *complexity, int *sizes, int max_sizes);
 /* One step.  scheme: fb_scheme; flags: FB_ROTATIONAL | FB_CHORIN | FB_DEVICE_PTRS.
  * forcing: fb_forcing; f0/f1 = f at t_n / t_{n+1}: gdim doubles (CONSTANT), ndofs(W)
  * doubles of nodal values (NODAL) or of the load vector int f.v dx (LOAD); NULL == 0.

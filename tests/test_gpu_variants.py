@@ -1,0 +1,134 @@
+"""Solver variants of the IPCS step against the oracle on a mesh large enough for the AMG hierarchy
+(>= 4096 pressure unknowns): smoothed-aggregation AMG vs Jacobi for the Poisson solve
+(pressure_correction.py:331, :414-419 use hypre BoomerAMG), warm-started CG, the chord Jacobian
+carried across steps, and the fp32-stored chord Jacobian.  Every variant has to land on the
+oracle's Newton+LU result within the north-star tolerance (1e-8 relative L2 after several steps)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import fem
+from oracle import navier_stokes as ons
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = {
+    "defaults": {},
+    "plain": dict(pressure_precond="jacobi", warm_start=0, jacobian_across_steps=0, jacobian_reuse=0, adaptive_forcing=0),
+    "jacobi_warm": dict(pressure_precond="jacobi", warm_start=1),
+    "amg_cold": dict(pressure_precond="amg", warm_start=0, jacobian_across_steps=0),
+    "fp32_jacobian": dict(jacobian_fp32=1),
+}
+
+
+@pytest.fixture(scope="module")
+def cavity2d():
+    """Regularised lid-driven cavity on UnitSquareMesh(70, 70): 5041 pressure dofs, 39762 velocity dofs;
+    4 oracle steps (Newton + LU, CG to 1e-12)."""
+    n = 70
+    om = fem.Mesh(*fem.unit_square_mesh(n, n, "right"))
+    ost = ons.IPCS(om)
+    X = ost.W.node_coords
+    bd = ost.W.boundary_dofs()
+    g = np.zeros((ost.W.nnodes, 2))
+    top = X[:, 1] > 1.0 - 1e-12
+    g[top, 0] = (1.0 - (2.0 * X[top, 0] - 1.0) ** 4)
+    g = g.reshape(-1)
+    dt, rho, mu = 0.02, 1.0, 0.01
+    states = []
+    u, p = np.zeros(ost.W.ndofs), np.zeros(ost.P.nnodes)
+    for _ in range(4):
+        # _step (:468-518) piece by piece so that Newton can be driven below the hard-wired 1e-10 of :499 (see the
+        # comment in test_variant_matches_oracle)
+        ui = ost.tentative_velocity(u, p, None, None, (bd, g[bd]), rho, mu, dt, tol=1e-14)
+        p1 = ost.pressure(ui, p, None, rho, mu, dt, 1e-12)
+        u = ost.velocity_correction(ui, p1, p, (bd, g[bd]), rho, mu, dt, 1e-12)
+        p = p1
+        states.append((u.copy(), p.copy()))
+    return om, g, (dt, rho, mu), states
+
+
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+def test_variant_matches_oracle(gpu_ctx, cavity2d, name):
+    from flow_b200 import dolfin as d
+    from flow_b200 import navier_stokes as nav
+
+    om, g, (dt, rho, mu), states = cavity2d
+    nav.reset_options()
+    # The reference's Newton test |F|_2 < 1e-10 (:499) is absolute and not mesh-normalised: on this mesh two iterates
+    # that both pass it can differ by 1e-7 relative.  Newton + LU (reference, oracle) overshoots it to ~1e-15 in its last
+    # update; the Krylov path is asked for the same depth here so that the comparison measures the discretisation and
+    # the solvers, not where each path happened to stop.
+    nav.set_options(newton_atol=1e-13, **VARIANTS[name])
+    try:
+        m = d.Mesh(om.points, om.cells)
+        W = d.VectorFunctionSpace(m, "CG", 2)
+        P = d.FunctionSpace(m, "CG", 1)
+        bcs = [d.DirichletBC(W, d.Function(W, g.copy()), "on_boundary")]
+        zero = d.Constant((0.0, 0.0))
+        u, p = d.Function(W), d.Function(P)
+        st = nav.IPCS()
+        assemblies, pits = [], []
+        for k in range(4):
+            u, p = st.step(d.Constant(dt), {0: u}, p, bcs, [], d.Constant(rho), d.Constant(mu), {0: zero, 1: zero},
+                           verbose=False, tol=1e-12)
+            s = nav.last_stats()
+            assemblies.append(s["jacobian_assemblies"])
+            pits.append(s["pressure_its"])
+            uo, po = states[k]
+            eu = np.linalg.norm(u._vec - uo) / np.linalg.norm(uo)
+            dp = (p._vec - p._vec.mean()) - (po - po.mean())
+            ep = np.linalg.norm(dp) / np.linalg.norm(po - po.mean())
+            assert eu < 1e-8, (name, k, eu)
+            assert ep < 1e-7, (name, k, ep)
+        if VARIANTS[name].get("pressure_precond", "amg") == "amg":
+            assert max(pits) < 60, pits  # mesh-independent iteration counts (Jacobi needs several hundred here)
+        if name == "plain":
+            assert min(assemblies) >= 2  # plain Newton assembles at every iteration
+    finally:
+        nav.reset_options()
+
+
+def test_amg_hierarchy_and_dirichlet_variant(gpu_ctx):
+    """Hierarchy statistics through the C ABI, and the p_bcs != [] branch (:325-339) with AMG on the
+    symmetrically eliminated matrix: same pressure as Jacobi-CG to solver tolerance."""
+    from flow_b200 import _lib
+    from flow_b200 import dolfin as d
+    from flow_b200 import navier_stokes as nav
+    from flow_b200._lib import lib
+    from flow_b200.navier_stokes.pressure_correction import _engine
+
+    n = 70
+    res = {}
+    for pc in ("amg", "jacobi"):
+        nav.reset_options()
+        nav.set_options(pressure_precond=pc, newton_atol=1e-13)
+        try:
+            m = d.UnitSquareMesh(n, n)
+            W = d.VectorFunctionSpace(m, "CG", 2)
+            P = d.FunctionSpace(m, "CG", 1)
+            if pc == "amg":
+                ns = _engine(W, P)
+                lv, cx, sz = C.c_int(), C.c_double(), (C.c_int * 12)()
+                _lib.check(lib.fb_ns_amg_info(ns, C.byref(lv), C.byref(cx), sz, 12), W.mesh().ctx, "amg_info")
+                sizes = list(sz)[:lv.value]
+                assert lv.value >= 2 and sizes[0] == (n + 1) ** 2 and sizes[-1] <= 400
+                assert all(a > 2 * b for a, b in zip(sizes, sizes[1:]))  # every level coarsens by more than 2x
+                assert 1.0 < cx.value < 2.5
+            inflow = d.DirichletBC(W, d.Expression(("x[1]*(1-x[1])", "0.0"), degree=2), lambda x, on: on and x[0] < 1e-12)
+            walls = d.DirichletBC(W, (0.0, 0.0), lambda x, on: on and (x[1] < 1e-12 or x[1] > 1 - 1e-12))
+            pout = d.DirichletBC(P, 0.0, lambda x, on: on and x[0] > 1 - 1e-12)
+            zero = d.Constant((0.0, 0.0))
+            u, p = d.Function(W), d.Function(P)
+            for _ in range(2):
+                u, p = nav.Rotational().step(d.Constant(0.05), {0: u}, p, [inflow, walls], [pout], d.Constant(1.0),
+                                             d.Constant(0.02), {0: zero, 1: zero}, verbose=False, tol=1e-12)
+            res[pc] = (u._vec.copy(), p._vec.copy(), nav.last_stats()["pressure_its"])
+        finally:
+            nav.reset_options()
+    ua, pa, ia = res["amg"]
+    uj, pj, ij = res["jacobi"]
+    assert np.linalg.norm(ua - uj) / np.linalg.norm(uj) < 1e-9
+    assert np.linalg.norm(pa - pj) / np.linalg.norm(pj) < 1e-8
+    assert ia < 40 and ia < ij / 4, (ia, ij)
