@@ -173,7 +173,7 @@ def main():
         # halo exchange + all-reduced dots over NCCL (flow_b200/parallel.py, csrc/fb_comm.cu)
         from flow_b200 import parallel
 
-        parallel.init_comm(ctx, rank, world, parallel.torch_broadcast(local_rank))
+        p2p = parallel.init_comm(ctx, rank, world, parallel.torch_broadcast(local_rank))
         mesh = parallel.distributed_mesh(mesh, rank, world)
     W = d.VectorFunctionSpace(mesh, "CG", 2)
     P = d.FunctionSpace(mesh, "CG", 1)
@@ -298,8 +298,9 @@ def main():
             "config": {
                 "workload": "3D lid-driven cavity, P2/P1 IPCS backward Euler, UnitCubeMesh(%d): %d dofs (%d u + %d p), "
                             "Re=100, dt=1e-2, tol=1e-10" % (n, nu_global + np_global, nu_global, np_global),
-                "parallelism": "single GPU" if world == 1 else "mesh partitioned over %d GPUs (RCB, 1 ghost-cell layer, NCCL halo exchange + "
-                               "one all-reduce per Krylov reduction); rank 0 holds %d local dofs" % (world, nu + npp),
+                "parallelism": "single GPU" if world == 1 else "mesh partitioned over %d GPUs (RCB, 1 ghost-cell layer, halo exchange + one all-reduce per "
+                               "Krylov reduction over %s); rank 0 holds %d local dofs"
+                               % (world, "NVLink peer-memory windows (own kernels)" if p2p else "NCCL", nu + npp),
                 "l2_policy": "working set (Jacobian %.1f GB) far exceeds the 126 MB L2" % (roofline["algorithmic_bytes_per_launch"] / 1e9 if roofline else 0),
             },
             "iterations": {"newton": avg("newton_its"), "jacobian_assemblies": avg("jacobian_assemblies"), "momentum_krylov": avg("momentum_its"), "pressure_cg": avg("pressure_its"),

@@ -115,6 +115,10 @@ SIGNATURES = {
     "fb_comm_unique_id": (C.c_int, [vp]),
     "fb_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "fb_comm_destroy": (C.c_int, [vp]),
+    "fb_comm_window_create": (C.c_int, [vp, i64, vp]),
+    "fb_comm_window_open": (C.c_int, [vp, vp]),
+    "fb_comm_window_disable": (C.c_int, [vp]),
+    "fb_comm_uses_peer_memory": (C.c_int, [vp]),
     "fb_space_halo_exchange": (C.c_int, [vp, C.c_int, pd]),
     "fb_assemble_mass": (C.c_int, [vp, C.POINTER(vp)]),
     "fb_assemble_stiffness": (C.c_int, [vp, C.POINTER(vp)]),
@@ -128,6 +132,7 @@ SIGNATURES = {
     "fb_ns_opts_default": (C.c_int, [C.POINTER(NSOpts)]),
     "fb_ns_create": (C.c_int, [vp, vp, C.POINTER(NSOpts), C.POINTER(vp)]),
     "fb_ns_destroy": (C.c_int, [vp]),
+    "fb_ns_set_pressure_amg_global": (C.c_int, [vp, vp, vp, pi64, i64]),
     "fb_ns_amg_info": (C.c_int, [vp, C.POINTER(C.c_int), pd, C.POINTER(C.c_int), C.c_int]),
     "fb_ns_step": (
         C.c_int,

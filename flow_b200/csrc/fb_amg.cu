@@ -273,12 +273,32 @@ struct AmgLevel {
 struct fb_amg {
   fb_ctx *ctx = nullptr;
   std::vector<AmgLevel *> levels;
+  // replicated mode (partitioned runs)
+  fb_peer_vec *gather = nullptr;
+  DBuf<int> l2g;
+  DBuf<double> zg;
+  int n_owned = 0;
   double operator_complexity = 1.0;
   bool singular = false;
   ~fb_amg() {
     for (auto *l : levels) delete l;
+    if (gather) fb_peer_vec_destroy(gather);
   }
 };
+
+void amg_set_replicated(fb_amg *amg, fb_peer_vec *gather, const int *l2g_host, int n_owned) {
+  amg->gather = gather;
+  amg->n_owned = n_owned;
+  amg->l2g.upload(l2g_host, (size_t)n_owned, amg->ctx->dev->stream);
+  amg->zg.alloc((size_t)amg->levels[0]->n);
+  FB_CUDA(cudaStreamSynchronize(amg->ctx->dev->stream));
+}
+
+namespace {
+__global__ void k_amg_extract(int n_owned, const int *__restrict__ l2g, const double *__restrict__ zg, double *__restrict__ z) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_owned; i += gridDim.x * blockDim.x) z[i] = zg[l2g[i]];
+}
+}  // namespace
 
 void amg_destroy(fb_amg *amg) { delete amg; }
 
@@ -478,7 +498,17 @@ static void amg_jacobi(fb_ctx *ctx, const AmgLevel &L, const double *b, const do
 
 // z = V-cycle(r): r and z are device vectors of the fine level (n entries).  Per level the working iterate lives
 // in L.tmp (pre-smooth, residual, coarse correction) and the post-smoothed result in L.x (z on the fine level).
+static void amg_cycle(fb_amg *amg, const double *r, double *z);
+
 void amg_apply(fb_amg *amg, const double *r, double *z) {
+  if (!amg->gather) return amg_cycle(amg, r, z);
+  fb_ctx *ctx = amg->ctx;
+  const double *rg = fb_peer_vec_gather(ctx, amg->gather, r, amg->l2g.p, amg->n_owned);
+  amg_cycle(amg, rg, amg->zg.p);
+  FB_LAUNCH(ctx, k_amg_extract, agrid(amg->n_owned, 1), 256, 0, amg->n_owned, amg->l2g.p, amg->zg.p, z);
+}
+
+static void amg_cycle(fb_amg *amg, const double *r, double *z) {
   fb_ctx *ctx = amg->ctx;
   const int nl = (int)amg->levels.size();
   if (nl == 1) {  // no coarse level: two Jacobi sweeps

@@ -578,9 +578,47 @@ int fb_ns_create(fb_space *Wsp, fb_space *Psp, const fb_ns_opts *opts, fb_ns **o
   ns->mask_p.alloc((size_t)ns->np);
   FB_CUDA(cudaStreamSynchronize(ctx->dev->stream));
   // tiny systems: the hierarchy would have one level and Jacobi-CG's kernels are cheaper than a V-cycle's
-  if (ns->opts.pressure_precond == FB_AMG && ns->np_o < 4096) ns->opts.pressure_precond = FB_JACOBI;
+  // (the GLOBAL size decides, so that all ranks of a partitioned run take the same branch)
+  if (ns->opts.pressure_precond == FB_AMG && fb_allreduce_host_sum(ctx, (double)ns->np_o) < 4096.0)
+    ns->opts.pressure_precond = FB_JACOBI;
   if (ns->opts.pressure_precond == FB_AMG) ns->amg_p = ns_build_amg(ns.get(), ns->Ap.val.p);
   *out = ns.release();
+  FB_API_END
+}
+
+int fb_ns_set_pressure_amg_global(fb_ns *ns, fb_space *Pglobal, fb_mat *Aglobal, const int64_t *l2g, int64_t n_owned) {
+  if (!ns || !Pglobal || !Aglobal || !l2g) return FB_EINVAL;
+  fb_ctx *ctx = ns->ctx;
+  if (n_owned != ns->np_o) return fb_fail(ctx, FB_EINVAL, "fb_ns_set_pressure_amg_global: l2g must cover the owned pressure dofs");
+  if (Aglobal->block != 1 || Aglobal->sp->nnodes != Pglobal->nnodes)
+    return fb_fail(ctx, FB_EINVAL, "fb_ns_set_pressure_amg_global: matrix and space do not match");
+  FB_API_BEGIN(ctx)
+  if (ns->opts.pressure_precond != FB_AMG) return FB_OK;  // Jacobi was chosen (small system or by option)
+  fb_peer_vec *gv = fb_peer_vec_create(ctx, Pglobal->nnodes);  // collective
+  if (!gv) return FB_OK;  // no peer-memory transport: keep the per-rank hierarchy
+  fb_space_build_pattern(Pglobal);
+  const int64_t nn = Pglobal->nnodes, nnz = (int64_t)Pglobal->indices.size();
+  std::vector<int> rp(nn + 1), map((size_t)n_owned);
+  for (int64_t i = 0; i <= nn; ++i) rp[i] = (int)Pglobal->indptr[i];
+  for (int64_t i = 0; i < n_owned; ++i) {
+    if (l2g[i] < 0 || l2g[i] >= nn) {
+      fb_peer_vec_destroy(gv);
+      return fb_fail(ctx, FB_EINVAL, "fb_ns_set_pressure_amg_global: global index out of range");
+    }
+    map[i] = (int)l2g[i];
+  }
+  // Every rank assembled the global matrix itself, with atomics: the values differ in the last bits, and the
+  // aggregation breaks ties between equal couplings by comparing them.  All ranks must build the SAME hierarchy
+  // (rank r applies "its" preconditioner to its rows; different hierarchies would make the global operator
+  // unsymmetric), so rank 0's values are used everywhere; the set-up itself is deterministic.
+  fb_broadcast_device(ctx, Aglobal->val.p, sizeof(double) * nnz, 0);
+  FB_CUDA(cudaStreamSynchronize(ctx->dev->stream));
+  std::vector<double> val((size_t)nnz);
+  FB_CUDA(cudaMemcpy(val.data(), Aglobal->val.p, sizeof(double) * nnz, cudaMemcpyDeviceToHost));
+  fb_amg *g = amg_setup(ctx, (int)nn, rp.data(), Pglobal->indices.data(), val.data());
+  amg_set_replicated(g, gv, map.data(), (int)n_owned);
+  if (ns->amg_p) amg_destroy(ns->amg_p);
+  ns->amg_p = g;
   FB_API_END
 }
 

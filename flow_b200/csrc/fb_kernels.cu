@@ -334,6 +334,14 @@ __global__ void __launch_bounds__(256)
     double acc[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+    double wv = 0.0, xd = 0.0;  // epilogue operands fetched up front (see k_bspmv_u)
+    bool masked = false;
+    if (row < nrows && lane < NC) {
+      const int64_t dof = row * NC + lane;
+      if (DOT >= 1) wv = w[dof];
+      if (DOT == 3 || mask) xd = x[dof];
+      if (mask) masked = mask[dof] != 0;
+    }
     if (row < nrows) {
       const int r0 = rowptr[row], r1 = rowptr[row + 1];
       for (int k = r0 + lane; k < r1; k += T) {
@@ -354,13 +362,12 @@ __global__ void __launch_bounds__(256)
       for (int c = 1; c < NC; ++c)
         if (lane == c) yc = acc[c];
       const int64_t dof = row * NC + lane;
-      if (mask && mask[dof]) yc = x[dof];
+      if (masked) yc = xd;
       y[dof] = yc;
-      if (DOT == 1 || DOT == 2) d[0] += w[dof] * yc;
+      if (DOT == 1 || DOT == 2) d[0] += wv * yc;
       if (DOT == 2) d[1] += yc * yc;
       if (DOT == 3) {  // single-reduction CG: (w.x, y.x, x.x) with x the multiplied vector
-        const double xd = x[dof];
-        d[0] += w[dof] * xd;
+        d[0] += wv * xd;
         d[1] += yc * xd;
         d[2] += xd * xd;
       }
@@ -408,6 +415,15 @@ __global__ void __launch_bounds__(256)
     double acc[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+    // epilogue operands fetched up front (see k_bspmv_u)
+    double wv = 0.0, xd = 0.0;
+    bool masked = false;
+    if (row < nrows && lane < NC) {
+      const int64_t dof = row * NC + lane;
+      if (DOT >= 1) wv = w[dof];
+      if (DOT == 3 || mask) xd = x[dof];
+      if (mask) masked = mask[dof] != 0;
+    }
     if (row < nrows) {
       const int r0 = rowptr[row], r1 = rowptr[row + 1];
       for (int k0 = r0 + lane; k0 < r1; k0 += T * U) {
@@ -460,13 +476,12 @@ __global__ void __launch_bounds__(256)
       for (int c = 1; c < NC; ++c)
         if (lane == c) yc = acc[c];
       const int64_t dof = row * NC + lane;
-      if (mask && mask[dof]) yc = x[dof];
+      if (masked) yc = xd;
       y[dof] = yc;
-      if (DOT == 1 || DOT == 2) d[0] += w[dof] * yc;
+      if (DOT == 1 || DOT == 2) d[0] += wv * yc;
       if (DOT == 2) d[1] += yc * yc;
       if (DOT == 3) {
-        const double xd = x[dof];
-        d[0] += w[dof] * xd;
+        d[0] += wv * xd;
         d[1] += yc * xd;
         d[2] += xd * xd;
       }
@@ -565,6 +580,9 @@ __global__ void __launch_bounds__(256, MINB)
     double acc[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) acc[i] = 0.0;
+    // the dot-product operand is fetched up front: loaded in the epilogue its latency would sit between two rows
+    double wv = 0.0;
+    if (DOT >= 1 && row < nrows && lane < D) wv = w[row * D + lane];
     if (row < nrows) {
       const int r0 = rowptr[row];
       const int len = (rowptr[row + 1] - r0) * D;
@@ -603,7 +621,7 @@ __global__ void __launch_bounds__(256, MINB)
         if (lane == i) yc = acc[i];
       const int64_t dof = row * D + lane;
       y[dof] = yc;
-      if (DOT >= 1) d[0] += w[dof] * yc;
+      if (DOT >= 1) d[0] += wv * yc;
       if (DOT >= 2) d[1] += yc * yc;
     }
   }
@@ -748,7 +766,9 @@ static void spmv_local(fb_ctx *ctx, const LinOp &A, const double *x, double *y, 
     case 2:
       return launch_spmm<2, 8>(ctx, A, x, y, dot_mode, w, slot, flag);
     case 3: {
-      static const int V = getenv("FB_SPMM_V") ? atoi(getenv("FB_SPMM_V")) : 0;
+      // measured on B200 at n = 74 (3.3 M rows, 29 entries per row): T=16 0.559 ms, T=8/U=2 0.423 ms, T=4/U=8 0.474 ms;
+      // contiguous row ranges per block and paired 16-byte gathers are slower (profiles/r1_spmm3_variants.txt)
+      static const int V = getenv("FB_SPMM_V") ? atoi(getenv("FB_SPMM_V")) : 7;
       switch (V) {
         case 1: return launch_spmm_u<3, 16, 2, 0>(ctx, A, x, y, dot_mode, w, slot, flag);
         case 2: return launch_spmm_u<3, 16, 2, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
@@ -763,6 +783,7 @@ static void spmv_local(fb_ctx *ctx, const LinOp &A, const double *x, double *y, 
         case 11: return launch_spmm_u<3, 4, 8, 0, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
         case 12: return launch_spmm_u<3, 4, 4, 0, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
         case 13: return launch_spmm_u<3, 8, 3, 0, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
+        case 14: return launch_spmm_u<3, 8, 1, 0>(ctx, A, x, y, dot_mode, w, slot, flag);
         default: return launch_spmm<3, 16>(ctx, A, x, y, dot_mode, w, slot, flag);
       }
     }

@@ -55,6 +55,13 @@ LinOp make_linop(const fb_mat &m, int ncomp, const uint8_t *mask);
 // ---- multi-GPU (fb_comm.cu): no-ops on a single rank
 bool fb_is_distributed(const fb_ctx *ctx);
 void fb_allreduce_slots(fb_ctx *ctx, int slot0, int count);
+double fb_allreduce_host_sum(fb_ctx *ctx, double v);
+void fb_broadcast_device(fb_ctx *ctx, void *p, size_t bytes, int root);
+// IPC-shared global vector assembled from the ranks' owned parts by remote stores (peer-memory transport only)
+struct fb_peer_vec;
+fb_peer_vec *fb_peer_vec_create(fb_ctx *ctx, int64_t n_global);  // collective; null without peer memory
+void fb_peer_vec_destroy(fb_peer_vec *v);
+const double *fb_peer_vec_gather(fb_ctx *ctx, fb_peer_vec *v, const double *owned, const int *l2g, int64_t n_owned);
 void halo_exchange(fb_ctx *ctx, DevSpace &sp, double *x, int ncomp);
 
 // ---- setup
@@ -127,6 +134,10 @@ struct KrylovWork {
 struct fb_amg;
 fb_amg *amg_setup(fb_ctx *ctx, int n, const int *rowptr, const int *col, const double *val);
 void amg_apply(fb_amg *amg, const double *r, double *z);  // z = V(1,1)-cycle applied to r (device vectors)
+// Partitioned runs: the hierarchy is the one of the GLOBAL matrix, replicated on every rank.  amg_apply then
+// gathers the ranks' owned residuals into the global vector (fb_peer_vec_gather), runs the cycle redundantly and
+// returns the owned part: the preconditioner -- hence the iteration count -- is the single-GPU one.
+void amg_set_replicated(fb_amg *amg, fb_peer_vec *gather, const int *l2g_host, int n_owned);
 void amg_destroy(fb_amg *amg);
 int amg_num_levels(const fb_amg *amg);
 double amg_complexity(const fb_amg *amg);

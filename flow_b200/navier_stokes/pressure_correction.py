@@ -64,7 +64,31 @@ def _engine(W, P, opts=None):
         _lib.check(lib.fb_ns_create(W.handle(), P.handle(), C.byref(opts) if opts is not None else None, C.byref(h)),
                    W.mesh().ctx, "fb_ns_create")
         cache[key] = h
+        _replicate_pressure_amg(h, W, P)
     return cache[key]
+
+
+def _replicate_pressure_amg(ns, W, P):
+    """Partitioned runs: hand the engine the GLOBAL P1 stiffness matrix so that the AMG preconditioner of the
+    pressure solve is the single-GPU hierarchy, replicated on every rank (fb_ns_set_pressure_amg_global).  The
+    matrix is assembled redundantly from the global mesh every rank already holds; collective, set-up only."""
+    mesh = W.mesh()
+    if getattr(mesh, "partition", None) is None or getattr(mesh, "global_mesh", None) is None:
+        return
+    if not lib.fb_comm_uses_peer_memory(mesh.ctx):
+        return
+    from ..dolfin import FunctionSpace
+
+    Pg = FunctionSpace(mesh.global_mesh, "CG", 1)
+    A = _lib.vp()
+    _lib.check(lib.fb_assemble_stiffness(Pg.handle(), C.byref(A)), mesh.ctx, "fb_assemble_stiffness(global P1)")
+    plan = P.nodes.plan
+    l2g = np.ascontiguousarray(plan.l2g[:plan.n_owned], dtype=np.int64)
+    try:
+        _lib.check(lib.fb_ns_set_pressure_amg_global(ns, Pg.handle(), A, _lib.as_pi64(l2g), l2g.size), mesh.ctx,
+                   "fb_ns_set_pressure_amg_global")
+    finally:
+        lib.fb_mat_destroy(A)
 
 
 def _forcing(f, W, theta):

@@ -132,17 +132,62 @@ def distributed_mesh(gmesh, rank, nranks, device=None, part=None):
     _lib.check(lib.fb_mesh_set_boundary_facets(m.handle, P.bf_cell.size, _lib.as_pi32(P.bf_cell), _lib.as_pi32(P.bf_local)),
                m.ctx, "fb_mesh_set_boundary_facets")
     m.partition = P
+    m.global_mesh = gmesh
     return m
 
 
-def init_comm(ctx, rank, nranks, broadcast_bytes):
-    """Create the library's NCCL communicator.  `broadcast_bytes(buf)` must broadcast a 128-byte
-    numpy uint8 array from rank 0 in place (e.g. through torch.distributed)."""
+def init_comm(ctx, rank, nranks, broadcast_bytes, allgather_bytes=None, staging_mb_per_peer=8):
+    """Create the library's communicator.  `broadcast_bytes(buf)` must broadcast a 128-byte numpy uint8
+    array from rank 0 in place (e.g. through torch.distributed).
+
+    If `allgather_bytes(buf) -> (nranks, len(buf)) uint8 array` is given (default: torch.distributed when it is
+    initialised) and FB_NO_P2P is unset, the ranks also exchange CUDA IPC handles of their peer-memory windows:
+    halo exchanges and dot-product all-reduces then run as the library's own kernels over NVLink peer memory and
+    NCCL is only the fallback.  Returns True if the peer-memory transport is active."""
+    import os
+
     ident = np.zeros(128, dtype=np.uint8)
     if rank == 0:
         _lib.check(lib.fb_comm_unique_id(ident.ctypes.data_as(C.c_void_p)), ctx, "fb_comm_unique_id")
     ident = broadcast_bytes(ident)
     _lib.check(lib.fb_comm_init(ctx, rank, nranks, ident.ctypes.data_as(C.c_void_p)), ctx, "fb_comm_init")
+    if nranks == 1 or nranks > 8 or os.environ.get("FB_NO_P2P", "0") not in ("", "0"):
+        return False
+    if allgather_bytes is None:
+        allgather_bytes = torch_allgather()
+        if allgather_bytes is None:
+            return False
+    handle = np.zeros(64, dtype=np.uint8)
+    ok = lib.fb_comm_window_create(ctx, int(staging_mb_per_peer) << 20, handle.ctypes.data_as(C.c_void_p)) == 0
+    # every rank takes part in both all-gathers, whatever happened locally: the transport must be the same everywhere
+    handles = np.ascontiguousarray(allgather_bytes(handle))
+    if ok:
+        ok = lib.fb_comm_window_open(ctx, handles.ctypes.data_as(C.c_void_p)) == 0
+    all_ok = bool(allgather_bytes(np.array([1 if ok else 0], dtype=np.uint8)).min())
+    if not all_ok:
+        lib.fb_comm_window_disable(ctx)
+    return all_ok
+
+
+def torch_allgather(device=None):
+    """allgather_bytes implementation on torch.distributed; None if no process group is initialised."""
+    try:
+        import torch
+        import torch.distributed as dist
+    except ImportError:
+        return None
+    if not dist.is_available() or not dist.is_initialized():
+        return None
+
+    def gather(buf):
+        t = torch.from_numpy(np.ascontiguousarray(buf).copy())
+        if dist.get_backend() == "nccl":
+            t = t.cuda(device)
+        out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+        dist.all_gather(out, t)
+        return torch.stack(out).cpu().numpy()
+
+    return gather
 
 
 def torch_broadcast(device=None):

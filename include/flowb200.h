@@ -104,6 +104,14 @@ int fb_space_set_halo(fb_space *space, int nneigh, const int32_t *ranks, const i
 int fb_comm_unique_id(void *id128);
 int fb_comm_init(fb_ctx *ctx, int rank, int nranks, const void *id128);
 int fb_comm_destroy(fb_ctx *ctx);
+/* Peer-memory transport over NVLink (replaces NCCL on the hot path: halo exchange and dot-product all-reduce
+ * become our own kernels storing into IPC-mapped windows of the other ranks).  Each rank creates its window
+ * and gets a 64-byte CUDA IPC handle; the launcher all-gathers the handles (rank order) and every rank opens
+ * them.  Optional: without it the same operations go through NCCL. */
+int fb_comm_window_create(fb_ctx *ctx, int64_t staging_bytes_per_peer, void *handle64);
+int fb_comm_window_open(fb_ctx *ctx, const void *handles);
+int fb_comm_window_disable(fb_ctx *ctx);
+int fb_comm_uses_peer_memory(fb_ctx *ctx);
 /* refresh the ghost entries of a host vector (ncomp interleaved components) -- test/debug helper */
 int fb_space_halo_exchange(fb_space *space, int ncomp, double *x);
 
@@ -179,6 +187,11 @@ int fb_ns_opts_default(fb_ns_opts *opts);
 /* W: vector P2 space (ncomp == gdim), P: scalar P1 space on the same mesh. */
 int fb_ns_create(fb_space *W, fb_space *P, const fb_ns_opts *opts, fb_ns **out);
 int fb_ns_destroy(fb_ns *ns);
+/* Partitioned runs with the peer-memory transport: replace the per-rank (additive Schwarz) hierarchy by the
+ * hierarchy of the GLOBAL P1 stiffness matrix, replicated on every rank; l2g[i] = global vertex of the i-th owned
+ * local pressure dof.  The preconditioner, hence the CG iteration count, is then the single-GPU one for any
+ * number of ranks.  Collective.  No-op when Jacobi is the pressure preconditioner or NCCL is the transport. */
+int fb_ns_set_pressure_amg_global(fb_ns *ns, fb_space *Pglobal, fb_mat *Aglobal, const int64_t *l2g, int64_t n_owned);
 /* AMG hierarchy of the pressure operator: number of levels, operator complexity, rows per level */
 int fb_ns_amg_info(fb_ns *ns, int *levels, double *complexity, int *sizes, int max_sizes);
 /* One step.  scheme: fb_scheme; flags: FB_ROTATIONAL | FB_CHORIN | FB_DEVICE_PTRS.

@@ -24,6 +24,10 @@ def main():
     os.environ["FLOW_B200_DEVICE"] = str(local)
     from flow_b200 import _lib, dolfin as d, navier_stokes as nav, parallel
 
+    # both runs are driven well below the reference's |F| < 1e-10 so that the comparison does not measure where each
+    # Newton iteration happened to stop (see tests/test_gpu_variants.py)
+    nav.set_options(newton_atol=1e-13)
+
     def cavity(mesh, steps, scheme):
         W = d.VectorFunctionSpace(mesh, "CG", 2)
         P = d.FunctionSpace(mesh, "CG", 1)
@@ -44,7 +48,9 @@ def main():
         results[name] = (ug._vec.copy(), pg._vec.copy(), hg)
 
     ctx = _lib.context()
-    parallel.init_comm(ctx, rank, world, parallel.torch_broadcast(local))
+    p2p = parallel.init_comm(ctx, rank, world, parallel.torch_broadcast(local))
+    if rank == 0:
+        print("dist_check transport: %s" % ("peer memory (NVLink windows)" if p2p else "NCCL"), flush=True)
     m = parallel.distributed_mesh(g, rank, world)
     ok = True
     for name, scheme in (("ipcs", nav.IPCS()), ("rotational_cn", nav.Rotational("crank-nicolson"))):
