@@ -55,7 +55,8 @@ class NSOpts(C.Structure):
         ("jacobian_across_steps", C.c_int),
         ("warm_start", C.c_int),
         ("jacobian_fp32", C.c_int),
-        ("reserved", C.c_int * 3),
+        ("extrapolate_guess", C.c_int),
+        ("reserved", C.c_int * 2),
     ]
 
 
@@ -79,7 +80,8 @@ class NSStats(C.Structure):
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
-        d["newton_residuals"] = [self.reserved[k] for k in range(min(7, self.newton_its + 1))]
+        d["newton_residuals"] = [self.reserved[k] for k in range(min(6, self.newton_its + 1))]
+        d["extrapolated_start"] = int(self.reserved[6])
         d["jacobian_assemblies"] = int(self.reserved[7])
         return d
 

@@ -414,6 +414,11 @@ struct fb_ns {
   int newton_fresh = 0;      // Newton iterations of the last step that started with a fresh Jacobian
   int newton_last = 0;
   DBuf<float> J32;           // fp32 copy of J for the Krylov solves (opts.jacobian_fp32)
+  bool qstate_valid = false; // qstate holds u, grad u of the CURRENT Newton iterate
+  // extrapolated Newton start: u0 of the previous call, its dt and the |F| that call started from
+  DBuf<double> uprev;
+  bool have_prev = false;
+  double dt_prev = 0.0, r0_prev = 0.0;
   fb_amg *amg_p = nullptr;      // AMG hierarchy of the P1 stiffness (pure Neumann variant)
   fb_amg *amg_pbc = nullptr;    // ... of the Dirichlet-eliminated matrix, rebuilt when the constrained set changes
   std::vector<int64_t> amg_pbc_dofs;
@@ -531,6 +536,7 @@ int fb_ns_opts_default(fb_ns_opts *o) {
   o->jacobian_across_steps = 1;
   o->warm_start = 1;
   o->jacobian_fp32 = 0;
+  o->extrapolate_guess = 0;
   return FB_OK;
 }
 
@@ -753,20 +759,6 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
   FB_CUDA(cudaMemcpyAsync(ns->ui.p, ns->u0.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));  // :220
   MomentumArgs ma{dt, rho, mu, theta, ns->ui.p, ns->u0.p, ns->p0.p, ns->P->cell_nodes.p};
   ns_build_Fconst(ns, ma, have_load);
-  auto residual = [&]() {
-    FB_CUDA(cudaEventRecord(dv->ev[8], st));
-    FB_CUDA(cudaMemcpyAsync(ns->F.p, ns->Fconst.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
-    assemble_momentum_F_new_state(ctx, *ns->W, ma, ns->F.p, ns_qstate(ns));
-    bc_residual(ctx, ns->F.p, ns->ui.p, ns->ubc_dofs.p, ns->ubc_vals.p, n_ubc);
-    FB_CUDA(cudaEventRecord(dv->ev[9], st));
-    const double nrm = vec_norm2_sync(ctx, ns->F.p, nu_o);
-    float t = 0;
-    FB_CUDA(cudaEventElapsedTime(&t, dv->ev[8], dv->ev[9]));
-    s.ms_assembly_F += t;
-    return nrm;
-  };
-  double r = residual();
-  int newton = 0;
   // A Jacobian from an earlier step is kept as the chord operator while nothing it depends on (other than the
   // linearisation point) changed and it still contracts as well as a fresh one did
   uint64_t bc_hash = 1469598103934665603ull;
@@ -775,8 +767,46 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
   bool have_J = o.jacobian_reuse && o.jacobian_across_steps && ns->J_valid && bc_hash == ns->J_bc_hash &&
                 std::memcmp(J_key, ns->J_key, sizeof(J_key)) == 0 && ns->contraction > 0.0 && ns->contraction < 1e-2 &&
                 ns->newton_last <= ns->newton_fresh;
+  // want_q: the residual kernel also stores u, grad u at the quadrature points (3.3 GB at n = 74) for a Jacobian
+  // assembly that follows immediately; otherwise the Jacobian kernel recomputes them
+  auto residual = [&](bool want_q) {
+    FB_CUDA(cudaEventRecord(dv->ev[8], st));
+    FB_CUDA(cudaMemcpyAsync(ns->F.p, ns->Fconst.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
+    assemble_momentum_F_new_state(ctx, *ns->W, ma, ns->F.p, want_q ? ns_qstate(ns) : nullptr);
+    ns->qstate_valid = want_q;
+    bc_residual(ctx, ns->F.p, ns->ui.p, ns->ubc_dofs.p, ns->ubc_vals.p, n_ubc);
+    FB_CUDA(cudaEventRecord(dv->ev[9], st));
+    const double nrm = vec_norm2_sync(ctx, ns->F.p, nu_o);
+    float t = 0;
+    FB_CUDA(cudaEventElapsedTime(&t, dv->ev[8], dv->ev[9]));
+    s.ms_assembly_F += t;
+    return nrm;
+  };
+  // Newton start.  The reference starts from u0 (:220).  In a time loop the linear extrapolation
+  // u0 + dt/dt_prev (u0 - u0_prev) is the better guess (its residual is O(dt^2) instead of O(dt)); it is kept only
+  // if its |F| is below twice what the previous step started from, otherwise u0 is used as in the reference.  The root and
+  // the acceptance test are unchanged.
+  double r = -1.0;
+  if (o.extrapolate_guess && ns->have_prev && ns->dt_prev > 0.0 && ns->r0_prev > 0.0) {
+    const double w = dt / ns->dt_prev;
+    vec_axpby(ctx, ns->ui.p, 1.0 + w, ns->u0.p, -w, ns->uprev.p, nu);
+    const double r_ext = residual(!have_J);
+    if (r_ext == r_ext && r_ext < 2.0 * ns->r0_prev) {
+      r = r_ext;
+      s.reserved[6] = 1.0;  // extrapolated start accepted
+    } else {
+      FB_CUDA(cudaMemcpyAsync(ns->ui.p, ns->u0.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  if (r < 0.0) r = residual(!have_J);
+  ns->uprev.alloc((size_t)nu);
+  FB_CUDA(cudaMemcpyAsync(ns->uprev.p, ns->u0.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
+  ns->have_prev = true;
+  ns->dt_prev = dt;
+  int newton = 0;
   const bool started_stale = have_J;
   bool reuse_ok = true;
+  ns->r0_prev = std::max(r, 10.0 * o.newton_atol);  // what the next extrapolated start has to beat
   s.reserved[0] = r;  // reserved[k] = |F| after k Newton updates (first 8)
   const int mom_check = o.check_every > 0 ? o.check_every : 2;
   float ms;
@@ -792,7 +822,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     // (chord iteration) as long as the previous update contracted the residual well -- the convergence
     // test on |F| is unchanged, only the path to it is cheaper (opts.jacobian_reuse = 0: plain Newton).
     if (!have_J || !o.jacobian_reuse || !reuse_ok) {
-      assemble_momentum_J(ctx, *ns->W, ma, ns->J.val.p, ns->qstate.p);
+      assemble_momentum_J(ctx, *ns->W, ma, ns->J.val.p, ns->qstate_valid ? ns->qstate.p : nullptr);
       bc_rows_identity_blocked(ctx, *ns->W, D, ns->J.val.p, ns->ubc_dofs.p, n_ubc);
       jacobi_setup_blocked(ctx, *ns->W, D, ns->J.val.p, o.momentum_precond == FB_BLOCK_JACOBI ? 1 : 0, ns->binv.p);
       if (o.jacobian_fp32) {
@@ -837,12 +867,12 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     vec_axpy(ctx, ns->ui.p, -1.0, ns->delta.p, nu_o);
     halo_exchange(ctx, *ns->W, ns->ui.p, D);  // the next assembly reads ui on ghost nodes
     ++newton;
-    const double r_new = residual();
+    const double r_new = residual(!o.jacobian_reuse);  // plain Newton re-assembles right away
     const double ratio = r > 0.0 ? r_new / r : 0.0;
     if (newton == 1) ns->contraction = ratio;
     reuse_ok = ratio < 0.1;
     r = r_new;
-    if (newton < 7) s.reserved[newton] = r;
+    if (newton < 6) s.reserved[newton] = r;
     FB_CUDA(cudaEventElapsedTime(&ms, dv->ev[4], dv->ev[5]));
     s.ms_assembly_J += ms;
     FB_CUDA(cudaEventElapsedTime(&ms, dv->ev[5], dv->ev[10]));

@@ -168,7 +168,10 @@ typedef struct fb_ns_opts {
   int jacobian_fp32;     /* 0 (default).  1: the chord Jacobian used INSIDE the Krylov solves is stored in fp32 (half the
                             SpMV bytes); residuals, vectors, dots and the Newton test |F| < atol stay fp64, so the
                             accepted solution satisfies the same fp64 criterion (mixed-precision inexact Newton) */
-  int reserved[3];
+  int extrapolate_guess; /* 0 (default): Newton starts from u0 (:220).  1: from u0 + dt/dt_prev (u0 - u0_prev) when that guess
+                            has a residual below twice what the previous step started from (smooth time loops; no gain
+                            on the impulsively started cavity of the benchmark) */
+  int reserved[2];
 } fb_ns_opts;
 
 typedef struct fb_ns_stats {
@@ -180,7 +183,8 @@ typedef struct fb_ns_stats {
   double ms_tentative, ms_pressure, ms_correction, ms_total; /* CUDA-event times */
   double ms_assembly_J, ms_assembly_F, ms_momentum_solve;
   int64_t launches;
-  double reserved[8]; /* [0..6]: |F| after k Newton updates; [7]: Jacobian assemblies in this step */
+  double reserved[8]; /* [0..5]: |F| after k Newton updates; [6]: 1 if the extrapolated start was used;
+                         [7]: Jacobian assemblies in this step */
 } fb_ns_stats;
 
 int fb_ns_opts_default(fb_ns_opts *opts);

@@ -15,10 +15,12 @@ pytestmark = pytest.mark.gpu
 
 VARIANTS = {
     "defaults": {},
-    "plain": dict(pressure_precond="jacobi", warm_start=0, jacobian_across_steps=0, jacobian_reuse=0, adaptive_forcing=0),
+    "plain": dict(pressure_precond="jacobi", warm_start=0, jacobian_across_steps=0, jacobian_reuse=0, adaptive_forcing=0,
+                  extrapolate_guess=0),
     "jacobi_warm": dict(pressure_precond="jacobi", warm_start=1),
     "amg_cold": dict(pressure_precond="amg", warm_start=0, jacobian_across_steps=0),
     "fp32_jacobian": dict(jacobian_fp32=1),
+    "extrapolated_start": dict(extrapolate_guess=1),
 }
 
 
