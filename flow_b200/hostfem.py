@@ -244,7 +244,11 @@ def structured_rectangle_with_hole(a, b, nx, ny, center, radius, diagonal="left/
     cells = cells[keep]
     # drop degenerate cells created by snapping and renumber the used vertices
     vol = cell_volumes(pts, cells)
-    cells = cells[vol > 1e-3 * h * h]
+    # ... and slivers (longest edge^2 / area > 16; a right isosceles triangle has 4): on fine grids the radial
+    # snap squashes a few cells next to the circle to aspect ratios of several hundred
+    tri = pts[cells]
+    emax2 = np.max([((tri[:, i] - tri[:, j]) ** 2).sum(axis=1) for i, j in ((0, 1), (1, 2), (0, 2))], axis=0)
+    cells = cells[(vol > 1e-3 * h * h) & (emax2 < 16.0 * np.maximum(vol, 1e-300))]
     used = np.unique(cells)
     remap = -np.ones(pts.shape[0], dtype=np.int64)
     remap[used] = np.arange(used.size)
