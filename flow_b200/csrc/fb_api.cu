@@ -399,7 +399,6 @@ struct fb_ns {
   int64_t nu_o = 0, np_o = 0;  // owned dofs (== local on a single rank)
   fb_ns_opts opts;
   fb_mat Ap, Mu, J;
-  DBuf<double> qstate;  // u, grad u of the current Newton iterate at the cell quadrature points (F kernel -> J kernel)
   DBuf<double> u0, p0, ui, p1, u1, F, Fconst, delta, load, ftmp, bp, bu, dinv_p, dinv_u, binv, tmp_u, tmp_p, xg_u, xg_p, Ap_bc;
   DBuf<uint8_t> mask_u, mask_p;
   DBuf<int64_t> ubc_dofs, pbc_dofs;
@@ -414,7 +413,6 @@ struct fb_ns {
   int newton_fresh = 0;      // Newton iterations of the last step that started with a fresh Jacobian
   int newton_last = 0;
   DBuf<float> J32;           // fp32 copy of J for the Krylov solves (opts.jacobian_fp32)
-  bool qstate_valid = false; // qstate holds u, grad u of the CURRENT Newton iterate
   // extrapolated Newton start: u0 of the previous call, its dt and the |F| that call started from
   DBuf<double> uprev;
   bool have_prev = false;
@@ -484,17 +482,10 @@ static bool ns_build_load(fb_ns *ns, int forcing, const double *f0, const double
   return true;
 }
 
-static double *ns_qstate(fb_ns *ns) {
-  const int D = ns->D;
-  const int64_t nq = D == 2 ? 7 : 14;
-  ns->qstate.alloc((size_t)(ns->W->nc * nq * D * (D + 1)));
-  return ns->qstate.p;
-}
-
 static void ns_assemble_F(fb_ns *ns, const MomentumArgs &a, bool have_load) {
   FB_CUDA(cudaMemsetAsync(ns->F.p, 0, sizeof(double) * ns->nu, ns->ctx->dev->stream));
   assemble_momentum_F_old_state(ns->ctx, *ns->W, a, ns->F.p);
-  assemble_momentum_F_new_state(ns->ctx, *ns->W, a, ns->F.p, ns_qstate(ns));
+  assemble_momentum_F_new_state(ns->ctx, *ns->W, a, ns->F.p);
   if (have_load) vec_axpy(ns->ctx, ns->F.p, -a.dt / a.rho, ns->load.p, ns->nu_o);
 }
 
@@ -663,7 +654,7 @@ int fb_ns_residual(fb_ns *ns, double dt, double rho, double mu, double theta, co
     have_load = true;
   }
   ns_assemble_F(ns, a, have_load);
-  if (want_J) assemble_momentum_J(_ctx, *ns->W, a, ns->J.val.p, ns->qstate.p);
+  if (want_J) assemble_momentum_J(_ctx, *ns->W, a, ns->J.val.p);
   FB_CUDA(cudaMemcpyAsync(F_out, ns->F.p, sizeof(double) * ns->nu, cudaMemcpyDeviceToHost, st));
   FB_CUDA(cudaStreamSynchronize(st));
   FB_API_END
@@ -767,13 +758,10 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
   bool have_J = o.jacobian_reuse && o.jacobian_across_steps && ns->J_valid && bc_hash == ns->J_bc_hash &&
                 std::memcmp(J_key, ns->J_key, sizeof(J_key)) == 0 && ns->contraction > 0.0 && ns->contraction < 1e-2 &&
                 ns->newton_last <= ns->newton_fresh;
-  // want_q: the residual kernel also stores u, grad u at the quadrature points (3.3 GB at n = 74) for a Jacobian
-  // assembly that follows immediately; otherwise the Jacobian kernel recomputes them
-  auto residual = [&](bool want_q) {
+  auto residual = [&]() {
     FB_CUDA(cudaEventRecord(dv->ev[8], st));
     FB_CUDA(cudaMemcpyAsync(ns->F.p, ns->Fconst.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
-    assemble_momentum_F_new_state(ctx, *ns->W, ma, ns->F.p, want_q ? ns_qstate(ns) : nullptr);
-    ns->qstate_valid = want_q;
+    assemble_momentum_F_new_state(ctx, *ns->W, ma, ns->F.p);
     bc_residual(ctx, ns->F.p, ns->ui.p, ns->ubc_dofs.p, ns->ubc_vals.p, n_ubc);
     FB_CUDA(cudaEventRecord(dv->ev[9], st));
     const double nrm = vec_norm2_sync(ctx, ns->F.p, nu_o);
@@ -790,7 +778,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
   if (o.extrapolate_guess && ns->have_prev && ns->dt_prev > 0.0 && ns->r0_prev > 0.0) {
     const double w = dt / ns->dt_prev;
     vec_axpby(ctx, ns->ui.p, 1.0 + w, ns->u0.p, -w, ns->uprev.p, nu);
-    const double r_ext = residual(!have_J);
+    const double r_ext = residual();
     if (r_ext == r_ext && r_ext < 2.0 * ns->r0_prev) {
       r = r_ext;
       s.reserved[6] = 1.0;  // extrapolated start accepted
@@ -798,7 +786,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
       FB_CUDA(cudaMemcpyAsync(ns->ui.p, ns->u0.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
     }
   }
-  if (r < 0.0) r = residual(!have_J);
+  if (r < 0.0) r = residual();
   ns->uprev.alloc((size_t)nu);
   FB_CUDA(cudaMemcpyAsync(ns->uprev.p, ns->u0.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
   ns->have_prev = true;
@@ -822,7 +810,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     // (chord iteration) as long as the previous update contracted the residual well -- the convergence
     // test on |F| is unchanged, only the path to it is cheaper (opts.jacobian_reuse = 0: plain Newton).
     if (!have_J || !o.jacobian_reuse || !reuse_ok) {
-      assemble_momentum_J(ctx, *ns->W, ma, ns->J.val.p, ns->qstate_valid ? ns->qstate.p : nullptr);
+      assemble_momentum_J(ctx, *ns->W, ma, ns->J.val.p);
       bc_rows_identity_blocked(ctx, *ns->W, D, ns->J.val.p, ns->ubc_dofs.p, n_ubc);
       jacobi_setup_blocked(ctx, *ns->W, D, ns->J.val.p, o.momentum_precond == FB_BLOCK_JACOBI ? 1 : 0, ns->binv.p);
       if (o.jacobian_fp32) {
@@ -867,7 +855,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     vec_axpy(ctx, ns->ui.p, -1.0, ns->delta.p, nu_o);
     halo_exchange(ctx, *ns->W, ns->ui.p, D);  // the next assembly reads ui on ghost nodes
     ++newton;
-    const double r_new = residual(!o.jacobian_reuse);  // plain Newton re-assembles right away
+    const double r_new = residual();
     const double ratio = r > 0.0 ? r_new / r : 0.0;
     if (newton == 1) ns->contraction = ratio;
     reuse_ok = ratio < 0.1;

@@ -142,6 +142,102 @@ FB_HD void fb_jac_point(double w, double c1, double c2, double pa, double pb, co
     }
 }
 
+// ---- closed-form element Jacobian ----------------------------------------------------
+// All integrands of the Jacobian are polynomials on an affine cell, and grad phi_a is affine: it is the P1
+// interpolant of its D+1 vertex values.  With
+//   GA[w][k] = d_k phi_a at vertex w,   SA[k] = sum_w GA[w][k],
+//   WA[w][k] = (1/|K|) int lambda_w phi_a u_k = sum_c M3[a][c][w] U_c[k]      (M3: fb_p2_tables.h),
+//   GU[v][i][j] = d_j u_i at vertex v = sum_c U_c[i] GC[v][j],
+//   int lambda_v lambda_w = |K| (1 + delta_vw) / ((D+1)(D+2))
+// the block (test a, trial b) is, exactly (same value as the degree-5 quadrature of fb_jac_point, ~160
+// instead of ~700 fused multiply-adds per block in 3D):
+//   J[i][j] = |K| { delta_ij [ m_ab + c1 (C_ab - C_ba) + c2 tr G ] + c1 (T2[i][j] - T3[i][j]) + c2 G[i][j] }
+//   m_ab = sum_v M3[a][b][v]                 C_ab = sum_{w,k} GB[w][k] WA[w][k]   (= int (u.grad phi_b) phi_a / |K|)
+//   G[i][j] = (SB[i] SA[j] + sum_v GB[v][i] GA[v][j]) / ((D+1)(D+2))              (= int d_i phi_b d_j phi_a / |K|)
+//   T2[i][j] = sum_v M3[a][b][v] GU[v][i][j]                                      (= int phi_a phi_b d_j u_i / |K|)
+//   T3[i][j] = sum_w GA[w][j] WB[w][i]                                            (= int phi_b u_i d_j phi_a / |K|)
+template <int D>
+FB_HD void fb_p2_vertex_grad(int a, int w, const double glam[D + 1][D], double g[D]) {
+  if (a <= D) {
+    const double s = (a == w) ? 3.0 : -1.0;  // 4 lambda_a - 1 at vertex w
+    for (int k = 0; k < D; ++k) g[k] = s * glam[a][k];
+  } else {
+    const int e = a - (D + 1);
+    const int va = edge_v<D>(e, 0), vb = edge_v<D>(e, 1);
+    const double sa = (w == vb) ? 4.0 : 0.0, sb = (w == va) ? 4.0 : 0.0;
+    for (int k = 0; k < D; ++k) g[k] = sa * glam[va][k] + sb * glam[vb][k];
+  }
+}
+
+template <int D>
+FB_HD void fb_jac_pair(double vol, double c1, double c2, const double *GA, const double *SA, const double *GB,
+                       const double *SB, const double *WA, const double *WB, const double *GU, const double *m3,
+                       double J[D][D]) {
+  constexpr int NV = D + 1;
+  const double lm = 1.0 / ((D + 1) * (D + 2));
+  double gb[NV * D], wb[NV * D], mv[NV], sb[D];  // trial-node operands in registers (shared memory on the device)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int t = 0; t < NV * D; ++t) {
+    gb[t] = GB[t];
+    wb[t] = WB[t];
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int v = 0; v < NV; ++v) mv[v] = m3[v];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < D; ++k) sb[k] = SB[k];
+  double mab = 0.0, cab = 0.0, cba = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int v = 0; v < NV; ++v) mab += mv[v];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int t = 0; t < NV * D; ++t) {
+    cab += gb[t] * WA[t];
+    cba += GA[t] * wb[t];
+  }
+  double kab = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < D; ++i) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < D; ++j) {
+      double g = sb[i] * SA[j], t2 = 0.0, t3 = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int v = 0; v < NV; ++v) {
+        g += gb[v * D + i] * GA[v * D + j];
+        t2 += mv[v] * GU[(v * D + i) * D + j];
+        t3 += GA[v * D + j] * wb[v * D + i];
+      }
+      g *= lm;
+      if (i == j) kab += g;
+      J[i][j] = c1 * (t2 - t3) + c2 * g;
+    }
+  }
+  const double dg = mab + c1 * (cab - cba) + c2 * kab;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < D; ++i) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < D; ++j) J[i][j] = vol * (J[i][j] + (i == j ? dg : 0.0));
+  }
+}
+
 // One quadrature point's contribution to  coef * R_cell(u; phi_a e_i)  without the forcing term:
 //   R = -rho/2 [ ((grad u)u)_i phi_a - (u.grad phi_a) u_i ] - 2 mu eps(u)_ik d_k phi_a + p0 d_i phi_a
 // (pressure_correction.py:138-141).  Returns the value for component i.

@@ -27,6 +27,9 @@ namespace dq {
 #include "fb_quadrature.h"
 #undef FB_TABLE
 }  // namespace dq
+#define FB_TABLE static __device__ const
+#include "fb_p2_tables.h"  // FB_M3_TRI / FB_M3_TET: copied to shared memory by k_momentum_J_cf
+#undef FB_TABLE
 
 // ---- quadrature accessors ---------------------------------------------------
 template <int D>
@@ -1199,7 +1202,7 @@ __global__ void __launch_bounds__(128)
     k_momentum_F_thread(int64_t nc, const int *__restrict__ cell_nodes, const int *__restrict__ cells,
                         const double *__restrict__ xyz, double dt, double rho, double mu, const double *__restrict__ u,
                         const double *__restrict__ p0, const int *__restrict__ pcn, double cm, double cr,
-                        double *__restrict__ F, double *__restrict__ qstate) {
+                        double *__restrict__ F) {
   constexpr int NL = Elem<D>::NL2, NQ = Q5<D>::NQ;
   const double cdt = cr * dt / rho;
   const bool need_R = (cr != 0.0);
@@ -1247,15 +1250,6 @@ __global__ void __launch_bounds__(128)
           }
         }
       }
-      if (qstate) {  // u and grad u at this point, re-used by the Jacobian kernel of the same Newton iterate
-        double *qs = qstate + ((int64_t)c * NQ + q) * (D * (D + 1));
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-          qs[i * (D + 1)] = uq[i];
-#pragma unroll
-          for (int k = 0; k < D; ++k) qs[i * (D + 1) + 1 + k] = gu[i][k];
-        }
-      }
 #pragma unroll
       for (int a = 0; a < NL; ++a) {
         const double pa = fb_p2_phi<D>(a, lam);
@@ -1280,15 +1274,14 @@ __global__ void __launch_bounds__(128)
 
 template <int D>
 static void momentum_F_cells(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, const double *u, double cm, double cr,
-                             double *F, double *qstate = nullptr) {
+                             double *F) {
   static const int variant = getenv("FB_F_KERNEL") ? atoi(getenv("FB_F_KERNEL")) : 1;  // 0: warp per cell, 1: thread per cell
   if (variant == 0) {
     const int g = grid_for(W.nc * 32, MOM_WARPS * 32, ctx->dev->sm_count * 16);
     FB_LAUNCH(ctx, k_momentum_F<D>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, a.dt, a.rho, a.mu, u, a.p0, a.pcn, cm, cr, F);
   } else {
     const int g = grid_for(W.nc, 128, ctx->dev->sm_count * 16);
-    FB_LAUNCH(ctx, k_momentum_F_thread<D>, g, 128, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, a.dt, a.rho, a.mu, u, a.p0, a.pcn, cm, cr, F,
-              (cr != 0.0) ? qstate : nullptr);
+    FB_LAUNCH(ctx, k_momentum_F_thread<D>, g, 128, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, a.dt, a.rho, a.mu, u, a.p0, a.pcn, cm, cr, F);
   }
 }
 
@@ -1302,13 +1295,13 @@ void assemble_momentum_F_old_state(fb_ctx *ctx, const DevSpace &W, const Momentu
 }
 
 // F += (ui, v) - dt/rho theta R_cell(ui; v) + boundary-facet terms of the blended state
-void assemble_momentum_F_new_state(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F, double *qstate) {
+void assemble_momentum_F_new_state(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F) {
   const int gf = grid_for(W.nbf * W.nl * W.dim, 128, ctx->dev->sm_count * 16);
   if (W.dim == 2) {
-    momentum_F_cells<2>(ctx, W, a, a.ui, 1.0, a.theta, F, qstate);
+    momentum_F_cells<2>(ctx, W, a, a.ui, 1.0, a.theta, F);
     if (W.nbf) FB_LAUNCH(ctx, k_momentum_F_facets<2>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.cells.p, W.xyz.p, a, F);
   } else {
-    momentum_F_cells<3>(ctx, W, a, a.ui, 1.0, a.theta, F, qstate);
+    momentum_F_cells<3>(ctx, W, a, a.ui, 1.0, a.theta, F);
     if (W.nbf) FB_LAUNCH(ctx, k_momentum_F_facets<3>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.cells.p, W.xyz.p, a, F);
   }
 }
@@ -1316,7 +1309,7 @@ void assemble_momentum_F_new_state(fb_ctx *ctx, const DevSpace &W, const Momentu
 void assemble_momentum_F(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F) {
   FB_CUDA(cudaMemsetAsync(F, 0, sizeof(double) * W.nnodes * W.dim, ctx->dev->stream));
   assemble_momentum_F_old_state(ctx, W, a, F);
-  assemble_momentum_F_new_state(ctx, W, a, F, nullptr);
+  assemble_momentum_F_new_state(ctx, W, a, F);
 }
 
 template <int D>
@@ -1385,89 +1378,113 @@ __global__ void __launch_bounds__(MOM_WARPS * 32)
   }
 }
 
-// Register-only Jacobian kernel: thread = (cell, test node a, half of the trial nodes).  u and grad u at the
-// quadrature points come from `qstate` (written by the residual kernel of the same Newton iterate), the basis
-// functions are recomputed from the barycentric point, the NL/2 D x D blocks accumulate in registers and are
-// scattered with fp64 atomics.  ncu on the warp-per-cell version (k_momentum_J): 165 registers, 12 warps/SM,
-// 29.8 ms at 2.43 M cells against an fp64-pipe floor of ~7 ms; the shared-memory staging was the limiter.
+// Closed-form element Jacobians (fb_jac_pair, fb_element.cuh): one warp per cell.
+//   phase A (cooperative, shared memory): nodal velocities U, the vertex values GV of the affine basis gradients
+//            and their sums S, the vertex values GU of grad u, the moments WT[a][w][k] = sum_c M3[a][c][w] U_c[k];
+//   phase B: lane = (test node a, group g); the a-dependent operands stay in registers, the lane walks
+//            the trial nodes b = g, g + NG, ... and scatters each D x D block with fp64 atomics through smap.
+// ~160 fused multiply-adds per block in 3D against ~700 of the quadrature kernel k_momentum_J, no quadrature
+// tables, no hand-off buffer from the residual kernel.
 template <int D>
-__global__ void __launch_bounds__(128)
-    k_momentum_J_reg(int64_t nc, const int *__restrict__ cell_nodes, const int *__restrict__ cells,
-                     const double *__restrict__ xyz, const int *__restrict__ rowptr, const int *__restrict__ smap,
-                     MomentumArgs a, const double *__restrict__ qstate, double *__restrict__ val) {
-  constexpr int NL = Elem<D>::NL2, NQ = Q5<D>::NQ, NH = NL / 2, TPC = 2 * NL, PERQ = D * (D + 1);
-  __shared__ double s_glam[(D + 1) * D][128];  // per-thread grad(lambda): indexed with the (dynamic) node number
+struct JcfShared {
+  static constexpr int NL = Elem<D>::NL2, NV = D + 1;
+  double M3[NL * NL * NV];
+  double U[MOM_WARPS][NL][D];
+  double GV[MOM_WARPS][NL][NV * D];
+  double S[MOM_WARPS][NL][D];
+  double WT[MOM_WARPS][NL][NV * D];
+  double GU[MOM_WARPS][NV * D * D];
+};
+
+template <int D>
+__global__ void __launch_bounds__(MOM_WARPS * 32)
+    k_momentum_J_cf(int64_t nc, const int *__restrict__ cell_nodes, const int *__restrict__ cells,
+                    const double *__restrict__ xyz, const int *__restrict__ rowptr, const int *__restrict__ smap,
+                    MomentumArgs a, double *__restrict__ val) {
+  constexpr int NL = Elem<D>::NL2, NV = D + 1, NP = NL * NL;
+  constexpr int NG = 32 / NL;               // lanes per test node (3 in 3D, 5 in 2D); 32 - NG * NL lanes idle in phase B
+  constexpr int ROUNDS = (NL + NG - 1) / NG;
+  __shared__ JcfShared<D> s;
+  {
+    const double *tab = (D == 2) ? FB_M3_TRI : FB_M3_TET;
+    for (int t = threadIdx.x; t < NL * NL * NV; t += blockDim.x) s.M3[t] = tab[t];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t warp0 = blockIdx.x * (int64_t)MOM_WARPS + wid;
+  const int64_t nwarps = (int64_t)gridDim.x * MOM_WARPS;
   const double c1 = 0.5 * a.theta * a.dt, c2 = a.theta * a.dt * a.mu / a.rho;
-  const int64_t total = nc * TPC;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = t / TPC;
-    const int r = (int)(t - c * TPC);
-    const int ta = r >> 1, b0 = (r & 1) * NH;
-    double vol;
-    {
-      double glam[D + 1][D];
-      cell_geometry<D>(cells + c * (D + 1), xyz, glam, vol);
-#pragma unroll
-      for (int m = 0; m <= D; ++m)
-#pragma unroll
-        for (int k = 0; k < D; ++k) s_glam[m * D + k][threadIdx.x] = glam[m][k];
+  const int ta = lane % NL, grp = lane / NL;
+  const bool active = lane < NG * NL;
+  for (int64_t c = warp0; c < nc; c += nwarps) {
+    const int *cn = cell_nodes + c * NL;
+    // scatter addresses first: their load latency hides behind phase A
+    int r0 = 0, len = 0;
+    if (active) {
+      const int I = cn[ta];
+      r0 = rowptr[I];
+      len = (rowptr[I + 1] - r0) * D;
     }
-    auto grad = [&](int n, const double *lam, double g[D]) {
-      if (n <= D) {
-        const double sc = 4.0 * lam[n] - 1.0;
+    // ---- phase A
+    double glam[D + 1][D], vol;
+    cell_geometry<D>(cells + c * (D + 1), xyz, glam, vol);  // every lane: broadcast loads, no staging
+    if (lane < NL * D) s.U[wid][lane / D][lane % D] = a.ui[(int64_t)cn[lane / D] * D + lane % D];
+    for (int t = lane; t < NL * NV; t += 32) {
+      const int n = t / NV, w = t - n * NV;
+      double g[D];
+      fb_p2_vertex_grad<D>(n, w, glam, g);
 #pragma unroll
-        for (int k = 0; k < D; ++k) g[k] = sc * s_glam[n * D + k][threadIdx.x];
-      } else {
-        const int e = n - (D + 1);
-        const int va = edge_v<D>(e, 0), vb = edge_v<D>(e, 1);
-        const double sa = 4.0 * lam[vb], sb = 4.0 * lam[va];
+      for (int k = 0; k < D; ++k) s.GV[wid][n][w * D + k] = g[k];
+    }
+    __syncwarp();
+    if (lane < NL * D) {
+      const int n = lane / D, k = lane % D;
+      double sum = 0.0;
 #pragma unroll
-        for (int k = 0; k < D; ++k) g[k] = sa * s_glam[va * D + k][threadIdx.x] + sb * s_glam[vb * D + k][threadIdx.x];
+      for (int w = 0; w < NV; ++w) sum += s.GV[wid][n][w * D + k];
+      s.S[wid][n][k] = sum;
+    }
+    for (int t = lane; t < NV * D * D; t += 32) {  // GU[v][i][j] = sum_c U_c[i] GV_c[v][j]
+      const int v = t / (D * D), i = (t / D) % D, j = t % D;
+      double sum = 0.0;
+#pragma unroll
+      for (int cc = 0; cc < NL; ++cc) sum += s.U[wid][cc][i] * s.GV[wid][cc][v * D + j];
+      s.GU[wid][t] = sum;
+    }
+    for (int t = lane; t < NL * NV * D; t += 32) {  // WT[n][w][k] = sum_c M3[n][c][w] U_c[k]
+      const int n = t / (NV * D), w = (t / D) % NV, k = t % D;
+      double sum = 0.0;
+#pragma unroll
+      for (int cc = 0; cc < NL; ++cc) sum += s.M3[(n * NL + cc) * NV + w] * s.U[wid][cc][k];
+      s.WT[wid][n][w * D + k] = sum;
+    }
+    __syncwarp();
+    // ---- phase B
+    if (active) {
+      double GA[NV * D], SA[D], WA[NV * D];  // GU is read from shared memory: one address per warp -> broadcast
+#pragma unroll
+      for (int t = 0; t < NV * D; ++t) {
+        GA[t] = s.GV[wid][ta][t];
+        WA[t] = s.WT[wid][ta][t];
       }
-    };
-    double acc[NH][D][D];
 #pragma unroll
-    for (int h = 0; h < NH; ++h)
+      for (int k = 0; k < D; ++k) SA[k] = s.S[wid][ta][k];
+#pragma unroll 1
+      for (int r = 0; r < ROUNDS; ++r) {
+        const int tb = grp + r * NG;
+        if (tb < NL) {
+          const int slot = smap[c * NP + ta * NL + tb];  // issued before the block's arithmetic
+          double J[D][D];
+          fb_jac_pair<D>(vol, c1, c2, GA, SA, s.GV[wid][tb], s.S[wid][tb], WA, s.WT[wid][tb], s.GU[wid], &s.M3[(ta * NL + tb) * NV], J);
+          double *base = val + (int64_t)r0 * (D * D) + (int64_t)(slot - r0) * D;
 #pragma unroll
-      for (int i = 0; i < D; ++i)
+          for (int i = 0; i < D; ++i)
 #pragma unroll
-        for (int j = 0; j < D; ++j) acc[h][i][j] = 0.0;
-    const double *qs = qstate + (int64_t)c * NQ * PERQ;
-    for (int q = 0; q < NQ; ++q) {
-      double lam[D + 1];
-#pragma unroll
-      for (int m = 0; m <= D; ++m) lam[m] = Q5<D>::lam(q, m);
-      const double w = Q5<D>::w(q) * vol;
-      double u[D], gu[D][D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        u[i] = qs[q * PERQ + i * (D + 1)];
-#pragma unroll
-        for (int k = 0; k < D; ++k) gu[i][k] = qs[q * PERQ + i * (D + 1) + 1 + k];
-      }
-      const double pa = fb_p2_phi<D>(ta, lam);
-      double ga[D];
-      grad(ta, lam, ga);
-#pragma unroll
-      for (int h = 0; h < NH; ++h) {
-        const double pb = fb_p2_phi<D>(b0 + h, lam);
-        double gb[D];
-        grad(b0 + h, lam, gb);
-        fb_jac_point<D>(w, c1, c2, pa, pb, ga, gb, u, gu, acc[h]);
+            for (int j = 0; j < D; ++j) atomicAdd(base + (int64_t)i * len + j, J[i][j]);
+        }
       }
     }
-    const int I = cell_nodes[c * NL + ta];
-    const int r0 = rowptr[I];
-    const int len = (rowptr[I + 1] - r0) * D;
-#pragma unroll
-    for (int h = 0; h < NH; ++h) {
-      const int slot = smap[c * (NL * NL) + ta * NL + b0 + h];
-      double *base = val + (int64_t)r0 * (D * D) + (int64_t)(slot - r0) * D;
-#pragma unroll
-      for (int i = 0; i < D; ++i)
-#pragma unroll
-        for (int j = 0; j < D; ++j) atomicAdd(base + (int64_t)i * len + j, acc[h][i][j]);
-    }
+    __syncwarp();
   }
 }
 
@@ -1503,22 +1520,19 @@ __global__ void k_momentum_J_facets(int64_t nbf, const int *__restrict__ bf_cell
 }
 
 
-void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *Jval, const double *qstate) {
+void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *Jval) {
   const int D = W.dim;
   FB_CUDA(cudaMemsetAsync(Jval, 0, sizeof(double) * W.nnz * D * D, ctx->dev->stream));
   const int g = grid_for(W.nc * 32, MOM_WARPS * 32, ctx->dev->sm_count * 16);
   const int gf = grid_for(W.nbf * W.nl * W.nl, 128, ctx->dev->sm_count * 16);
-  // 0 (default): warp per cell with shared-memory staging; 1: registers + qstate (needs the thread-per-cell
-  // residual kernel).  Measured at n = 74 on B200: 32 ms vs 39 ms per assembly -- the register version is
-  // limited by its 229 registers (8 warps/SM) and scattered atomics, kept for further tuning.
-  static const int variant = (getenv("FB_F_KERNEL") && atoi(getenv("FB_F_KERNEL")) == 0) ? 0
-                             : (getenv("FB_J_KERNEL") ? atoi(getenv("FB_J_KERNEL")) : 0);
-  if (variant == 1 && qstate && a.theta != 0.0) {
-    const int gr = grid_for(W.nc * 2 * W.nl, 128, ctx->dev->sm_count * 16);
+  // 2 (default): closed form (k_momentum_J_cf); 0: degree-5 quadrature (k_momentum_J), kept as the cross-check.
+  // Measured at n = 74 on B200 (2.43 M cells): 14.7 ms vs 29.8 ms per launch.
+  static const int variant = getenv("FB_J_KERNEL") ? atoi(getenv("FB_J_KERNEL")) : 2;
+  if (variant == 2) {
     if (D == 2)
-      FB_LAUNCH(ctx, k_momentum_J_reg<2>, gr, 128, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, qstate, Jval);
+      FB_LAUNCH(ctx, k_momentum_J_cf<2>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
     else
-      FB_LAUNCH(ctx, k_momentum_J_reg<3>, gr, 128, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, qstate, Jval);
+      FB_LAUNCH(ctx, k_momentum_J_cf<3>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
   } else if (D == 2) {
     FB_LAUNCH(ctx, k_momentum_J<2>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
   } else {

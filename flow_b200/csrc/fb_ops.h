@@ -106,9 +106,8 @@ struct MomentumArgs {
 };
 void assemble_momentum_F(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F);  // zero + both parts
 void assemble_momentum_F_old_state(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F);  // += u0 part
-// += ui part; qstate (optional, nc*NQ*D*(D+1)) receives u, grad u at the quadrature points for assemble_momentum_J
-void assemble_momentum_F_new_state(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F, double *qstate = nullptr);
-void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *Jval, const double *qstate = nullptr);
+void assemble_momentum_F_new_state(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F);  // += ui part
+void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *Jval);
 void assemble_pressure_rhs(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, double dt, double rho, double mu,
                            int rotational, const double *ui, const double *p0, double *b);
 // adds -dt/rho (grad phi, v) to b (which already holds M ui)

@@ -12,8 +12,11 @@
 namespace hq {
 #define FB_TABLE static const
 #include "../../flow_b200/csrc/fb_quadrature.h"
+#include "../../flow_b200/csrc/fb_p2_tables.h"
 #undef FB_TABLE
 }  // namespace hq
+template <int D> static const double *m3_table() { return D == 2 ? hq::FB_M3_TRI : hq::FB_M3_TET; }
+static int g_closed_form = 0;  // 1: cell part of J from fb_jac_pair (closed form) instead of fb_jac_point (quadrature)
 
 template <int D> struct HQ5;
 template <> struct HQ5<2> { static constexpr int NQ = hq::TRI_D5_NQ; static const double *lam() { return &hq::TRI_D5_LAM[0][0]; } static const double *w() { return hq::TRI_D5_W; } };
@@ -74,7 +77,7 @@ static void momentum(int64_t nc, const int *cell_nodes, const double *xyz, int64
             if (wt != 0.0) acc -= cdt * wt * w * fb_rhs_point<D>(i, rho, mu, phi[a], g[a], uq, gu, p0q);
             F[(int64_t)cn[a] * D + i] += acc;
           }
-        if (J && state == 0) {
+        if (J && state == 0 && !g_closed_form) {
           for (int a = 0; a < NL; ++a)
             for (int b = 0; b < NL; ++b) {
               double blk[D][D];
@@ -86,6 +89,48 @@ static void momentum(int64_t nc, const int *cell_nodes, const double *xyz, int64
             }
         }
       }
+    }
+  }
+  if (J && g_closed_form) {
+    // the staging the CUDA kernel k_momentum_J_cf does per cell, then one fb_jac_pair per block
+    constexpr int NV = D + 1;
+    const double *M3 = m3_table<D>();
+    for (int64_t c = 0; c < nc; ++c) {
+      const int *cn = cell_nodes + c * NL;
+      double glam[D + 1][D], vol;
+      geom<D>(cn, xyz, glam, vol);
+      double U[NL][D], GV[NL][NV * D], S[NL][D], Wt[NL][NV * D], GU[NV * D * D];
+      for (int a = 0; a < NL; ++a) {
+        for (int i = 0; i < D; ++i) {
+          U[a][i] = ui[(int64_t)cn[a] * D + i];
+          S[a][i] = 0.0;
+        }
+        for (int w = 0; w < NV; ++w) {
+          fb_p2_vertex_grad<D>(a, w, glam, &GV[a][w * D]);
+          for (int k = 0; k < D; ++k) S[a][k] += GV[a][w * D + k];
+        }
+      }
+      for (int v = 0; v < NV; ++v)
+        for (int i = 0; i < D; ++i)
+          for (int j = 0; j < D; ++j) {
+            double s2 = 0.0;
+            for (int cc = 0; cc < NL; ++cc) s2 += U[cc][i] * GV[cc][v * D + j];
+            GU[(v * D + i) * D + j] = s2;
+          }
+      for (int a = 0; a < NL; ++a)
+        for (int w = 0; w < NV; ++w)
+          for (int k = 0; k < D; ++k) {
+            double s2 = 0.0;
+            for (int cc = 0; cc < NL; ++cc) s2 += M3[(a * NL + cc) * NV + w] * U[cc][k];
+            Wt[a][w * D + k] = s2;
+          }
+      for (int a = 0; a < NL; ++a)
+        for (int b = 0; b < NL; ++b) {
+          double blk[D][D];
+          fb_jac_pair<D>(vol, c1, c2, GV[a], S[a], GV[b], S[b], Wt[a], Wt[b], GU, M3 + (a * NL + b) * NV, blk);
+          for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j) J[((int64_t)cn[a] * D + i) * ndofs + (int64_t)cn[b] * D + j] += blk[i][j];
+        }
     }
   }
   for (int64_t fi = 0; fi < nbf; ++fi) {
@@ -139,6 +184,7 @@ static void rhs(int64_t nc, const int *cell_nodes, const double *xyz, double dt,
 }
 
 extern "C" {
+void hs_set_closed_form(int on) { g_closed_form = on; }
 double hs_supg_tau(const double *X, const double *v, double eps, int p) { return fb_supg_tau(X, v, eps, p); }
 int hs_momentum(int dim, int64_t nc, const int *cell_nodes, const double *xyz, int64_t nbf, const int *bf_cell,
                 const int *bf_local, double dt, double rho, double mu, double theta, const double *ui, const double *u0,

@@ -20,7 +20,11 @@ def _pi(a):
 
 @pytest.mark.parametrize("name", list(MESHES))
 @pytest.mark.parametrize("theta", [1.0, 0.5, 0.0])
-def test_momentum_element_math(hostsim, name, theta):
+@pytest.mark.parametrize("closed_form", [0, 1])
+def test_momentum_element_math(hostsim, name, theta, closed_form):
+    """closed_form = 1: the cell part of J from fb_jac_pair (exact integrals through the vertex values of the affine
+    gradients and the M3 table, as k_momentum_J_cf computes it) instead of the degree-5 quadrature of fb_jac_point."""
+    hostsim.hs_set_closed_form(closed_form)
     om = oracle_mesh(name)
     W, P, ui, u0, p0, _ = rand_state(om)
     n = W.ndofs
@@ -31,6 +35,7 @@ def test_momentum_element_math(hostsim, name, theta):
                         _pi(om.bfacet_cell), _pi(om.bfacet_local), C.c_double(dt), C.c_double(rho), C.c_double(mu),
                         C.c_double(theta), _pd(ui), _pd(u0), _pd(p0), C.c_int64(n), _pd(F), _pd(J))
     Fo, Jo = forms.momentum_residual_jacobian(W, P, ui, u0, p0, np.zeros(n), dt, rho, mu, theta)
+    hostsim.hs_set_closed_form(0)
     assert rel(F, Fo) < 1e-13
     assert rel(J, Jo.toarray()) < 1e-13
 
