@@ -56,7 +56,8 @@ class NSOpts(C.Structure):
         ("warm_start", C.c_int),
         ("jacobian_fp32", C.c_int),
         ("extrapolate_guess", C.c_int),
-        ("reserved", C.c_int * 2),
+        ("momentum_inner_its", C.c_int),
+        ("reserved", C.c_int * 1),
     ]
 
 
@@ -80,7 +81,8 @@ class NSStats(C.Structure):
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
-        d["newton_residuals"] = [self.reserved[k] for k in range(min(6, self.newton_its + 1))]
+        d["newton_residuals"] = [self.reserved[k] for k in range(min(5, self.newton_its + 1))]
+        d["momentum_inner_its"] = int(self.reserved[5])
         d["extrapolated_start"] = int(self.reserved[6])
         d["jacobian_assemblies"] = int(self.reserved[7])
         return d

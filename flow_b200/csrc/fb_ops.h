@@ -150,3 +150,25 @@ int krylov_pcg(fb_ctx *ctx, const LinOp &A, const double *dinv, const double *b,
 // stops when ||r||_2 <= atol
 int krylov_bicgstab(fb_ctx *ctx, const LinOp &A, const double *minv, const double *b, double *x, double atol, int maxit,
                     int check_every, KrylovWork &w, int *iters);
+
+// Flexible GMRES(m), right preconditioning with a variable preconditioner z = pc.apply(self, v): stops when the
+// residual estimate is <= atol (absolute, like krylov_bicgstab).  inner_iters: preconditioner iterations spent.
+struct FgmresPrecond {
+  void *self = nullptr;
+  int (*apply)(void *self, const double *v, double *z, int *inner_its) = nullptr;
+};
+struct FgmresWork {
+  std::vector<DBuf<double>> V, Z;
+  DBuf<double> w;
+  void ensure(int m, int64_t n) {
+    if ((int)V.size() < m + 1) {
+      V = std::vector<DBuf<double>>(m + 1);
+      Z = std::vector<DBuf<double>>(m);
+    }
+    for (auto &v : V) v.alloc((size_t)n);
+    for (auto &z : Z) z.alloc((size_t)n);
+    w.alloc((size_t)n);
+  }
+};
+int krylov_fgmres(fb_ctx *ctx, const LinOp &A, const FgmresPrecond &pc, const double *b, double *x, double atol, int maxit,
+                  int m, FgmresWork &fw, int *iters, int *inner_iters);

@@ -23,6 +23,7 @@ _SCHEMES = {"forward euler": _lib.FORWARD_EULER, "backward euler": _lib.BACKWARD
 _last_stats = {}
 _options = {}
 _PRECONDS = {"jacobi": _lib.JACOBI, "amg": _lib.AMG}
+_SOLVERS = {"bicgstab": _lib.BICGSTAB, "fgmres": _lib.GMRES, "gmres": _lib.GMRES}
 
 
 def set_options(**kw):
@@ -34,7 +35,11 @@ def set_options(**kw):
     for k, v in kw.items():
         if k not in known or k == "reserved":
             raise KeyError("unknown option %r" % (k,))
-        _options[k] = _PRECONDS[v] if k == "pressure_precond" and isinstance(v, str) else v
+        if k == "pressure_precond" and isinstance(v, str):
+            v = _PRECONDS[v]
+        if k == "momentum_solver" and isinstance(v, str):
+            v = _SOLVERS[v]
+        _options[k] = v
 
 
 def reset_options():

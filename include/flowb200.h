@@ -142,7 +142,9 @@ int fb_mat_bench_spmv(fb_mat *mat, int ncomp, int reps, double *ms_avg, double *
  * (pressure_correction.py:468-518) = _compute_tentative_velocity (:147-255) +
  * _compute_pressure (:258-433) + _compute_velocity_correction (:436-465). */
 typedef struct fb_ns_opts {
-  int momentum_solver;   /* fb_krylov: FB_BICGSTAB (default) or FB_GMRES */
+  int momentum_solver;   /* FB_BICGSTAB: block-Jacobi BiCGStab on the Jacobian; FB_GMRES: flexible GMRES whose
+                            preconditioner is momentum_inner_its CG iterations on the constant scalar operator
+                            M + theta dt nu K per component (the Jacobian is streamed ~5x less often) */
   int momentum_precond;  /* FB_JACOBI or FB_BLOCK_JACOBI (default) */
   int pressure_precond;  /* FB_AMG (default; smoothed aggregation, V(1,1), dense pseudo-inverse on the coarsest level;
                             replaces hypre BoomerAMG of pressure_correction.py:331,:414-419; systems of fewer than
@@ -171,7 +173,8 @@ typedef struct fb_ns_opts {
   int extrapolate_guess; /* 0 (default): Newton starts from u0 (:220).  1: from u0 + dt/dt_prev (u0 - u0_prev) when that guess
                             has a residual below twice what the previous step started from (smooth time loops; no gain
                             on the impulsively started cavity of the benchmark) */
-  int reserved[2];
+  int momentum_inner_its; /* CG iterations per preconditioner application of the FB_GMRES momentum solver (default 4) */
+  int reserved[1];
 } fb_ns_opts;
 
 typedef struct fb_ns_stats {
@@ -183,8 +186,8 @@ typedef struct fb_ns_stats {
   double ms_tentative, ms_pressure, ms_correction, ms_total; /* CUDA-event times */
   double ms_assembly_J, ms_assembly_F, ms_momentum_solve;
   int64_t launches;
-  double reserved[8]; /* [0..5]: |F| after k Newton updates; [6]: 1 if the extrapolated start was used;
-                         [7]: Jacobian assemblies in this step */
+  double reserved[8]; /* [0..4]: |F| after k Newton updates; [5]: inner CG iterations of the FB_GMRES momentum
+                         solver; [6]: 1 if the extrapolated start was used; [7]: Jacobian assemblies in this step */
 } fb_ns_stats;
 
 int fb_ns_opts_default(fb_ns_opts *opts);

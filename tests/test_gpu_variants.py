@@ -21,6 +21,9 @@ VARIANTS = {
     "amg_cold": dict(pressure_precond="amg", warm_start=0, jacobian_across_steps=0),
     "fp32_jacobian": dict(jacobian_fp32=1),
     "extrapolated_start": dict(extrapolate_guess=1),
+    "bicgstab": dict(momentum_solver="bicgstab"),
+    "fgmres": dict(momentum_solver="fgmres"),
+    "fgmres_inner8": dict(momentum_solver="fgmres", momentum_inner_its=8),
 }
 
 
