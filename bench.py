@@ -11,9 +11,11 @@ tol = 1e-10, starting from rest; every step continues from the previous one.
 One JSON line on stdout (rank 0).  `value` = steps/s with the state resident in HBM
 (C ABI called with FB_DEVICE_PTRS); `e2e` = the same steps through the public API
 `flow_b200.navier_stokes.IPCS().step` with pinned host buffers, H2D/D2H inside the timed
-region.  `roofline` = the block-CSR SpMV of the momentum Jacobian (the dominant kernel).
-`cpu_baseline` = the oracle's Krylov variant (numpy assembly + C/OpenMP Jacobi-Krylov) on a
-bounded sample of the same cavity, extrapolated linearly in dofs.  The reference's own stack
+region.  `roofline` = whichever of the two SpMV kernels carries the larger share of the step
+(scalar P2 operator x 3 components, or the block-CSR momentum Jacobian), the other one is in
+`other_kernels.second_kernel`.  `cpu_baseline` = the CPU port oracle/_cstep.so (C++/OpenMP assembly,
+block-Jacobi BiCGStab for the momentum systems, Jacobi-CG for pressure and correction: the GPU path's
+first algorithm, without AMG / FGMRES) on a bounded sample of the same cavity, extrapolated linearly in dofs.  The reference's own stack
 (FEniCS/PETSc) cannot be installed here, so `--impl reference` times that same
 oracle port on the host cores.
 """
@@ -106,7 +108,7 @@ def run_reference(args, rank):
     nd_full = sum(dof_counts(n_full))
     sec, nd, threads, info = oracle_cavity_step_time(args.cpu_n, max(1, args.steps), min(args.warmup, 1))
     value = (1.0 / sec) * (nd / float(nd_full))
-    sample = ("CPU port oracle/_cstep.so (C++/OpenMP assembly + Jacobi-BiCGStab/CG, same algorithm as the GPU path) of the "
+    sample = ("CPU port oracle/_cstep.so (C++/OpenMP assembly + block-Jacobi BiCGStab / Jacobi-CG on all host threads) of the "
               "same cavity on UnitCubeMesh(%d) = %d dofs, %.2f s/step measured on %d threads (iterations %s); steps/s "
               "extrapolated linearly in dofs to %d dofs (optimistic for the CPU: Krylov counts grow with the mesh). "
               "FEniCS/PETSc itself is not installable here." % (args.cpu_n, nd, sec, threads, info, nd_full))
@@ -257,10 +259,10 @@ def main():
         e2e = {"value": ke / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int((nu + npp) * 8 + ud.size * 16),
                "d2h_bytes_per_step": int((nu + npp) * 8), "steps": ke}
 
-    # ---- roofline of the dominant kernel: block-CSR SpMV of the momentum Jacobian
+    # ---- roofline: the two SpMV kernels that carry the step (shares from the measured iteration counts)
     roofline = None
     extra = {}
-    if True:  # every rank takes part (the SpMV refreshes ghosts over NCCL); rank 0 reports
+    if True:  # every rank takes part (the SpMV refreshes ghosts over the halo exchange); rank 0 reports
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -268,30 +270,42 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         which = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")))
+        except Exception:
+            tj = {}
         h = _lib.vp()
-        lib.fb_ns_matrix(ns, 2, C.byref(h))
         msv, byt = C.c_double(), C.c_double()
-        _lib.check(lib.fb_mat_bench_spmv(h, 1, 30, C.byref(msv), C.byref(byt)), ctx, "bench_spmv")
-        ach = byt.value / (msv.value * 1e-3) / 1e9
-        traffic, traffic_src = None, None
-        if world == 1 and n == 74:  # the ncu capture is of this configuration (profiles/r1_kernel_traffic.json)
-            try:
-                tj = json.load(open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")))["k_bspmv_u<3,16,*,4,1>"]
-                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
-            except Exception:
-                pass
-        roofline = {"bound": "hbm", "kernel": "k_bspmv_u<3,16,*,4,1> (momentum Jacobian block-CSR SpMV, 60 % of the step)",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "traffic_source": traffic_src, "peak_source": which,
-                    "algorithmic_bytes_per_launch": byt.value, "ms_per_launch": msv.value,
-                    "note": "algorithmic bytes = scalar-CSR figure of SURVEY.md 8d (12 B per nnz + 20 B per row); the row-planar "
-                            "block format stores 7.5 GB, which is why achieved/peak exceeds 1; DRAM traffic / time = real HBM rate"}
-        if traffic:
-            roofline["dram_GBs"] = traffic / (msv.value * 1e-3) / 1e9
-        for name, idx, nc in (("p1_stiffness_spmv", 0, 1), ("p2_mass_spmm3", 1, 3)):
+        avg_ = lambda k: float(np.mean([hh[k] for hh in timed]))  # noqa: E731
+        cands = []
+        # (kernel label, matrix index, ncomp, launches per step, key of the ncu traffic record)
+        specs = (("k_spmm_u<3,8,*,2> (scalar P2 operator x 3 components: inner CG of the momentum preconditioner, "
+                  "velocity-correction CG, mass products)", 1, 3,
+                  avg_("momentum_inner_its") + avg_("correction_its") + 2.0, "k_spmm_u<3,8,*,2>"),
+                 ("k_bspmv_u<3,16,*,4,1> (momentum Jacobian, row-planar block CSR)", 2, 1,
+                  avg_("momentum_its") + avg_("newton_its") + 1.0 if avg_("momentum_inner_its") > 0
+                  else 2.0 * avg_("momentum_its") + avg_("newton_its") + 1.0, "k_bspmv_u<3,16,*,4,1>"))
+        for label, idx, nc, per_step, key in specs:
             lib.fb_ns_matrix(ns, idx, C.byref(h))
-            lib.fb_mat_bench_spmv(h, nc, 30, C.byref(msv), C.byref(byt))
-            extra[name] = {"ms": msv.value, "GB/s": byt.value / (msv.value * 1e-3) / 1e9}
+            _lib.check(lib.fb_mat_bench_spmv(h, nc, 30, C.byref(msv), C.byref(byt)), ctx, "bench_spmv")
+            ach = byt.value / (msv.value * 1e-3) / 1e9
+            rec = {"bound": "hbm", "kernel": label, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                   "traffic": None, "peak_source": which, "algorithmic_bytes_per_launch": byt.value, "ms_per_launch": msv.value,
+                   "launches_per_step": per_step, "share_of_step": per_step * msv.value / ms_per_step}
+            if world == 1 and n == 74 and key in tj:  # the ncu captures are of this configuration
+                rec["traffic"] = tj[key]["dram_bytes_per_launch"]
+                rec["traffic_source"] = tj[key]["source"]
+                rec["dram_GBs"] = rec["traffic"] / (msv.value * 1e-3) / 1e9
+            cands.append(rec)
+        cands.sort(key=lambda r: -r["share_of_step"])
+        roofline = cands[0]
+        roofline["note"] = ("algorithmic bytes = scalar-CSR figure of SURVEY.md 8d (12 B per nnz + 20 B per row, per component); "
+                            "both formats store less (one scalar matrix serves 3 components / one column index per 3x3 block), "
+                            "which is why achieved/peak can exceed 1; traffic / time (dram_GBs) is the real HBM rate")
+        extra["second_kernel"] = cands[1]
+        lib.fb_ns_matrix(ns, 0, C.byref(h))
+        lib.fb_mat_bench_spmv(h, 1, 30, C.byref(msv), C.byref(byt))
+        extra["p1_stiffness_spmv"] = {"ms": msv.value, "GB/s": byt.value / (msv.value * 1e-3) / 1e9}
 
     # ---- opt-in variant: chord Jacobian stored in fp32 inside the Krylov solves (residuals / vectors / tests fp64)
     variants = {}
@@ -325,7 +339,7 @@ def main():
         sec, nd, threads, info = oracle_cavity_step_time(args.cpu_n, 2, 1)
         nd_full = nu_global + np_global
         cpu = {"value": (1.0 / sec) * (nd / float(nd_full)), "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "CPU port oracle/_cstep.so (C++/OpenMP, same algorithm) on UnitCubeMesh(%d) = %d dofs: %.2f s/step on %d "
+               "sample": "CPU port oracle/_cstep.so (C++/OpenMP assembly, block-Jacobi BiCGStab / Jacobi-CG) on UnitCubeMesh(%d) = %d dofs: %.2f s/step on %d "
                          "threads, iterations %s; extrapolated linearly in dofs to %d" % (args.cpu_n, nd, sec, threads, info, nd_full)}
 
     if rank == 0:
@@ -340,9 +354,11 @@ def main():
                 "parallelism": "single GPU" if world == 1 else "mesh partitioned over %d GPUs (RCB, 1 ghost-cell layer, halo exchange + one all-reduce per "
                                "Krylov reduction over %s); rank 0 holds %d local dofs"
                                % (world, "NVLink peer-memory windows (own kernels)" if p2p else "NCCL", nu + npp),
-                "l2_policy": "working set (Jacobian %.1f GB) far exceeds the 126 MB L2" % (roofline["algorithmic_bytes_per_launch"] / 1e9 if roofline else 0),
+                "l2_policy": "working set (Jacobian %.1f GB, scalar P2 operators 1.2 GB each) far exceeds the 126 MB L2"
+                             % (6.9 * nu / 9923847.0),
             },
-            "iterations": {"newton": avg("newton_its"), "jacobian_assemblies": avg("jacobian_assemblies"), "momentum_krylov": avg("momentum_its"), "pressure_cg": avg("pressure_its"),
+            "iterations": {"newton": avg("newton_its"), "jacobian_assemblies": avg("jacobian_assemblies"), "momentum_krylov": avg("momentum_its"),
+                           "momentum_inner_cg": avg("momentum_inner_its"), "pressure_cg": avg("pressure_its"),
                            "correction_cg": avg("correction_its")},
             "phase_ms": {"tentative": avg("ms_tentative"), "pressure": avg("ms_pressure"), "correction": avg("ms_correction"),
                          "assembly_J": avg("ms_assembly_J"), "momentum_solve": avg("ms_momentum_solve")},

@@ -7,7 +7,7 @@
 //                   neighbours' windows over NVLink, then publishes an epoch flag)
 //                 + k_halo_pull (waits for the neighbours' flags, copies the staged values into the ghost
 //                   segment of x, acknowledges).
-//   all-reduce    = k_peer_allreduce: one block writes its <= 8 partial sums into every window, waits for
+//   all-reduce    = k_peer_allreduce: one block writes its <= 32 partial sums into every window, waits for
 //                   all contributions and sums them in rank order (bit-identical result on all ranks).
 // Both cost a few microseconds instead of an NCCL launch each (the Krylov iterations of a partitioned
 // run are latency bound: 560 pressure iterations of ~50 us each at 8 GPUs).  NCCL (grouped send/recv,
@@ -28,7 +28,8 @@
 #include "fb_ops.h"
 
 constexpr int FB_MAX_PEERS = 8;  // one NVSwitch domain
-constexpr size_t FB_WIN_HEADER = 4096;
+constexpr size_t FB_WIN_HEADER = 8192;
+constexpr int FB_AR_MAX = 32;  // doubles per peer all-reduce (FGMRES: up to m + 2 inner products at once)
 
 // Header of every rank's window.  All words are written by remote GPUs with system-scope stores and read
 // locally with volatile loads (the local L2 is the point of coherence for this memory).
@@ -36,7 +37,7 @@ struct PeerHeader {
   unsigned long long halo_flag[FB_MAX_PEERS];  // [sender]  : epoch of the sender's last completed push into this window
   unsigned long long halo_ack[FB_MAX_PEERS];   // [receiver]: epoch of my last push that this receiver has consumed
   unsigned long long ar_flag[2][FB_MAX_PEERS];  // [parity][rank]
-  double ar_data[2][FB_MAX_PEERS][8];
+  double ar_data[2][FB_MAX_PEERS][FB_AR_MAX];
   unsigned long long gather_flag[FB_MAX_PEERS];  // [sender]: epoch of the sender's last completed fb_peer_vec_gather
 };
 static_assert(sizeof(PeerHeader) <= FB_WIN_HEADER, "window header too large");
@@ -375,7 +376,7 @@ void fb_allreduce_slots(fb_ctx *ctx, int slot0, int count) {
   if (!fb_is_distributed(ctx)) return;
   fb_comm *c = ctx->comm;
   double *p = ctx->dev->red + slot0;
-  if (c->p2p && count <= 8) {
+  if (c->p2p && count <= FB_AR_MAX) {
     ++c->ar_epoch;
     k_peer_allreduce<<<1, 32, 0, ctx->dev->stream>>>(peer_ptrs(c), c->rank, c->nranks, c->ar_epoch, ctx->dev->red, slot0, count);
     ctx->launches++;
