@@ -260,10 +260,12 @@ def pinned_empty(ctx, n):
     return arr
 
 
-def state_array(ctx, n, threshold=1 << 16):
-    """Zero-initialised dof array: pinned when a device is present and the array is large."""
+def state_array(ctx, n, threshold=1 << 16, zero=True):
+    """Dof array: pinned when a device is present and the array is large.  zero=False skips the fill for arrays
+    the library overwrites completely (the outputs of a step: an 80 MB memset per step at 10 M dofs otherwise)."""
     if n >= threshold and has_device():
         a = pinned_empty(ctx, n)
-        a[:] = 0.0
+        if zero:
+            a[:] = 0.0
         return a
-    return np.zeros(n)
+    return np.zeros(n) if zero else np.empty(n)

@@ -140,8 +140,8 @@ def _step(dt, u, p0, u_bcs, p_bcs, rho, mu, time_step_method, f, rotational_form
     ud, uv = collect_bcs(u_bcs, W)
     pd_, pv = collect_bcs(p_bcs, P)
     ctx = W.mesh().ctx
-    u1 = Function(W, _lib.state_array(ctx, W.dim()))
-    p1 = Function(P, _lib.state_array(ctx, P.dim()))
+    u1 = Function(W, _lib.state_array(ctx, W.dim(), zero=False))  # fb_ns_step writes every entry
+    p1 = Function(P, _lib.state_array(ctx, P.dim(), zero=False))
     flags = (_lib.ROTATIONAL if rotational_form else 0) | (_lib.CHORIN if chorin else 0)
     stats = _lib.NSStats()
 

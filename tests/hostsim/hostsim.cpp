@@ -7,6 +7,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../flow_b200/csrc/fb_amg_host.h"
 #include "../../flow_b200/csrc/fb_element.cuh"
 
 namespace hq {
@@ -183,7 +184,106 @@ static void rhs(int64_t nc, const int *cell_nodes, const double *xyz, double dt,
   }
 }
 
+// ---- host V-cycle + PCG on the hierarchy built by fb_amg_host::build_hierarchy (the set-up code the library
+// uploads to the GPU); mirrors amg_cycle / krylov_pcg_single_reduction of the CUDA path operation by operation
+namespace {
+using fb_amg_host::HostCsr;
+using fb_amg_host::HostLevel;
+
+void csr_mv(const HostCsr &M, const std::vector<double> &x, std::vector<double> &y) {
+  y.assign(M.nrows, 0.0);
+  for (int i = 0; i < M.nrows; ++i) {
+    double s = 0.0;
+    for (int k = M.ptr[i]; k < M.ptr[i + 1]; ++k) s += M.val[k] * x[M.col[k]];
+    y[i] = s;
+  }
+}
+
+void vcycle(const std::vector<HostLevel> &lv, size_t l, const std::vector<double> &b, std::vector<double> &x) {
+  const HostLevel &L = lv[l];
+  const int n = L.n;
+  x.assign(n, 0.0);
+  if (l + 1 == lv.size()) {
+    if (!L.Ainv.empty()) {
+      for (int i = 0; i < n; ++i) {
+        double s = 0.0;
+        for (int k = 0; k < n; ++k) s += L.Ainv[(size_t)i * n + k] * b[k];
+        x[i] = s;
+      }
+    } else {  // a single level (or a stalled coarsening): damped Jacobi sweeps
+      std::vector<double> ax;
+      for (int i = 0; i < n; ++i) x[i] = L.omega * L.dinv[i] * b[i];
+      for (int sweep = 0; sweep < (lv.size() == 1 ? 1 : 4); ++sweep) {
+        csr_mv(L.A, x, ax);
+        for (int i = 0; i < n; ++i) x[i] += L.omega * L.dinv[i] * (b[i] - ax[i]);
+      }
+    }
+    return;
+  }
+  std::vector<double> ax, r(n), bc, xc, px;
+  for (int i = 0; i < n; ++i) x[i] = L.omega * L.dinv[i] * b[i];  // pre-smooth from zero
+  csr_mv(L.A, x, ax);
+  for (int i = 0; i < n; ++i) r[i] = b[i] - ax[i];
+  csr_mv(L.R, r, bc);
+  vcycle(lv, l + 1, bc, xc);
+  csr_mv(L.P, xc, px);
+  for (int i = 0; i < n; ++i) x[i] += px[i];
+  csr_mv(L.A, x, ax);
+  for (int i = 0; i < n; ++i) x[i] += L.omega * L.dinv[i] * (b[i] - ax[i]);  // post-smooth
+}
+}  // namespace
+
 extern "C" {
+// PCG with the AMG V-cycle, PETSc's default test ||M^-1 r|| <= rtol ||M^-1 b||.  Returns the iteration count
+// (-1: not converged); levels/sizes/complexity/singular describe the hierarchy.
+int hs_amg_pcg(int n, const int *rowptr, const int *col, const double *val, const double *b, double *x, double rtol,
+               int maxit, int *levels, int *sizes, double *complexity, int *singular, int *has_dense) {
+  std::vector<HostLevel> lv;
+  bool sing = false;
+  double cx = 1.0;
+  fb_amg_host::build_hierarchy(n, rowptr, col, val, lv, sing, cx);
+  *levels = (int)lv.size();
+  for (size_t l = 0; l < lv.size() && l < 12; ++l) sizes[l] = lv[l].n;
+  *complexity = cx;
+  *singular = sing ? 1 : 0;
+  *has_dense = lv.back().Ainv.empty() ? 0 : 1;
+  std::vector<double> r(b, b + n), z, p, Ap, xs(n, 0.0);
+  vcycle(lv, 0, r, z);
+  p = z;
+  double rz = 0.0, zz0 = 0.0;
+  for (int i = 0; i < n; ++i) {
+    rz += r[i] * z[i];
+    zz0 += z[i] * z[i];
+  }
+  int it = 0;
+  for (; it < maxit; ++it) {
+    csr_mv(lv[0].A, p, Ap);
+    double pAp = 0.0;
+    for (int i = 0; i < n; ++i) pAp += p[i] * Ap[i];
+    if (!(pAp > 0.0)) break;
+    const double alpha = rz / pAp;
+    for (int i = 0; i < n; ++i) {
+      xs[i] += alpha * p[i];
+      r[i] -= alpha * Ap[i];
+    }
+    vcycle(lv, 0, r, z);
+    double rz2 = 0.0, zz = 0.0;
+    for (int i = 0; i < n; ++i) {
+      rz2 += r[i] * z[i];
+      zz += z[i] * z[i];
+    }
+    if (zz <= rtol * rtol * zz0) {
+      ++it;
+      for (int i = 0; i < n; ++i) x[i] = xs[i];
+      return it;
+    }
+    const double beta = rz2 / rz;
+    rz = rz2;
+    for (int i = 0; i < n; ++i) p[i] = z[i] + beta * p[i];
+  }
+  for (int i = 0; i < n; ++i) x[i] = xs[i];
+  return -1;
+}
 void hs_set_closed_form(int on) { g_closed_form = on; }
 double hs_supg_tau(const double *X, const double *v, double eps, int p) { return fb_supg_tau(X, v, eps, p); }
 int hs_momentum(int dim, int64_t nc, const int *cell_nodes, const double *xyz, int64_t nbf, const int *bf_cell,

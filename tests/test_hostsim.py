@@ -72,3 +72,52 @@ def test_supg_tau_device_routine(hostsim):
         got = np.array([[hostsim.hs_supg_tau(_pd(X[c]), _pd(np.ascontiguousarray(V[c, v])), C.c_double(eps), 2) for v in range(3)]
                         for c in range(om.nc)])
         assert np.allclose(got, ref, rtol=1e-12, atol=1e-300)
+
+
+@pytest.mark.parametrize("variant", ["neumann", "dirichlet"])
+@pytest.mark.parametrize("meshname", ["cube14", "square70"])
+def test_amg_hierarchy_and_pcg(hostsim, variant, meshname):
+    """Host set-up of the smoothed-aggregation AMG (flow_b200/csrc/fb_amg_host.h, the code whose output the library
+    uploads) driven by a host V-cycle + PCG: hierarchy statistics, mesh-independent iteration counts, and the solution
+    of the pressure Poisson problem of pressure_correction.py:317-339 (Dirichlet) / :340-432 (pure Neumann, singular,
+    consistent right-hand side) against scipy's direct solve."""
+    import scipy.sparse.linalg as sla
+
+    if meshname == "cube14":
+        om = fem.Mesh(*fem.unit_cube_mesh(14, 14, 14))
+    else:
+        om = fem.Mesh(*fem.unit_square_mesh(70, 70, "right"))
+    P = fem.Space(om, 1, 1)
+    A = forms.stiffness_matrix(P).tocsr()
+    A.sort_indices()
+    n = A.shape[0]
+    X = P.node_coords
+    rng = np.random.default_rng(1)
+    b = rng.standard_normal(n)
+    if variant == "neumann":
+        b -= b.mean()  # consistent: b orthogonal to the constants
+    else:
+        bd = np.nonzero(X[:, 0] > 1.0 - 1e-12)[0]
+        A, b = forms.apply_bc_symmetric(A, b, bd, np.zeros(bd.size))
+        A = A.tocsr()
+        A.sort_indices()
+    rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), np.ascontiguousarray(A.data)
+    x = np.zeros(n)
+    lev, cx, sing, dense = C.c_int(), C.c_double(), C.c_int(), C.c_int()
+    sizes = (C.c_int * 12)()
+    its = hostsim.hs_amg_pcg(n, _pi(rp), _pi(ci), _pd(va), _pd(b), _pd(x), C.c_double(1e-10), 200, C.byref(lev), sizes,
+                             C.byref(cx), C.byref(sing), C.byref(dense))
+    sz = list(sizes)[:lev.value]
+    assert lev.value >= 2 and sz[0] == n and sz[-1] <= 400 and dense.value == 1
+    assert all(a > 2 * c for a, c in zip(sz, sz[1:]))  # every level coarsens by more than 2x
+    assert 1.0 < cx.value < 2.6
+    assert sing.value == (1 if variant == "neumann" else 0)
+    assert 0 < its < 40, its  # Jacobi-CG needs several hundred iterations on these meshes
+    if variant == "neumann":
+        ref = sla.lsqr(A, b, atol=1e-14, btol=1e-14, iter_lim=20000)[0]
+        d = (x - x.mean()) - (ref - ref.mean())
+        assert np.linalg.norm(d) / np.linalg.norm(ref - ref.mean()) < 1e-6
+        assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) < 1e-8
+    else:
+        ref = sla.spsolve(A.tocsc(), b)
+        assert np.linalg.norm(x - ref) / np.linalg.norm(ref) < 1e-8
