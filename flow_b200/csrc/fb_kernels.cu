@@ -648,9 +648,6 @@ static void launch_bspmv_u(fb_ctx *ctx, const LinOp &A, const double *x, double 
 #define FB_BSU(DOT)                                                                                                    \
   FB_LAUNCH(ctx, (k_bspmv_u<D, T, DOT, U, MINB>), g, block, 0, A.nrows, A.rowptr, A.col, A.val, x, y, w, dv->partials, \
             dv->counter, dv->red, slot, flag)
-#define FB_BSUC(DOT)                                                                                                    \
-  FB_LAUNCH(ctx, (k_bspmv_u<D, T, DOT, U, MINB, double, 1>), g, block, 0, A.nrows, A.rowptr, A.col, A.val, x, y, w,      \
-            dv->partials, dv->counter, dv->red, slot, flag)
 #define FB_BSU32(DOT)                                                                                                   \
   FB_LAUNCH(ctx, (k_bspmv_u<D, T, DOT, U, MINB, float>), g, block, 0, A.nrows, A.rowptr, A.col, A.val32, x, y, w,        \
             dv->partials, dv->counter, dv->red, slot, flag)
@@ -660,18 +657,10 @@ static void launch_bspmv_u(fb_ctx *ctx, const LinOp &A, const double *x, double 
     else FB_BSU32(2);
     return;
   }
-  static const int chunked = getenv("FB_BSPMV_CHUNK") ? atoi(getenv("FB_BSPMV_CHUNK")) : 0;
-  if (chunked) {
-    if (dot_mode == 0) FB_BSUC(0);
-    else if (dot_mode == 1) FB_BSUC(1);
-    else FB_BSUC(2);
-    return;
-  }
   if (dot_mode == 0) FB_BSU(0);
   else if (dot_mode == 1) FB_BSU(1);
   else FB_BSU(2);
 #undef FB_BSU
-#undef FB_BSUC
 #undef FB_BSU32
 }
 
@@ -741,26 +730,12 @@ static void spmv_local(fb_ctx *ctx, const LinOp &A, const double *x, double *y, 
                        const int *flag) {
   if (A.block == 2) return launch_bspmv_u<2, 8, 4, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
   if (A.block == 3) {
-    // tuning knob (kernel variant); measured on B200 at n = 74 (profiles/r1_spmv_variants.txt):
-    // plain 1.76 ms, T=32/U=2 1.37 ms, T=16/U=3 1.28 ms, T=16/U=4 1.25 ms (= 8.2 GB DRAM traffic at 6.5 TB/s)
+    // Variants measured on B200 at n = 74 (profiles/r1_spmv_variants.txt): one chunk per lane, 32 lanes per row 1.76 ms;
+    // T=32/U=2 1.37 ms; T=16/U=3 1.28 ms; T=16/U=4 1.25 ms (7.9 GB of DRAM traffic at 6.4 TB/s); T=16/U=6 1.25 ms;
+    // T=8/U=4 1.44 ms; contiguous row ranges per block 1.96 ms.  FB_BSPMV_V=0 selects the first version.
     static const int V = getenv("FB_BSPMV_V") ? atoi(getenv("FB_BSPMV_V")) : 9;
-    switch (V) {
-      case 1: return launch_bspmv_u<3, 32, 2, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-      case 2: return launch_bspmv_u<3, 32, 3, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-      case 3: return launch_bspmv_u<3, 32, 2, 6>(ctx, A, x, y, dot_mode, w, slot, flag);
-      case 4: return launch_bspmv_u<3, 32, 3, 5>(ctx, A, x, y, dot_mode, w, slot, flag);
-      case 5: return launch_bspmv_u<3, 32, 1, 8>(ctx, A, x, y, dot_mode, w, slot, flag);
-      case 6: return launch_bspmv_u<3, 16, 3, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-      case 7: return launch_bspmv_u<3, 32, 4, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-      case 8: return launch_bspmv_u<3, 16, 2, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-      case 9: return launch_bspmv_u<3, 16, 4, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-      case 10: return launch_bspmv_u<3, 16, 6, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-      case 11: return launch_bspmv_u<3, 8, 4, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-      case 12: return launch_bspmv_u<3, 8, 6, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-      case 13: return launch_bspmv_u<3, 16, 3, 5>(ctx, A, x, y, dot_mode, w, slot, flag);
-      case 14: return launch_bspmv_u<3, 8, 8, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-      default: return launch_bspmv<3, 32>(ctx, A, x, y, dot_mode, w, slot, flag);
-    }
+    if (V == 0) return launch_bspmv<3, 32>(ctx, A, x, y, dot_mode, w, slot, flag);
+    return launch_bspmv_u<3, 16, 4, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
   }
   // scalar: pick lanes per row from the average row length
   switch (A.ncomp) {
@@ -769,26 +744,12 @@ static void spmv_local(fb_ctx *ctx, const LinOp &A, const double *x, double *y, 
     case 2:
       return launch_spmm<2, 8>(ctx, A, x, y, dot_mode, w, slot, flag);
     case 3: {
-      // measured on B200 at n = 74 (3.3 M rows, 29 entries per row): T=16 0.559 ms, T=8/U=2 0.423 ms, T=4/U=8 0.474 ms;
-      // contiguous row ranges per block and paired 16-byte gathers are slower (profiles/r1_spmm3_variants.txt)
+      // measured on B200 at n = 74 (3.3 M rows, 29 entries per row; profiles/r1_spmm3_variants.txt): T=16 0.559 ms,
+      // T=8/U=2 0.423 ms, T=8/U=4 0.424 ms, T=4/U=8 0.474 ms; contiguous row ranges per block, paired 16-byte and
+      // padded 32-byte gathers are all slower.  FB_SPMM_V=0 selects the first version.
       static const int V = getenv("FB_SPMM_V") ? atoi(getenv("FB_SPMM_V")) : 7;
-      switch (V) {
-        case 1: return launch_spmm_u<3, 16, 2, 0>(ctx, A, x, y, dot_mode, w, slot, flag);
-        case 2: return launch_spmm_u<3, 16, 2, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-        case 3: return launch_spmm_u<3, 8, 4, 0>(ctx, A, x, y, dot_mode, w, slot, flag);
-        case 4: return launch_spmm_u<3, 8, 4, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-        case 5: return launch_spmm_u<3, 16, 1, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-        case 6: return launch_spmm_u<3, 32, 1, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-        case 7: return launch_spmm_u<3, 8, 2, 0>(ctx, A, x, y, dot_mode, w, slot, flag);
-        case 8: return launch_spmm_u<3, 4, 8, 0>(ctx, A, x, y, dot_mode, w, slot, flag);
-        case 9: return launch_spmm_u<3, 8, 4, 0, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-        case 10: return launch_spmm_u<3, 16, 2, 0, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-        case 11: return launch_spmm_u<3, 4, 8, 0, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-        case 12: return launch_spmm_u<3, 4, 4, 0, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-        case 13: return launch_spmm_u<3, 8, 3, 0, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
-        case 14: return launch_spmm_u<3, 8, 1, 0>(ctx, A, x, y, dot_mode, w, slot, flag);
-        default: return launch_spmm<3, 16>(ctx, A, x, y, dot_mode, w, slot, flag);
-      }
+      if (V == 0) return launch_spmm<3, 16>(ctx, A, x, y, dot_mode, w, slot, flag);
+      return launch_spmm_u<3, 8, 2, 0>(ctx, A, x, y, dot_mode, w, slot, flag);
     }
     default:
       throw fb_cuda_error(FB_EINVAL, "spmv: ncomp must be 1..3");
