@@ -101,6 +101,12 @@ def oracle_cavity_step_time(n, steps, warmup=0):
     return float(np.mean(times)), cv.ndofs, cv.threads(), info
 
 
+def workload_string(n):
+    nu, npr = dof_counts(n)
+    return ("3D lid-driven cavity, P2/P1 IPCS backward Euler, UnitCubeMesh(%d): %d dofs (%d u + %d p), "
+            "Re=100, dt=1e-2, tol=1e-10" % (n, nu + npr, nu, npr))
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -116,7 +122,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3D lid-driven cavity P2/P1 IPCS, UnitCubeMesh(%d), %d dofs" % (n_full, nd_full)},
+        "config": {"workload": workload_string(n_full),
+                   "parallelism": "host CPU, %d threads (rank 0 only)" % threads},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -349,8 +356,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {
-                "workload": "3D lid-driven cavity, P2/P1 IPCS backward Euler, UnitCubeMesh(%d): %d dofs (%d u + %d p), "
-                            "Re=100, dt=1e-2, tol=1e-10" % (n, nu_global + np_global, nu_global, np_global),
+                "workload": workload_string(n),
                 "parallelism": "single GPU" if world == 1 else "mesh partitioned over %d GPUs (RCB, 1 ghost-cell layer, halo exchange + one all-reduce per "
                                "Krylov reduction over %s); rank 0 holds %d local dofs"
                                % (world, "NVLink peer-memory windows (own kernels)" if p2p else "NCCL", nu + npp),
