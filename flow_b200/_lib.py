@@ -57,7 +57,7 @@ class NSOpts(C.Structure):
         ("jacobian_fp32", C.c_int),
         ("extrapolate_guess", C.c_int),
         ("momentum_inner_its", C.c_int),
-        ("reserved", C.c_int * 1),
+        ("inner_fp32", C.c_int),
     ]
 
 

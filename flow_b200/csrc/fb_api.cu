@@ -420,6 +420,8 @@ struct fb_ns {
   uint64_t S_bc_hash = 0;
   FgmresWork fw;
   KrylovWork kw_inner;
+  DBuf<float> Sval32, dinv_S32;  // fp32 copies for opts.inner_fp32
+  Inner32 in32;
   // extrapolated Newton start: u0 of the previous call, its dt and the |F| that call started from
   DBuf<double> uprev;
   bool have_prev = false;
@@ -536,6 +538,7 @@ int fb_ns_opts_default(fb_ns_opts *o) {
   o->jacobian_fp32 = 0;
   o->extrapolate_guess = 0;
   o->momentum_inner_its = 4;
+  o->inner_fp32 = 0;
   return FB_OK;
 }
 
@@ -869,6 +872,12 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
         jacobi_setup_scalar(ctx, *ns->W, ns->Sval.p, D, n_ubc > 0 ? ns->mask_u.p : nullptr, ns->dinv_S.p);
         ns->S_key = c2;
         ns->S_bc_hash = bc_hash;
+        if (o.inner_fp32 && !fb_is_distributed(ctx)) {
+          ns->Sval32.alloc((size_t)ns->W->nnz);
+          ns->dinv_S32.alloc((size_t)nu);
+          vec_to_float(ctx, ns->Sval32.p, ns->Sval.p, ns->W->nnz);
+          vec_to_float(ctx, ns->dinv_S32.p, ns->dinv_S.p, nu);
+        }
       } else {
         mask_build(ctx, ns->mask_u.p, nu, ns->ubc_dofs.p, n_ubc);  // the correction solve of the last step rebuilt it alike
       }
@@ -890,6 +899,30 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
         *ii = n_it;
         return st_ == FB_ENAN ? FB_ENAN : FB_OK;  // "not converged" is the expected outcome of a fixed iteration count
       };
+      struct Inner32Call {
+        fb_ctx *ctx;
+        Inner32 *in;
+      } call32{ctx, &ns->in32};
+      if (o.inner_fp32 && !fb_is_distributed(ctx) && ns->Sval32.p) {
+        // same preconditioner with S, the CG vectors and the products in fp32 (reductions fp64); the outer FGMRES
+        // and everything that leaves it stay fp64
+        Inner32 &q = ns->in32;
+        q.nrows = ns->W->n_owned;
+        q.ncomp = D;
+        q.its = inner.its;
+        q.rowptr = ns->W->rowptr.p;
+        q.col = ns->W->col.p;
+        q.val = ns->Sval32.p;
+        q.dinv = ns->dinv_S32.p;
+        q.mask = n_ubc > 0 ? ns->mask_u.p : nullptr;
+        pc.self = &call32;
+        pc.apply = [](void *self, const double *v, double *z, int *ii) -> int {
+          Inner32Call *c32 = static_cast<Inner32Call *>(self);
+          inner32_apply(c32->ctx, *c32->in, v, z);
+          *ii = c32->in->its;
+          return FB_OK;
+        };
+      }
       int inner_its = 0;
       status = krylov_fgmres(ctx, Jop, pc, ns->F.p, ns->delta.p, atol_inner, o.momentum_maxit,
                              std::min(o.gmres_restart > 0 ? o.gmres_restart : 20, 20), ns->fw, &its, &inner_its);

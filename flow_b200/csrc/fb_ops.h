@@ -172,3 +172,16 @@ struct FgmresWork {
 };
 int krylov_fgmres(fb_ctx *ctx, const LinOp &A, const FgmresPrecond &pc, const double *b, double *x, double atol, int maxit,
                   int m, FgmresWork &fw, int *iters, int *inner_iters);
+
+// fp32 inner solver of the momentum preconditioner (fb_inner32.cu)
+struct Inner32 {
+  int64_t nrows = 0;  // node rows
+  int ncomp = 3;
+  int its = 4;
+  const int *rowptr = nullptr, *col = nullptr;
+  const float *val = nullptr, *dinv = nullptr;
+  const uint8_t *mask = nullptr;
+  DBuf<float> r, z, p, Ap, x;
+  void ensure(int64_t n);
+};
+void inner32_apply(fb_ctx *ctx, Inner32 &in, const double *v, double *z_out);

@@ -174,7 +174,9 @@ typedef struct fb_ns_opts {
                             has a residual below twice what the previous step started from (smooth time loops; no gain
                             on the impulsively started cavity of the benchmark) */
   int momentum_inner_its; /* CG iterations per preconditioner application of the FB_GMRES momentum solver (default 4) */
-  int reserved[1];
+  int inner_fp32;        /* 0 (default).  1: the CG iterations of the FB_GMRES preconditioner run in fp32 (operator,
+                            vectors, products; reductions fp64).  The flexible outer iteration, its residual test and all
+                            results stay fp64: a looser preconditioner costs outer iterations, not accuracy.  1 GPU only. */
 } fb_ns_opts;
 
 typedef struct fb_ns_stats {

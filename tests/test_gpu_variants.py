@@ -24,6 +24,7 @@ VARIANTS = {
     "bicgstab": dict(momentum_solver="bicgstab"),
     "fgmres": dict(momentum_solver="fgmres"),
     "fgmres_inner8": dict(momentum_solver="fgmres", momentum_inner_its=8),
+    "fgmres_inner_fp32": dict(momentum_solver="fgmres", inner_fp32=1),
 }
 
 
