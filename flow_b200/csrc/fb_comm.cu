@@ -393,12 +393,21 @@ struct fb_peer_vec {
   int rank = 0, nranks = 1;
 };
 
+void fb_peer_vec_destroy(fb_peer_vec *v);
+
 // collective; returns null if the peer-memory transport is not active
 fb_peer_vec *fb_peer_vec_create(fb_ctx *ctx, int64_t n_global) {
   if (!fb_is_distributed(ctx) || !ctx->comm->p2p) return nullptr;
   fb_comm *c = ctx->comm;
   cudaStream_t st = ctx->dev->stream;
-  fb_peer_vec *v = new fb_peer_vec();
+  // owned by a guard until every buffer is mapped: a CUDA / NCCL error below must not leak the allocations
+  struct Guard {
+    fb_peer_vec *v;
+    ~Guard() {
+      if (v) fb_peer_vec_destroy(v);
+    }
+  } guard{new fb_peer_vec()};
+  fb_peer_vec *v = guard.v;
   v->n = n_global;
   v->rank = c->rank;
   v->nranks = c->nranks;
@@ -427,6 +436,7 @@ fb_peer_vec *fb_peer_vec_create(fb_ctx *ctx, int64_t n_global) {
       v->buf[par][r] = static_cast<char *>(q);
     }
   }
+  guard.v = nullptr;
   return v;
 }
 

@@ -1589,7 +1589,6 @@ __global__ void k_heat(int64_t nc, const int *__restrict__ cell_nodes, const int
     const int64_t c = t / (NL * NL);
     const int r = (int)(t - c * NL * NL);
     const int a = r / NL, b = r - a * NL;
-    const int *cn = cell_nodes + c * NL;
     double glam[D + 1][D], vol;
     cell_geometry<D>(cells + c * (D + 1), xyz, glam, vol);
     double e = 0.0;
