@@ -49,7 +49,7 @@ enum fb_scheme { FB_FORWARD_EULER = 0, FB_BACKWARD_EULER = 1, FB_CRANK_NICOLSON 
 enum fb_flags { FB_DEVICE_PTRS = 1, FB_ROTATIONAL = 2, FB_CHORIN = 4 };
 enum fb_forcing { FB_F_NONE = 0, FB_F_CONSTANT = 1, FB_F_NODAL = 2, FB_F_LOAD = 3 };
 enum fb_krylov { FB_BICGSTAB = 0, FB_GMRES = 1, FB_CG = 2 };
-enum fb_precond { FB_JACOBI = 0, FB_BLOCK_JACOBI = 1, FB_CHEBYSHEV = 2, FB_AMG = 3 };
+enum fb_precond { FB_JACOBI = 0, FB_BLOCK_JACOBI = 1, FB_CHEBYSHEV = 2 /* reserved: not implemented, acts as FB_JACOBI */, FB_AMG = 3 };
 
 /* ---- context ---------------------------------------------------------- */
 int fb_version(void);
@@ -157,7 +157,7 @@ typedef struct fb_ns_opts {
   int correction_maxit;  /* default 1000 */
   int gmres_restart;     /* 30 (PETSc default) */
   int check_every;       /* Krylov iterations enqueued between host convergence checks */
-  int chebyshev_degree;  /* default 4 */
+  int chebyshev_degree;  /* reserved (no Chebyshev preconditioner yet); ignored */
   int jacobian_reuse;    /* 1 (default): keep the step's first Jacobian for later Newton iterations while the
                             residual contracts by > 10x per iteration (chord); 0: re-assemble every iteration */
   int adaptive_forcing;  /* 1 (default): the first linear solve of a step stops at the nonlinear remainder observed
