@@ -145,7 +145,7 @@ typedef struct fb_ns_opts {
   int momentum_solver;   /* FB_BICGSTAB: block-Jacobi BiCGStab on the Jacobian; FB_GMRES: flexible GMRES whose
                             preconditioner is momentum_inner_its CG iterations on the constant scalar operator
                             M + theta dt nu K per component (the Jacobian is streamed ~5x less often) */
-  int momentum_precond;  /* FB_JACOBI or FB_BLOCK_JACOBI (default) */
+  int momentum_precond;  /* preconditioner of the FB_BICGSTAB solver: FB_JACOBI or FB_BLOCK_JACOBI (default) */
   int pressure_precond;  /* FB_AMG (default; smoothed aggregation, V(1,1), dense pseudo-inverse on the coarsest level;
                             replaces hypre BoomerAMG of pressure_correction.py:331,:414-419; systems of fewer than
                             4096 unknowns fall back to Jacobi) or FB_JACOBI */
@@ -155,7 +155,7 @@ typedef struct fb_ns_opts {
   int momentum_maxit;    /* 1000 (commented-out block, pressure_correction.py:249) */
   int pressure_maxit;    /* Krylov cap for the Poisson solve; default 20000 (Jacobi needs more than AMG's 1000) */
   int correction_maxit;  /* default 1000 */
-  int gmres_restart;     /* 30 (PETSc default) */
+  int gmres_restart;     /* restart length of the FB_GMRES solver: default 30 (PETSc default), at most 20 vectors are kept */
   int check_every;       /* Krylov iterations enqueued between host convergence checks */
   int chebyshev_degree;  /* reserved (no Chebyshev preconditioner yet); ignored */
   int jacobian_reuse;    /* 1 (default): keep the step's first Jacobian for later Newton iterations while the
