@@ -141,7 +141,10 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=32, help="cube size of the bounded CPU sample (32 -> 0.86 M dofs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-variants", action="store_true", help="skip the opt-in fp32-Jacobian variant")
+    ap.add_argument("--no-variants", action="store_true", help="skip the opt-in mixed-precision variants")
+    ap.add_argument("--node-order", default="canonical", choices=["canonical", "lexicographic"],
+                    help="experimental: number the nodes by coordinate for cache locality (single GPU; default: the canonical "
+                         "numbering of the oracle and the parity tests)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -177,6 +180,8 @@ def main():
     t_setup = time.perf_counter()
     n = args.n
     mesh = d.UnitCubeMesh(n, n, n)
+    if args.node_order != "canonical" and world == 1:
+        mesh.node_order = args.node_order
     nu_global, np_global = 3 * mesh.node_space(2).nnodes, mesh.node_space(1).nnodes
     if world > 1:
         # strong scaling: the SAME cavity, cells split by recursive coordinate bisection, one ghost-cell layer,
@@ -366,6 +371,7 @@ def main():
             "data": "synthetic",
             "config": {
                 "workload": workload_string(n),
+                "node_order": args.node_order if world == 1 else "canonical",
                 "parallelism": "single GPU" if world == 1 else "mesh partitioned over %d GPUs (RCB, 1 ghost-cell layer, halo exchange + one all-reduce per "
                                "Krylov reduction over %s); rank 0 holds %d local dofs"
                                % (world, "NVLink peer-memory windows (own kernels)" if p2p else "NCCL", nu + npp),

@@ -69,6 +69,12 @@ class Mesh(object):
         self._spaces = {}
         self._vol = None
         self.partition = None  # set by flow_b200.parallel.distributed_mesh
+        # None: canonical node numbering (vertices, then edges in lexicographic order -- the numbering the oracle and
+        # the parity tests use).  "lexicographic": nodes numbered by coordinate (z, then y, then x): the columns of a
+        # matrix row and the rows a warp works on then sit in neighbouring cache lines (experimental, single GPU;
+        # vectors are in that numbering, like the rank-local vectors of a partitioned run).  Set before the first
+        # FunctionSpace is created on the mesh.
+        self.node_order = None
 
     def coordinates(self):
         return self._points
@@ -152,6 +158,9 @@ class _NodeSpace(object):
         self.mesh, self.degree = mesh, degree
         self._vec_handles = {}
         self.plan = mesh.partition.plans[degree] if mesh.partition is not None else None
+        self.perm = None  # canonical -> this numbering, when mesh.node_order asks for one (single GPU)
+        if self.plan is None and getattr(mesh, "node_order", None):
+            self.perm = self._coordinate_order(mesh.node_order)
         self.handle = self._create(1)
         h = self.handle
         nn, nd, nl = _lib.i64(), _lib.i64(), C.c_int()
@@ -168,9 +177,31 @@ class _NodeSpace(object):
         self.on_boundary = np.ctypeslib.as_array(b, shape=(self.nnodes,)).astype(bool)
         self._mass = None
 
+    def _coordinate_order(self, kind):
+        """perm[canonical node] = new index for a numbering by coordinate."""
+        if kind != "lexicographic":
+            raise ValueError("unknown node order %r" % (kind,))
+        mesh = self.mesh
+        h = _lib.vp()
+        _lib.check(lib.fb_space_create(mesh.handle, self.degree, 1, C.byref(h)), mesh.ctx, "fb_space_create")
+        nn, nd, nl = _lib.i64(), _lib.i64(), C.c_int()
+        lib.fb_space_info(h, C.byref(nn), C.byref(nd), C.byref(nl))
+        q = _lib.pd()
+        lib.fb_space_node_coords(h, C.byref(q))
+        X = np.ctypeslib.as_array(q, shape=(nn.value, mesh.dim)).copy()
+        lib.fb_space_destroy(h)
+        order = np.lexsort(tuple(X[:, k] for k in range(mesh.dim)))  # last key (highest coordinate index) is the primary one
+        perm = np.empty(nn.value, dtype=np.int32)
+        perm[order] = np.arange(nn.value, dtype=np.int32)
+        return perm
+
     def _create(self, ncomp):
         h = _lib.vp()
         mesh, pl = self.mesh, self.plan
+        if pl is None and self.perm is not None:
+            _lib.check(lib.fb_space_create_numbered(mesh.handle, self.degree, ncomp, _lib.as_pi32(self.perm), self.perm.size,
+                                                    C.byref(h)), mesh.ctx, "fb_space_create_numbered")
+            return h
         if pl is None:
             _lib.check(lib.fb_space_create(mesh.handle, self.degree, ncomp, C.byref(h)), mesh.ctx, "fb_space_create")
             return h

@@ -138,3 +138,31 @@ def test_amg_hierarchy_and_dirichlet_variant(gpu_ctx):
     assert np.linalg.norm(ua - uj) / np.linalg.norm(uj) < 1e-9
     assert np.linalg.norm(pa - pj) / np.linalg.norm(pj) < 1e-8
     assert ia < 40 and ia < ij / 4, (ia, ij)
+
+
+def test_coordinate_node_order_same_solution(gpu_ctx):
+    """mesh.node_order = "lexicographic" (experimental locality numbering, tests/test_topology.py) changes the
+    numbering only: two IPCS steps give the canonical solution under the node permutation."""
+    from flow_b200 import dolfin as d
+    from flow_b200 import navier_stokes as nav
+
+    res = {}
+    for order in (None, "lexicographic"):
+        mesh = d.UnitCubeMesh(6, 5, 7)
+        mesh.node_order = order
+        W = d.VectorFunctionSpace(mesh, "CG", 2)
+        P = d.FunctionSpace(mesh, "CG", 1)
+        bcs = [d.DirichletBC(W, (0.0, 0.0, 0.0), "on_boundary"),
+               d.DirichletBC(W, d.Expression(("4*x[0]*(1-x[0])", "0.0", "0.0"), degree=2), lambda x, on: x[2] > 1 - 1e-12)]
+        f = d.Constant((0.0, 0.1, -1.0))
+        u, p = d.Function(W), d.Function(P)
+        for _ in range(2):
+            u, p = nav.IPCS().step(d.Constant(0.02), {0: u}, p, bcs, [], d.Constant(1.0), d.Constant(0.02), {0: f, 1: f},
+                                   verbose=False, tol=1e-11)
+        res[order] = (u._vec.copy(), p._vec.copy(), W.nodes.perm, P.nodes.perm)
+    ua, pa, _, _ = res[None]
+    ub, pb, permW, permP = res["lexicographic"]
+    assert permW is not None and permP is not None
+    assert np.linalg.norm(ub.reshape(-1, 3)[permW] - ua.reshape(-1, 3)) / np.linalg.norm(ua) < 1e-8
+    da = pa - pa.mean()
+    assert np.linalg.norm((pb - pb.mean())[permP] - da) / np.linalg.norm(da) < 1e-7

@@ -79,3 +79,34 @@ def test_unsorted_cells_are_canonicalised():
     shuffled = np.stack([rng.permutation(c) for c in cells])
     m = d.Mesh(pts, shuffled)
     assert np.array_equal(m.cells(), cells)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_coordinate_node_order_is_a_consistent_renumbering(dim):
+    """mesh.node_order = "lexicographic" (experimental locality numbering): dof map, coordinates, boundary flags and
+    sparsity pattern are those of the canonical space under one permutation."""
+    from flow_b200 import _lib
+    from flow_b200 import dolfin as d
+    from flow_b200._lib import lib
+
+    def pattern(ns):
+        nnz, ip, ix = _lib.i64(), _lib.pi64(), _lib.pi32()
+        lib.fb_space_pattern(ns.handle, C.byref(nnz), C.byref(ip), C.byref(ix))
+        indptr = np.ctypeslib.as_array(ip, shape=(ns.nnodes + 1,)).copy()
+        return indptr, np.ctypeslib.as_array(ix, shape=(nnz.value,)).copy()
+
+    make = (lambda: d.UnitSquareMesh(5, 4, "crossed")) if dim == 2 else (lambda: d.UnitCubeMesh(3, 2, 4))
+    m0, m1 = make(), make()
+    m1.node_order = "lexicographic"
+    for degree in (1, 2):
+        a, b = m0.node_space(degree), m1.node_space(degree)
+        perm = b.perm
+        assert a.perm is None and sorted(perm) == list(range(a.nnodes))
+        assert np.array_equal(b.cell_nodes, perm[a.cell_nodes])
+        assert np.array_equal(b.coords[perm], a.coords) and np.array_equal(b.on_boundary[perm], a.on_boundary)
+        keys = [tuple(x[::-1]) for x in b.coords]
+        assert keys == sorted(keys)  # numbered by (z, y, x)
+        ipa, ixa = pattern(a)
+        ipb, ixb = pattern(b)
+        for i in range(a.nnodes):
+            assert np.array_equal(np.sort(perm[ixa[ipa[i]:ipa[i + 1]]]), ixb[ipb[perm[i]]:ipb[perm[i] + 1]])
