@@ -58,6 +58,7 @@ class NSOpts(C.Structure):
         ("extrapolate_guess", C.c_int),
         ("momentum_inner_its", C.c_int),
         ("inner_fp32", C.c_int),
+        ("newton_overshoot", C.c_double),
     ]
 
 

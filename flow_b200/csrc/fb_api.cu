@@ -524,21 +524,22 @@ int fb_ns_opts_default(fb_ns_opts *o) {
   o->pressure_precond = FB_AMG;
   o->newton_maxit = 10;
   o->newton_atol = 1e-10;
-  o->momentum_rtol = 1e-12;
+  o->momentum_rtol = 1e-6;
   o->momentum_maxit = 1000;
   o->pressure_maxit = 20000;
   o->correction_maxit = 1000;
   o->gmres_restart = 30;
   o->check_every = 0;  // 0: automatic
   o->chebyshev_degree = 4;
-  o->jacobian_reuse = 1;
-  o->adaptive_forcing = 1;
-  o->jacobian_across_steps = 1;
+  o->jacobian_reuse = 0;
+  o->adaptive_forcing = 0;
+  o->jacobian_across_steps = 0;
   o->warm_start = 1;
   o->jacobian_fp32 = 0;
   o->extrapolate_guess = 0;
   o->momentum_inner_its = 4;
   o->inner_fp32 = 0;
+  o->newton_overshoot = 1e-3;
   return FB_OK;
 }
 
@@ -809,8 +810,26 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
   s.reserved[0] = r;  // reserved[k] = |F| after k Newton updates (first 8)
   const int mom_check = o.check_every > 0 ? o.check_every : 2;
   float ms;
-  while (!(r < o.newton_atol)) {
+  // Acceptance and linear tolerances.
+  //  * Default (jacobian_reuse = 0): the reference's Newton iteration itself (:224-254) -- Jacobian of the CURRENT iterate
+  //    at every iteration, stop at the FIRST iterate with |F|_2 < atol.  The reference solves each update exactly (LU);
+  //    its accepted iterate is whatever that exact update produces, anywhere between 1e-10 and 1e-17 (oracle traces:
+  //    9.8e-11 as well as 3e-17 occur), and |F|_2 is not mesh-normalised: an iterate at 9.8e-11 is 3e-8 relative away
+  //    from the root on a 130 k-dof mesh.  Agreement with the reference to 1e-8 therefore needs ITS iterates, not just
+  //    its test: every linear solve goes to max(overshoot * atol, momentum_rtol * |F|), i.e. far enough below the
+  //    nonlinear remainder that the Krylov update is the LU update to ~1e-10 relative.
+  //  * Chord variant (jacobian_reuse = 1): cheaper path to the ROOT of F1 -- a Jacobian kept across iterations and
+  //    steps, looser first solves; it runs to target = overshoot * atol so that the accepted iterate is at least as
+  //    close to the root as the reference's typical one.  An iterate below atol is accepted as soon as further
+  //    updates stop paying (rounding floor of F, iteration cap): the reference's criterion always holds.
+  const bool chord = o.jacobian_reuse != 0;
+  const double overshoot = (o.newton_overshoot > 0.0 && o.newton_overshoot <= 1.0) ? o.newton_overshoot : 1.0;
+  const double lin_floor = o.newton_atol * overshoot;
+  const double target = chord ? lin_floor : o.newton_atol;
+  double last_ratio = 0.0;
+  while (!(r < target)) {
     if (r != r) return fb_fail(ctx, FB_ENAN, "fb_ns_step: NaN in the momentum residual");
+    if (r < o.newton_atol && (newton >= o.newton_maxit || last_ratio > 0.5)) break;
     if (newton >= o.newton_maxit) {
       char buf[160];
       snprintf(buf, sizeof buf, "Newton solver did not converge in %d iterations (|F| = %.3e)", newton, r);
@@ -838,11 +857,11 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     FB_CUDA(cudaEventRecord(dv->ev[5], st));
     // Inner tolerance (inexact Newton): the first update cannot reduce |F| below the nonlinear remainder
     // c*|F| (c = contraction observed at the previous time step), so the first linear solve stops there.
-    double atol_inner = std::max(0.1 * o.newton_atol, o.momentum_rtol * r);
-    if (o.adaptive_forcing && ns->contraction > 0.0 && ns->contraction < 0.1) {
+    double atol_inner = std::max(chord ? 0.1 * target : lin_floor, o.momentum_rtol * r);
+    if (chord && o.adaptive_forcing && ns->contraction > 0.0 && ns->contraction < 0.1) {
       const double predicted = ns->contraction * r;  // |F| the update can reach at best
-      if (predicted < 0.5 * o.newton_atol)
-        atol_inner = std::max(atol_inner, 0.3 * o.newton_atol);  // expected to be the last iteration
+      if (predicted < 0.5 * target)
+        atol_inner = std::max(atol_inner, 0.3 * target);  // expected to be the last iteration
       else
         atol_inner = std::max(atol_inner, 0.5 * predicted);
     }
@@ -946,6 +965,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     const double ratio = r > 0.0 ? r_new / r : 0.0;
     if (newton == 1) ns->contraction = ratio;
     reuse_ok = ratio < 0.1;
+    last_ratio = ratio;
     r = r_new;
     if (newton < 5) s.reserved[newton] = r;
     FB_CUDA(cudaEventElapsedTime(&ms, dv->ev[4], dv->ev[5]));

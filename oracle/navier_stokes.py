@@ -48,8 +48,12 @@ class Stepper:
                 self.W, self.P, x, u0, p0, load, dt, rho, mu, theta, want_J=want_J
             )
 
-        newton = solvers.newton if self.linear == "lu" else solvers.newton_krylov
-        ui, its = newton(rj, u0, dofs, vals, atol=tol, maxit=10, report=self.info)
+        if self.linear == "tight-krylov":  # the LU iterates, computed without the (infeasible) 3D LU fill
+            ui, its = solvers.newton(rj, u0, dofs, vals, atol=tol, maxit=10, report=self.info,
+                                     linear_solve=solvers.tight_krylov_solve)
+        else:
+            newton = solvers.newton if self.linear == "lu" else solvers.newton_krylov
+            ui, its = newton(rj, u0, dofs, vals, atol=tol, maxit=10, report=self.info)
         self.info["newton_its"] = its
         return ui
 

@@ -13,18 +13,22 @@ from oracle import navier_stokes as ons
 
 pytestmark = pytest.mark.gpu
 
+CHORD = dict(jacobian_reuse=1, jacobian_across_steps=1, adaptive_forcing=1)  # the round-1 default path, now opt-in
+
 VARIANTS = {
     "defaults": {},
-    "plain": dict(pressure_precond="jacobi", warm_start=0, jacobian_across_steps=0, jacobian_reuse=0, adaptive_forcing=0,
-                  extrapolate_guess=0),
+    "jacobi_cold": dict(pressure_precond="jacobi", warm_start=0),
     "jacobi_warm": dict(pressure_precond="jacobi", warm_start=1),
-    "amg_cold": dict(pressure_precond="amg", warm_start=0, jacobian_across_steps=0),
+    "amg_cold": dict(pressure_precond="amg", warm_start=0),
     "fp32_jacobian": dict(jacobian_fp32=1),
-    "extrapolated_start": dict(extrapolate_guess=1),
     "bicgstab": dict(momentum_solver="bicgstab"),
-    "fgmres": dict(momentum_solver="fgmres"),
     "fgmres_inner8": dict(momentum_solver="fgmres", momentum_inner_its=8),
     "fgmres_inner_fp32": dict(momentum_solver="fgmres", inner_fp32=1),
+    "chord": dict(CHORD),
+    "chord_within_step_only": dict(jacobian_reuse=1, jacobian_across_steps=0, adaptive_forcing=0),
+    "chord_extrapolated_start": dict(CHORD, extrapolate_guess=1),
+    "chord_bicgstab": dict(CHORD, momentum_solver="bicgstab"),
+    "chord_fp32_jacobian": dict(CHORD, jacobian_fp32=1),
 }
 
 
@@ -42,16 +46,18 @@ def cavity2d():
     g[top, 0] = (1.0 - (2.0 * X[top, 0] - 1.0) ** 4)
     g = g.reshape(-1)
     dt, rho, mu = 0.02, 1.0, 0.01
-    states = []
-    u, p = np.zeros(ost.W.ndofs), np.zeros(ost.P.nnodes)
-    for _ in range(4):
-        # _step (:468-518) piece by piece so that Newton can be driven below the hard-wired 1e-10 of :499 (see the
-        # comment in test_variant_matches_oracle)
-        ui = ost.tentative_velocity(u, p, None, None, (bd, g[bd]), rho, mu, dt, tol=1e-14)
-        p1 = ost.pressure(ui, p, None, rho, mu, dt, 1e-12)
-        u = ost.velocity_correction(ui, p1, p, (bd, g[bd]), rho, mu, dt, 1e-12)
-        p = p1
-        states.append((u.copy(), p.copy()))
+    # "reference": _step (:468-518) exactly as the reference runs it (Newton |F| < 1e-10 hard-wired at :499, LU updates);
+    # "root": Newton driven to 1e-14, i.e. the root of F1 -- what the chord variants converge to
+    states = {}
+    for kind, newton_tol in (("reference", 1e-10), ("root", 1e-14)):
+        u, p = np.zeros(ost.W.ndofs), np.zeros(ost.P.nnodes)
+        states[kind] = []
+        for _ in range(4):
+            ui = ost.tentative_velocity(u, p, None, None, (bd, g[bd]), rho, mu, dt, tol=newton_tol)
+            p1 = ost.pressure(ui, p, None, rho, mu, dt, 1e-12)
+            u = ost.velocity_correction(ui, p1, p, (bd, g[bd]), rho, mu, dt, 1e-12)
+            p = p1
+            states[kind].append((u.copy(), p.copy()))
     return om, g, (dt, rho, mu), states
 
 
@@ -62,11 +68,12 @@ def test_variant_matches_oracle(gpu_ctx, cavity2d, name):
 
     om, g, (dt, rho, mu), states = cavity2d
     nav.reset_options()
-    # The reference's Newton test |F|_2 < 1e-10 (:499) is absolute and not mesh-normalised: on this mesh two iterates
-    # that both pass it can differ by 1e-7 relative.  Newton + LU (reference, oracle) overshoots it to ~1e-15 in its last
-    # update; the Krylov path is asked for the same depth here so that the comparison measures the discretisation and
-    # the solvers, not where each path happened to stop.
-    nav.set_options(newton_atol=1e-13, **VARIANTS[name])
+    # Solver options as they ship (no newton_atol override).  The default path reproduces the reference's Newton iterates
+    # and is compared with the oracle at the reference's settings; the chord variants converge to the root of F1 and are
+    # compared with the oracle driven to the root (the two oracle runs differ by up to 3e-8 on this mesh: that is the
+    # reference's own distance from the root when its last exact update lands just below 1e-10).
+    nav.set_options(**VARIANTS[name])
+    kind = "root" if VARIANTS[name].get("jacobian_reuse", 0) else "reference"
     try:
         m = d.Mesh(om.points, om.cells)
         W = d.VectorFunctionSpace(m, "CG", 2)
@@ -82,7 +89,7 @@ def test_variant_matches_oracle(gpu_ctx, cavity2d, name):
             s = nav.last_stats()
             assemblies.append(s["jacobian_assemblies"])
             pits.append(s["pressure_its"])
-            uo, po = states[k]
+            uo, po = states[kind][k]
             eu = np.linalg.norm(u._vec - uo) / np.linalg.norm(uo)
             dp = (p._vec - p._vec.mean()) - (po - po.mean())
             ep = np.linalg.norm(dp) / np.linalg.norm(po - po.mean())
@@ -90,8 +97,10 @@ def test_variant_matches_oracle(gpu_ctx, cavity2d, name):
             assert ep < 1e-7, (name, k, ep)
         if VARIANTS[name].get("pressure_precond", "amg") == "amg":
             assert max(pits) < 60, pits  # mesh-independent iteration counts (Jacobi needs several hundred here)
-        if name == "plain":
-            assert min(assemblies) >= 2  # plain Newton assembles at every iteration
+        if kind == "reference":
+            assert min(assemblies) >= 2  # the reference's Newton assembles at every iteration
+        if name == "chord":
+            assert sum(assemblies) < 6   # ... the chord variant keeps its operator
     finally:
         nav.reset_options()
 
@@ -109,7 +118,7 @@ def test_amg_hierarchy_and_dirichlet_variant(gpu_ctx):
     res = {}
     for pc in ("amg", "jacobi"):
         nav.reset_options()
-        nav.set_options(pressure_precond=pc, newton_atol=1e-13)
+        nav.set_options(pressure_precond=pc)
         try:
             m = d.UnitSquareMesh(n, n)
             W = d.VectorFunctionSpace(m, "CG", 2)
