@@ -141,7 +141,8 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=32, help="cube size of the bounded CPU sample (32 -> 0.86 M dofs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-variants", action="store_true", help="skip the opt-in mixed-precision variants")
+    ap.add_argument("--no-variants", action="store_true", help="skip the opt-in variants")
+    ap.add_argument("--variants", default="chord,inner_fp32", help="comma-separated opt-in variants to time beside the headline")
     ap.add_argument("--node-order", default="canonical", choices=["canonical", "lexicographic"],
                     help="experimental: number the nodes by coordinate for cache locality (single GPU; default: the canonical "
                          "numbering of the oracle and the parity tests)")
@@ -324,15 +325,23 @@ def main():
     #   inner_fp32:    the CG iterations of the FGMRES preconditioner (operator S, vectors, products) run in fp32
     variants = {}
     if world == 1 and not args.no_variants:
-        notes = {"jacobian_fp32": "opts.jacobian_fp32 = 1: chord Jacobian stored in fp32 for the Krylov solves; Newton residual, "
+        CHORD = {"jacobian_reuse": 1, "jacobian_across_steps": 1, "adaptive_forcing": 1}
+        vsets = {"chord": dict(CHORD), "jacobian_fp32": {"jacobian_fp32": 1}, "inner_fp32": {"inner_fp32": 1},
+                 "chord_inner_fp32": dict(CHORD, inner_fp32=1)}
+        notes = {"chord": "opts.jacobian_reuse / jacobian_across_steps / adaptive_forcing = 1 (the round-1 default): chord Jacobian "
+                          "kept across Newton iterations and time steps, iterated to |F| < 1e-13; converges to the root of F1 "
+                          "instead of reproducing the reference's last Newton iterate (include/flowb200.h)",
+                 "jacobian_fp32": "opts.jacobian_fp32 = 1: Jacobian stored in fp32 for the Krylov solves; Newton residual, "
                                   "vectors and the |F| < 1e-10 test stay fp64 (same steps, same acceptance test)",
                  "inner_fp32": "opts.inner_fp32 = 1: the inner CG of the flexible-GMRES preconditioner runs in fp32; the outer "
-                               "iteration, its residual test and all results stay fp64 (differs from the default by 2e-11 relative)"}
-        for vname in ("jacobian_fp32", "inner_fp32"):
+                               "iteration, its residual test and all results stay fp64",
+                 "chord_inner_fp32": "chord + inner_fp32"}
+        for vname in [v for v in args.variants.split(",") if v]:
             try:
                 o = _lib.NSOpts()
                 lib.fb_ns_opts_default(C.byref(o))
-                setattr(o, vname, 1)
+                for kk, vv in vsets[vname].items():
+                    setattr(o, kk, vv)
                 h2 = _lib.vp()
                 _lib.check(lib.fb_ns_create(W.handle(), P.handle(), C.byref(o), C.byref(h2)), ctx, "fb_ns_create(%s)" % vname)
                 va, vb = torch.zeros(nu, dtype=torch.float64, device=dev), torch.zeros(nu, dtype=torch.float64, device=dev)
@@ -349,7 +358,8 @@ def main():
                 finally:
                     lib.fb_ns_destroy(h2)
                 variants[vname] = {"value": 1e3 / float(np.mean(tms)), "unit": UNIT, "ms_per_step": float(np.mean(tms)),
-                                   "final_newton_residual": st2.newton_residual, "note": "NOT the headline: " + notes[vname]}
+                                   "final_newton_residual": st2.newton_residual, "last_step": st2.as_dict(),
+                                   "note": "NOT the headline: " + notes[vname]}
                 del va, vb, qa, qb
             except Exception as e:  # a variant must never cost the headline line
                 variants[vname] = {"error": "%s: %s" % (type(e).__name__, e)}
