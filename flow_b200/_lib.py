@@ -26,6 +26,7 @@ DEVICE_PTRS, ROTATIONAL, CHORIN = 1, 2, 4
 F_NONE, F_CONSTANT, F_NODAL, F_LOAD = 0, 1, 2, 3
 BICGSTAB, GMRES, CG = 0, 1, 2
 JACOBI, BLOCK_JACOBI, CHEBYSHEV, AMG = 0, 1, 2, 3
+FORMAT_CSR, FORMAT_TILE = 0, 1
 
 vp = C.c_void_p
 i64 = C.c_int64
@@ -133,6 +134,9 @@ SIGNATURES = {
     "fb_mat_values": (C.c_int, [vp, pd]),
     "fb_mat_spmv": (C.c_int, [vp, C.c_int, pd, pd]),
     "fb_mat_solve_cg": (C.c_int, [vp, C.c_int, pd, pd, i64, pi64, pd, dbl, C.c_int, C.POINTER(C.c_int)]),
+    "fb_mat_set_format": (C.c_int, [vp, C.c_int]),
+    "fb_space_tile_check": (C.c_int, [vp, pi64]),
+    "fb_mat_format_info": (C.c_int, [vp, C.POINTER(C.c_int), pi64, pi64, pi64]),
     "fb_mat_bench_spmv": (C.c_int, [vp, C.c_int, C.c_int, pd, pd]),
     "fb_ns_opts_default": (C.c_int, [C.POINTER(NSOpts)]),
     "fb_ns_create": (C.c_int, [vp, vp, C.POINTER(NSOpts), C.POINTER(vp)]),

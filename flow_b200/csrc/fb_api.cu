@@ -3,6 +3,7 @@
 // reference call each entry point replaces.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -293,6 +294,30 @@ int fb_mat_spmv(fb_mat *mat, int ncomp, const double *x, double *y) {
   FB_API_END
 }
 
+int fb_mat_set_format(fb_mat *mat, int format) {
+  if (!mat || (format != FB_FORMAT_CSR && format != FB_FORMAT_TILE)) return FB_EINVAL;
+  FB_NEED_DEVICE(mat->ctx);
+  if (mat->block != 1) return fb_fail(mat->ctx, FB_EINVAL, "fb_mat_set_format: scalar node matrices only");
+  FB_API_BEGIN(mat->ctx)
+  if (format == FB_FORMAT_TILE) {
+    mat_enable_tile(_ctx, *mat);
+  } else {
+    mat->tval.release();
+  }
+  FB_CUDA(cudaStreamSynchronize(_ctx->dev->stream));
+  FB_API_END
+}
+
+int fb_mat_format_info(fb_mat *mat, int *format, int64_t *ntiles, int64_t *entries, int64_t *union_columns) {
+  if (!mat) return FB_EINVAL;
+  const bool tiled = mat->block == 1 && mat->tval.p && mat->sp->tile;
+  if (format) *format = tiled ? FB_FORMAT_TILE : FB_FORMAT_CSR;
+  if (ntiles) *ntiles = tiled ? mat->sp->tile->ntiles : 0;
+  if (entries) *entries = tiled ? mat->sp->tile->nent : 0;
+  if (union_columns) *union_columns = tiled ? mat->sp->tile->union_total : 0;
+  return FB_OK;
+}
+
 int fb_mat_bench_spmv(fb_mat *mat, int ncomp, int reps, double *ms_avg, double *bytes) {
   if (!mat || reps < 1) return FB_EINVAL;
   FB_API_BEGIN(mat->ctx)
@@ -415,7 +440,7 @@ struct fb_ns {
   DBuf<float> J32;           // fp32 copy of J for the Krylov solves (opts.jacobian_fp32)
   // FGMRES path (opts.momentum_solver == FB_GMRES): scalar operator S = M + theta dt mu/rho K of the inner CG
   fb_mat Ku;                 // scalar P2 stiffness (assembled on first use)
-  DBuf<double> Sval, dinv_S;
+  DBuf<double> Sval, dinv_S, Sval_t;
   double S_key = -1.0;       // theta dt mu / rho of the current Sval
   uint64_t S_bc_hash = 0;
   FgmresWork fw;
@@ -576,6 +601,13 @@ int fb_ns_create(fb_space *Wsp, fb_space *Psp, const fb_ns_opts *opts, fb_ns **o
   ns->Mu.block = 1;
   ns->Mu.val.alloc((size_t)ns->W->nnz);
   assemble_constant(ctx, *ns->W, 1, ns->Mu.val.p);
+  // scalar P2 operators x D components run from the tile format (fb_tile.cu) once the mesh is large enough for a
+  // persistent kernel to pay off; FB_TILE_MIN_ROWS overrides the threshold (0: always, tests)
+  {
+    const char *e = getenv("FB_TILE_MIN_ROWS");
+    const int64_t min_rows = e ? atoll(e) : 16384;
+    if (ns->W->n_owned >= min_rows) mat_enable_tile(ctx, ns->Mu);
+  }
   ns->J.sp = ns->W;
   ns->J.block = D;
   ns->J.val.alloc((size_t)ns->W->nnz * D * D);
@@ -855,9 +887,18 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
       s.reserved[7] += 1.0;  // number of Jacobian assemblies
     }
     FB_CUDA(cudaEventRecord(dv->ev[5], st));
+    LinOp Jop = make_linop(ns->J, 1, nullptr);
+    if (o.jacobian_fp32) Jop.val32 = ns->J32.p;
+    // Only the first Newton update moves the Dirichlet dofs (delta = ui - g there); lift them so
+    // that the Krylov space lives on the free dofs (BiCGStab breaks down otherwise).
+    const bool lifted = (newton == 0 && n_ubc > 0);
+    if (lifted) lift_identity_rows(ctx, Jop, ns->F.p, ns->ubc_dofs.p, n_ubc, ns->xg_u.p, ns->tmp_u.p);
     // Inner tolerance (inexact Newton): the first update cannot reduce |F| below the nonlinear remainder
     // c*|F| (c = contraction observed at the previous time step), so the first linear solve stops there.
-    double atol_inner = std::max(chord ? 0.1 * target : lin_floor, o.momentum_rtol * r);
+    // the relative part refers to the right-hand side the Krylov solver sees: after the lift of the Dirichlet rows
+    // (first update of a step: |F| is dominated by the rows u - g of dofs whose boundary value changed)
+    const double r_rhs = lifted ? vec_norm2_sync(ctx, ns->F.p, nu_o) : r;
+    double atol_inner = std::max(chord ? 0.1 * target : lin_floor, o.momentum_rtol * std::min(r, r_rhs));
     if (chord && o.adaptive_forcing && ns->contraction > 0.0 && ns->contraction < 0.1) {
       const double predicted = ns->contraction * r;  // |F| the update can reach at best
       if (predicted < 0.5 * target)
@@ -866,12 +907,6 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
         atol_inner = std::max(atol_inner, 0.5 * predicted);
     }
     int its = 0;
-    LinOp Jop = make_linop(ns->J, 1, nullptr);
-    if (o.jacobian_fp32) Jop.val32 = ns->J32.p;
-    // Only the first Newton update moves the Dirichlet dofs (delta = ui - g there); lift them so
-    // that the Krylov space lives on the free dofs (BiCGStab breaks down otherwise).
-    const bool lifted = (newton == 0 && n_ubc > 0);
-    if (lifted) lift_identity_rows(ctx, Jop, ns->F.p, ns->ubc_dofs.p, n_ubc, ns->xg_u.p, ns->tmp_u.p);
     int status;
     if (o.momentum_solver == FB_GMRES) {
       // flexible GMRES preconditioned by a few CG iterations on S (x) I, S = M + theta dt nu K (constant in time)
@@ -889,6 +924,10 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
         vec_axpby(ctx, ns->Sval.p, 1.0, ns->Mu.val.p, c2, ns->Ku.val.p, ns->W->nnz);
         mask_build(ctx, ns->mask_u.p, nu, ns->ubc_dofs.p, n_ubc);
         jacobi_setup_scalar(ctx, *ns->W, ns->Sval.p, D, n_ubc > 0 ? ns->mask_u.p : nullptr, ns->dinv_S.p);
+        if (ns->Mu.tval.p) {  // same operator in tile order
+          ns->Sval_t.alloc((size_t)ns->W->tile->nent);
+          tile_pack(ctx, *ns->W->tile, ns->Sval.p, ns->Sval_t.p);
+        }
         ns->S_key = c2;
         ns->S_bc_hash = bc_hash;
         if (o.inner_fp32 && !fb_is_distributed(ctx)) {
@@ -909,6 +948,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
       } inner{ctx, make_linop(ns->Mu, D, n_ubc > 0 ? ns->mask_u.p : nullptr), ns->dinv_S.p, &ns->kw_inner,
               o.momentum_inner_its > 0 ? o.momentum_inner_its : 4};
       inner.S.val = ns->Sval.p;
+      if (inner.S.tile) inner.S.tval = ns->Sval_t.p;
       FgmresPrecond pc;
       pc.self = &inner;
       pc.apply = [](void *self, const double *v, double *z, int *ii) -> int {

@@ -15,6 +15,8 @@
 #include <vector>
 
 #include "fb_element.cuh"
+#include <memory>
+
 #include "fb_ops.h"
 
 namespace hq {
@@ -180,6 +182,7 @@ void dev_space_build(fb_space *s, DevSpace &d) {
   fb_space_build_pattern(s);
   const fb_mesh *m = s->mesh;
   d.ctx = ctx;
+  d.host = s;
   d.dim = m->dim;
   d.nl = s->nl;
   d.degree = s->degree;
@@ -222,7 +225,27 @@ LinOp make_linop(const fb_mat &m, int ncomp, const uint8_t *mask) {
   A.col = m.sp->col.p;
   A.val = m.val.p;
   A.mask = mask;
+  if (m.block == 1 && m.tval.p && m.sp->tile && tile_enabled()) {
+    A.tile = m.sp->tile;
+    A.tval = m.tval.p;
+  }
   return A;
+}
+
+void mat_enable_tile(fb_ctx *ctx, fb_mat &m) {
+  if (m.block != 1 || !tile_enabled()) return;
+  DevSpace *sp = m.sp;
+  if (!sp->tile) {
+    std::unique_ptr<TileFormat> tf(new TileFormat());
+    tile_format_build(sp->host, *tf, ctx->dev->stream);
+    sp->tile = tf.release();
+  }
+  m.tval.alloc((size_t)sp->tile->nent);
+  tile_pack(ctx, *sp->tile, m.val.p, m.tval.p);
+}
+
+void mat_repack(fb_ctx *ctx, fb_mat &m) {
+  if (m.tval.p && m.sp->tile) tile_pack(ctx, *m.sp->tile, m.val.p, m.tval.p);
 }
 
 // =============================================================================
@@ -737,6 +760,7 @@ static void spmv_local(fb_ctx *ctx, const LinOp &A, const double *x, double *y, 
     if (V == 0) return launch_bspmv<3, 32>(ctx, A, x, y, dot_mode, w, slot, flag);
     return launch_bspmv_u<3, 16, 4, 1>(ctx, A, x, y, dot_mode, w, slot, flag);
   }
+  if (A.tile && A.tval) return tile_spmm(ctx, A, x, y, dot_mode, w, slot, flag);
   // scalar: pick lanes per row from the average row length
   switch (A.ncomp) {
     case 1:

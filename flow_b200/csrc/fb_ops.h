@@ -4,9 +4,24 @@
 
 #include "fb_device.cuh"
 
+// Tile-CSR format of a node pattern (fb_tile.cu): rows grouped into tiles of spatially close nodes, entries stored
+// as (fp64 value, 16-bit index into the tile's column union), the union gathered into shared memory once per tile.
+struct TileFormat {
+  int64_t nrows = 0, ntiles = 0, nent = 0, union_total = 0;
+  DBuf<int> desc;        // ntiles * 8: row0, nr, e0, ne_pad, u0, nu, -, -
+  DBuf<int> rowid;       // tile-order row -> canonical row
+  DBuf<int> rptr;        // per tile nr + 1 entry offsets relative to e0
+  DBuf<int> ucol;        // column unions (canonical node ids)
+  DBuf<uint16_t> lidx;   // nent
+  DBuf<int> src;         // nent: CSR slot of the entry (-1: padding) -- used to (re)pack values
+};
+
 // Device copy of a node space: dof map, node-level CSR pattern, element->slot scatter map.
 struct DevSpace {
   fb_ctx *ctx = nullptr;
+  fb_space *host = nullptr;  // the space this is the device copy of
+  TileFormat *tile = nullptr;  // built on first use (mat_enable_tile)
+  ~DevSpace() { delete tile; }
   int dim = 0, nl = 0, degree = 0;
   int64_t nnodes = 0, nc = 0, nnz = 0, nbf = 0;
   DBuf<double> xyz;         // vertex coordinates (mesh.nv * dim)
@@ -30,6 +45,7 @@ struct fb_mat {
   DevSpace *sp = nullptr;  // pattern owner (not owned)
   int block = 1;           // 1: scalar node matrix; D: D x D blocks stored row-planar
   DBuf<double> val;        // nnz * block * block
+  DBuf<double> tval;       // block == 1 only: the same values in tile order (empty: CSR kernels only)
   bool owned_space = false;
 };
 
@@ -45,6 +61,8 @@ struct LinOp {
   const double *val = nullptr;
   const float *val32 = nullptr;   // block > 1 only: fp32 copy of val; when set the product streams this one
   const uint8_t *mask = nullptr;  // per dof: 1 -> identity row (Dirichlet); may be null
+  const TileFormat *tile = nullptr;  // block == 1: tile format of the pattern and the values packed for it
+  const double *tval = nullptr;      // (both set: spmv() runs the tile kernel)
   int64_t ndofs() const { return nrows * (block > 1 ? block : ncomp); }
   int64_t nlocal_dofs() const { return nlocal * (block > 1 ? block : ncomp); }
   int dofs_per_node() const { return block > 1 ? block : ncomp; }
@@ -69,6 +87,16 @@ void dev_space_build(fb_space *s, DevSpace &d);
 // kind: 0 P1/P2 stiffness, 1 mass
 void assemble_constant(fb_ctx *ctx, DevSpace &sp, int kind, double *val);
 void assemble_lumped(fb_ctx *ctx, DevSpace &sp, double *diag);
+
+// ---- tile format (fb_tile.cu)
+bool tile_enabled();  // FB_TILE=0 disables the format globally (CSR kernels everywhere)
+void tile_format_build(fb_space *s, TileFormat &tf, cudaStream_t st);
+void tile_pack(fb_ctx *ctx, const TileFormat &tf, const double *val, double *tval);  // tval[k] = val[src[k]]
+void tile_spmm(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_mode, const double *w, int slot,
+               const int *flag);
+// build the space's tile format if needed and pack m's values for it; mat_repack after m.val changed
+void mat_enable_tile(fb_ctx *ctx, fb_mat &m);
+void mat_repack(fb_ctx *ctx, fb_mat &m);
 
 // ---- SpMV: y = A x; dot_mode 0 none, 1: red[slot] = w.y, 2: red[slot] = w.y and red[slot+1] = y.y
 void spmv(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_mode = 0, const double *w = nullptr,

@@ -135,6 +135,16 @@ int fb_mat_spmv(fb_mat *mat, int ncomp, const double *x, double *y);
  * (pressure_correction.py:451-464) and project() in the tests. */
 int fb_mat_solve_cg(fb_mat *mat, int ncomp, const double *b, double *x, int64_t nbc, const int64_t *bc_dofs,
                     const double *bc_vals, double rtol, int maxit, int *iterations);
+/* Storage format of a scalar node matrix on the device.  FB_FORMAT_CSR: row-wise CSR kernels.  FB_FORMAT_TILE: tile-CSR
+ * (csrc/fb_tile.cu): rows grouped into tiles of spatially close nodes, the union of a tile's columns staged in shared
+ * memory, entries streamed by TMA bulk copies as (fp64 value, 16-bit local column).  Same results up to summation
+ * order; the Navier-Stokes engine selects it by itself for its P2 operators on meshes of >= 16384 nodes. */
+enum fb_format { FB_FORMAT_CSR = 0, FB_FORMAT_TILE = 1 };
+int fb_mat_set_format(fb_mat *mat, int format);
+/* host-only self check of the tile format of a space's pattern (no device needed): the format must reproduce the CSR
+ * pattern exactly.  stats[6]: tiles, entries incl. padding, sum of union sizes, max rows / entries / union per tile */
+int fb_space_tile_check(fb_space *space, int64_t *stats);
+int fb_mat_format_info(fb_mat *mat, int *format, int64_t *ntiles, int64_t *entries, int64_t *union_columns);
 /* SpMV micro-benchmark on resident data: runs `reps` products, returns avg ms and algorithmic bytes */
 int fb_mat_bench_spmv(fb_mat *mat, int ncomp, int reps, double *ms_avg, double *bytes);
 

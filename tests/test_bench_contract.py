@@ -41,5 +41,5 @@ def test_b200_arm_line(gpu_ctx):
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
-    assert d["variants"]["jacobian_fp32"]["value"] > 0 and d["variants"]["inner_fp32"]["value"] > 0
+    assert d["variants"]["chord"]["value"] > 0 and d["variants"]["inner_fp32"]["value"] > 0
     assert d["iterations"]["newton"] <= 10

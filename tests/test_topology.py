@@ -110,3 +110,27 @@ def test_coordinate_node_order_is_a_consistent_renumbering(dim):
         ipb, ixb = pattern(b)
         for i in range(a.nnodes):
             assert np.array_equal(np.sort(perm[ixa[ipa[i]:ipa[i + 1]]]), ixb[ipb[perm[i]]:ipb[perm[i] + 1]])
+
+
+@pytest.mark.parametrize("dim,degree", [(2, 1), (2, 2), (3, 1), (3, 2)])
+def test_tile_format_reproduces_csr_pattern(dim, degree):
+    """Tile-CSR format of csrc/fb_tile.cu (host build, no device): every owned row exactly once, union-local column
+    indices map back to the CSR columns, value slots to the CSR slots, TMA alignment and shared-memory caps hold."""
+    import ctypes as C
+
+    import numpy as np
+
+    from flow_b200 import _lib
+    from flow_b200 import dolfin as d
+
+    mesh = d.UnitSquareMesh(37, 29, "crossed") if dim == 2 else d.UnitCubeMesh(11, 9, 13)
+    V = d.FunctionSpace(mesh, "CG", degree)
+    stats = np.zeros(6, dtype=np.int64)
+    _lib.check(_lib.lib.fb_space_tile_check(V.handle(), _lib.as_pi64(stats)), mesh.ctx, "fb_space_tile_check")
+    nt, nent, usum, max_r, max_e, max_u = [int(x) for x in stats]
+    nnz = _lib.i64()
+    _lib.lib.fb_space_pattern(V.handle(), C.byref(nnz), None, None)
+    assert nt >= 1 and nnz.value <= nent < nnz.value + 8 * nt
+    assert max_r <= 256 and max_e <= 6144 and max_u <= 1280
+    # locality: a tile's column union stays far below one column per entry (this is what the format buys)
+    assert usum < 0.45 * nnz.value or nt == 1
