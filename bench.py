@@ -13,11 +13,13 @@ One JSON line on stdout (rank 0).  `value` = steps/s with the state resident in 
 `flow_b200.navier_stokes.IPCS().step` with pinned host buffers, H2D/D2H inside the timed
 region.  `roofline` = whichever of the two SpMV kernels carries the larger share of the step
 (scalar P2 operator x 3 components, or the block-CSR momentum Jacobian), the other one is in
-`other_kernels.second_kernel`.  `cpu_baseline` = the CPU port oracle/_cstep.so (C++/OpenMP assembly,
-block-Jacobi BiCGStab for the momentum systems, Jacobi-CG for pressure and correction: the GPU path's
-first algorithm, without AMG / FGMRES) on a bounded sample of the same cavity, extrapolated linearly in dofs.  The reference's own stack
-(FEniCS/PETSc) cannot be installed here, so `--impl reference` times that same
-oracle port on the host cores.
+`other_kernels.second_kernel`.  `cpu_baseline` / `--impl reference`: the reference's own stack (FEniCS/PETSc/hypre)
+cannot be installed here; the CPU arm is oracle/_cstep.so, a self-contained C++/OpenMP restatement of
+the same step (Newton with the Jacobian of the current iterate, Jacobi-BiCGStab updates, Jacobi-CG for pressure and
+correction -- a DIFFERENT, weaker preconditioning than the GPU arm's FGMRES/AMG, stated in `config`), run on the STATED
+mesh (n = 74) with all host cores; the number of steps it is given is bounded by --cpu-budget-s and printed.
+`checksum` = |u|_2 and |p - mean p|_2 of the state after warmup + steps steps (all-reduced): the same numbers at
+N = 1, 2, 4, 8 show that the partitioned runs computed the single-GPU solution.
 """
 import argparse
 import ctypes as C
@@ -83,22 +85,47 @@ def cavity_bcs(d, W):
     return [walls, lid]  # the lid wins on the shared edges
 
 
-def oracle_cavity_step_time(n, steps, warmup=0):
-    """Seconds per IPCS step of the CPU port on UnitCubeMesh(n): oracle/_cstep.so (C++/OpenMP assembly with
-    the shared element routines + Jacobi-BiCGStab/CG on all host threads; validated against the numpy oracle in
-    tests/test_oracle.py).  Patterns and constant matrices come from the numpy oracle (set-up, untimed)."""
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_cavity_run(n, max_steps, warmup, budget_s, spmv_reps=3):
+    """IPCS steps of the CPU implementation oracle/_cstep.so on UnitCubeMesh(n) with all host threads (torchrun exports
+    OMP_NUM_THREADS=1: the thread count is set explicitly).  Runs `warmup` untimed and at most `max_steps` timed steps,
+    stopping early once `budget_s` seconds of stepping are spent.  Returns a dict with the step times, iteration
+    counts, checksums and the OpenMP SpMV throughput."""
     from oracle import cstep
 
+    threads = host_threads()
+    cstep.set_threads(threads)
+    t0 = time.perf_counter()
     cv = cstep.CavityCPU(n)
+    setup_s = time.perf_counter() - t0
     u, p = np.zeros(cv.W.ndofs), np.zeros(cv.P.nnodes)
     times, stats = [], None
-    for k in range(warmup + steps):
+    spent = 0.0
+    for k in range(warmup + max_steps):
         t0 = time.perf_counter()
         u, p, stats = cv.step(u, p, DT, RHO, MU, TOL)
+        dt_ = time.perf_counter() - t0
+        spent += dt_
         if k >= warmup:
-            times.append(time.perf_counter() - t0)
+            times.append(dt_)
+        if spent > budget_s and len(times) >= 1:
+            break
     info = dict(zip(("newton_its", "momentum_its", "pressure_its", "correction_its"), stats))
-    return float(np.mean(times)), cv.ndofs, cv.threads(), info
+    return {"sec_per_step": float(np.mean(times)), "steps": len(times), "warmup": min(warmup, k), "ndofs": cv.ndofs,
+            "threads": cv.threads(), "iterations": info, "setup_s": setup_s, "spmv": cv.spmv_bench(spmv_reps),
+            "checksum": {"steps_total": k + 1, "u_l2": float(np.linalg.norm(u)), "p_l2_mean_free": float(np.linalg.norm(p - p.mean()))}}
+
+
+CPU_ALGORITHM = ("CPU arm = oracle/_cstep.so: C++/OpenMP restatement of the same IPCS step (FEniCS/PETSc/hypre are not installable "
+                 "here); DIFFERENT ALGORITHM from the GPU arm: Newton with the Jacobian of the current iterate like the GPU arm, but "
+                 "Jacobi-BiCGStab for the updates (GPU: FGMRES preconditioned by CG on M + dt nu K) and Jacobi-CG for the pressure "
+                 "Poisson (GPU: smoothed-aggregation AMG) and the velocity correction (same)")
 
 
 def workload_string(n):
@@ -110,21 +137,23 @@ def workload_string(n):
 def run_reference(args, rank):
     if rank != 0:
         return
-    n_full = args.n
-    nd_full = sum(dof_counts(n_full))
-    sec, nd, threads, info = oracle_cavity_step_time(args.cpu_n, max(1, args.steps), min(args.warmup, 1))
-    value = (1.0 / sec) * (nd / float(nd_full))
-    sample = ("CPU port oracle/_cstep.so (C++/OpenMP assembly + block-Jacobi BiCGStab / Jacobi-CG on all host threads) of the "
-              "same cavity on UnitCubeMesh(%d) = %d dofs, %.2f s/step measured on %d threads (iterations %s); steps/s "
-              "extrapolated linearly in dofs to %d dofs (optimistic for the CPU: Krylov counts grow with the mesh). "
-              "FEniCS/PETSc itself is not installable here." % (args.cpu_n, nd, sec, threads, info, nd_full))
+    run = cpu_cavity_run(args.n, max(1, args.steps), min(args.warmup, args.cpu_warmup), args.cpu_budget_s)
+    value = 1.0 / run["sec_per_step"]
+    sample = ("%d timed step(s) after %d warm-up step(s) of the stated workload itself (UnitCubeMesh(%d), %d dofs) on %d threads, "
+              "%.1f s/step, iterations of the last step %s; set-up %.0f s (untimed); requested --steps %d --warmup %d, bounded by "
+              "--cpu-budget-s %.0f" % (run["steps"], run["warmup"], args.n, run["ndofs"], run["threads"], run["sec_per_step"],
+                                      run["iterations"], run["setup_s"], args.steps, args.warmup, args.cpu_budget_s))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": run["steps"],
+        "warmup": run["warmup"], "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": 1e3 * run["sec_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_string(n_full),
-                   "parallelism": "host CPU, %d threads (rank 0 only)" % threads},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": workload_string(args.n),
+                   "parallelism": "host CPU, %d OpenMP threads (rank 0 only)" % run["threads"],
+                   "algorithm": CPU_ALGORITHM},
+        "iterations": run["iterations"], "checksum": run["checksum"],
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": run["threads"], "kind": "port", "sample": sample,
+                         "openmp_spmv": run["spmv"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -138,7 +167,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=74, help="cells per edge of the unit cube (74 -> 10.3 M dofs)")
-    ap.add_argument("--cpu-n", type=int, default=32, help="cube size of the bounded CPU sample (32 -> 0.86 M dofs)")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="stepping time the CPU arm may spend (it stops after the step that exceeds it)")
+    ap.add_argument("--cpu-warmup", type=int, default=1, help="warm-up steps of the CPU arm (at most --warmup)")
+    ap.add_argument("--cpu-sample-steps", type=int, default=1, help="timed steps of the cpu_baseline leg of the b200 arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the opt-in variants")
@@ -243,6 +274,16 @@ def main():
     ms_per_step = ms_total / args.steps
     value = args.steps / (ms_total * 1e-3)  # whole job: all ranks advance ONE partitioned cavity
     timed = list(hist)
+    # checksum of the state after warmup + steps steps: owned dofs only, summed over the ranks
+    nuo = W.nodes.plan.n_owned * 3 if world > 1 else nu
+    npo = P.nodes.plan.n_owned if world > 1 else npp
+    cs = torch.stack([(ua[:nuo] ** 2).sum(), pa[:npo].sum(), (pa[:npo] ** 2).sum(),
+                      torch.tensor(float(npo), dtype=torch.float64, device=dev)])
+    if world > 1:
+        dist.all_reduce(cs)
+    cs = cs.tolist()
+    checksum = {"steps_total": args.warmup + args.steps, "u_l2": cs[0] ** 0.5,
+                "p_l2_mean_free": max(cs[2] - cs[1] * cs[1] / cs[3], 0.0) ** 0.5}
 
     # ---- end-to-end through the public API with pinned host buffers
     e2e = None
@@ -259,7 +300,7 @@ def main():
             u0, p0 = u1, p1
         barrier()
         t0 = time.perf_counter()
-        ke = max(2, min(args.steps, 5))
+        ke = args.steps
         for _ in range(ke):
             u1, p1 = stepper.step(d.Constant(DT), {0: u0}, p0, bcs, [], d.Constant(RHO), d.Constant(MU), {0: zero, 1: zero},
                                   verbose=False, tol=TOL)
@@ -367,17 +408,18 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same cavity
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sec, nd, threads, info = oracle_cavity_step_time(args.cpu_n, 2, 1)
-        nd_full = nu_global + np_global
-        cpu = {"value": (1.0 / sec) * (nd / float(nd_full)), "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "CPU port oracle/_cstep.so (C++/OpenMP assembly, block-Jacobi BiCGStab / Jacobi-CG) on UnitCubeMesh(%d) = %d dofs: %.2f s/step on %d "
-                         "threads, iterations %s; extrapolated linearly in dofs to %d" % (args.cpu_n, nd, sec, threads, info, nd_full)}
+        run = cpu_cavity_run(n, args.cpu_sample_steps, 0, args.cpu_budget_s)
+        cpu = {"value": 1.0 / run["sec_per_step"], "unit": UNIT, "cores": run["threads"], "kind": "port",
+               "sample": "%d step(s) from rest of the same workload (UnitCubeMesh(%d), %d dofs) on %d threads: %.1f s/step, iterations %s; "
+                         "no extrapolation.  %s" % (run["steps"], n, run["ndofs"], run["threads"], run["sec_per_step"], run["iterations"],
+                                                    CPU_ALGORITHM),
+               "openmp_spmv": run["spmv"]}
 
     if rank == 0:
         avg = lambda k: float(np.mean([h[k] for h in timed]))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {
                 "workload": workload_string(n),
@@ -394,7 +436,7 @@ def main():
             "phase_ms": {"tentative": avg("ms_tentative"), "pressure": avg("ms_pressure"), "correction": avg("ms_correction"),
                          "assembly_J": avg("ms_assembly_J"), "momentum_solve": avg("ms_momentum_solve")},
             "newton_residuals_last_step": timed[-1]["newton_residuals"],
-            "setup_s": t_setup, "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
+            "checksum": checksum, "setup_s": t_setup, "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
             "other_kernels": extra, "variants": variants, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
