@@ -28,6 +28,7 @@ struct fb_mesh {
   std::vector<int32_t> cell_edges;  // nc*NE, UFC local edge order
   std::vector<int32_t> bf_cell, bf_local;
   std::vector<uint8_t> bvert, bedge;
+  std::vector<int32_t> cell_order;  // device storage order of the cells (Morton order of the centroids), built lazily
   void *dev = nullptr;  // DeviceMesh*
 };
 
@@ -51,5 +52,7 @@ struct fb_space {
 
 int fb_fail(fb_ctx *ctx, int status, const std::string &msg);
 int fb_space_build_pattern(fb_space *s);
+// new position -> mesh cell: Morton order of the cell centroids (identity with FB_CELL_ORDER=0)
+const std::vector<int32_t> &fb_mesh_cell_order(fb_mesh *m);
 
 static inline int fb_num_local_edges(int dim) { return dim == 2 ? 3 : 6; }

@@ -8,6 +8,7 @@
 // as (fp64 value, 16-bit index into the tile's column union), the union gathered into shared memory once per tile.
 struct TileFormat {
   int64_t nrows = 0, ntiles = 0, nent = 0, union_total = 0;
+  int cfg = 0;           // kernel configuration the tiles were sized for (fb_tile.cu TileCfg)
   DBuf<int> desc;        // ntiles * 8: row0, nr, e0, ne_pad, u0, nu, -, -
   DBuf<int> rowid;       // tile-order row -> canonical row
   DBuf<int> rptr;        // per tile nr + 1 entry offsets relative to e0

@@ -23,12 +23,52 @@
 
 namespace {
 
-constexpr int TILE_THREADS = 1024;
-constexpr int TILE_T = 4;                           // lanes per row
-constexpr int TILE_RCAP = TILE_THREADS / TILE_T;    // rows per tile: one pass of the block
-constexpr int TILE_ECAP = 6144;                     // entries per tile (multiple of 8)
-constexpr int TILE_UCAP = 1280;                     // union columns per tile (NC = 3: 30 KB of x per stage)
-constexpr int TILE_DESC = 8;                        // ints per tile descriptor
+constexpr int TILE_T = 4;      // lanes per row
+constexpr int TILE_DESC = 8;   // ints per tile descriptor
+
+// Kernel configurations (threads per CTA, entry / union caps per tile, pipeline stages, CTAs per SM).  A tile is one
+// pass of the block: at most THREADS / TILE_T rows.  What bounds the kernel is the number of bytes in flight per SM
+// (HBM needs ~45 KB per SM outstanding at all times), i.e. (stages - 1) x CTAs per SM tile loads.
+template <int ID>
+struct TileCfg;
+template <>
+struct TileCfg<0> {  // one big CTA per SM, one tile ahead
+  static constexpr int THREADS = 1024, ECAP = 6144, UCAP = 1280, NSTAGE = 2, CTAS = 1;
+};
+template <>
+struct TileCfg<1> {  // two CTAs per SM, one tile ahead each
+  static constexpr int THREADS = 512, ECAP = 3072, UCAP = 768, NSTAGE = 2, CTAS = 2;
+};
+template <>
+struct TileCfg<2> {  // one CTA per SM, three tiles ahead
+  static constexpr int THREADS = 512, ECAP = 3072, UCAP = 768, NSTAGE = 4, CTAS = 1;
+};
+template <>
+struct TileCfg<3> {  // four small CTAs per SM
+  static constexpr int THREADS = 256, ECAP = 1536, UCAP = 448, NSTAGE = 2, CTAS = 4;
+};
+template <>
+struct TileCfg<4> {  // two CTAs per SM, two tiles ahead each
+  static constexpr int THREADS = 256, ECAP = 1792, UCAP = 512, NSTAGE = 3, CTAS = 2;
+};
+constexpr int TILE_NCFG = 5;
+
+struct TileCaps {
+  int threads, ecap, ucap, nstage, ctas;
+};
+template <int ID>
+constexpr TileCaps caps_of() {
+  return TileCaps{TileCfg<ID>::THREADS, TileCfg<ID>::ECAP, TileCfg<ID>::UCAP, TileCfg<ID>::NSTAGE, TileCfg<ID>::CTAS};
+}
+inline TileCaps tile_caps(int id) {
+  switch (id) {
+    case 0: return caps_of<0>();
+    case 1: return caps_of<1>();
+    case 2: return caps_of<2>();
+    case 3: return caps_of<3>();
+    default: return caps_of<4>();
+  }
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -59,6 +99,35 @@ __device__ __forceinline__ void tma_bulk_load(void *dst, const void *src, uint32
 __device__ __forceinline__ void cp_async8(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// the NC values of node `col` -> xs[slot * NC ..]; NC = 3: 24 bytes at a multiple of 24, i.e. one 16-byte and one
+// 8-byte piece in an order that depends on the parity of the node (source and destination have the same parity
+// only if col and slot do: otherwise three 8-byte pieces)
+template <int NC>
+__device__ __forceinline__ void gather_node(double *xs, int slot, const double *x, int col) {
+  double *dst = xs + slot * NC;
+  const double *src = x + (int64_t)col * NC;
+  if (NC == 3) {  // slot parity == column parity by construction (tile_format_build_host)
+    if (col & 1) {
+      cp_async8(dst, src);
+      cp_async16(dst + 1, src + 1);
+    } else {
+      cp_async16(dst, src);
+      cp_async8(dst + 2, src + 2);
+    }
+  } else if (NC == 2) {
+    cp_async16(dst, src);
+  } else {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) cp_async8(dst + c, src + c);
+  }
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 struct TileArgs {
   int ntiles;
@@ -79,26 +148,28 @@ struct TileArgs {
   const int *flag;
 };
 
-template <int NC>
+template <int NC, class CFG>
 struct TileSmem {
-  static constexpr int VAL_BYTES = TILE_ECAP * 8;
-  static constexpr int X_BYTES = TILE_UCAP * NC * 8;
-  static constexpr int IDX_BYTES = TILE_ECAP * 2;
-  static constexpr int STAGE = VAL_BYTES + X_BYTES + IDX_BYTES;
-  static constexpr int TOTAL = 2 * STAGE + 64;
+  static constexpr int VAL_BYTES = CFG::ECAP * 8;
+  static constexpr int X_BYTES = CFG::UCAP * NC * 8;
+  static constexpr int IDX_BYTES = CFG::ECAP * 2;
+  static constexpr int STAGE = (VAL_BYTES + X_BYTES + IDX_BYTES + 127) / 128 * 128;
+  static constexpr int TOTAL = CFG::NSTAGE * STAGE + 64;
 };
 
 // DOT: 0 none; 1: red[slot] = w.y; 2: + red[slot+1] = y.y; 3: (w.x, y.x, x.x) -- as k_spmm_u
-template <int NC, int DOT>
-__global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_spmm(const TileArgs a) {
+template <int NC, int DOT, class CFG>
+__global__ void __launch_bounds__(CFG::THREADS, CFG::CTAS) k_tile_spmm(const TileArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  using L = TileSmem<NC>;
+  using L = TileSmem<NC, CFG>;
+  constexpr int NS = CFG::NSTAGE, THREADS = CFG::THREADS;
+  static_assert(CFG::UCAP <= 2 * THREADS, "two union columns per thread");
   if (a.flag && *a.flag) return;
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 2 * L::STAGE);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + NS * L::STAGE);
   const int tid = threadIdx.x;
   if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) mbar_init(&bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -109,13 +180,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_spmm(const TileArgs a)
   auto stage_x = [&](int s) { return reinterpret_cast<double *>(smem + s * L::STAGE + L::VAL_BYTES); };
   auto stage_idx = [&](int s) { return reinterpret_cast<uint16_t *>(smem + s * L::STAGE + L::VAL_BYTES + L::X_BYTES); };
 
-  // union columns of a tile, two per thread (TILE_UCAP <= 2 * TILE_THREADS), held in registers one tile ahead
+  // union columns of a tile, two per thread, fetched into registers one iteration before they are used
   auto load_ucols = [&](int t, int &c0, int &c1) {
     c0 = c1 = -1;
     if (t < a.ntiles) {
       const int u0 = a.desc[t * TILE_DESC + 4], nu = a.desc[t * TILE_DESC + 5];
       if (tid < nu) c0 = a.ucol[u0 + tid];
-      if (tid + TILE_THREADS < nu) c1 = a.ucol[u0 + tid + TILE_THREADS];
+      if (tid + THREADS < nu) c1 = a.ucol[u0 + tid + THREADS];
     }
   };
   // start the loads of tile t into stage s: TMA for the entries, cp.async gather for the x union
@@ -129,30 +200,29 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_spmm(const TileArgs a)
         tma_bulk_load(stage_idx(s), a.lidx + e0, (uint32_t)ne * 2u, &bar[s], policy);
       }
       double *xs = stage_x(s);
-      if (c0 >= 0) {
-#pragma unroll
-        for (int c = 0; c < NC; ++c) cp_async8(xs + tid * NC + c, a.x + (int64_t)c0 * NC + c);
-      }
-      if (c1 >= 0) {
-#pragma unroll
-        for (int c = 0; c < NC; ++c) cp_async8(xs + (tid + TILE_THREADS) * NC + c, a.x + (int64_t)c1 * NC + c);
-      }
+      if (c0 >= 0) gather_node<NC>(xs, tid, a.x, c0);
+      if (c1 >= 0) gather_node<NC>(xs, tid + THREADS, a.x, c1);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
   double d[3] = {0.0, 0.0, 0.0};
+  const int G = gridDim.x;
   int t = blockIdx.x;
   int c0, c1;
-  load_ucols(t, c0, c1);
-  issue(t, 0, c0, c1);
-  load_ucols(t + gridDim.x, c0, c1);
-  uint32_t phasebits = 0u;  // bit s: parity the next wait on bar[s] expects
+  // prologue: NS - 1 tiles in flight
+#pragma unroll
+  for (int k = 0; k < NS - 1; ++k) {
+    load_ucols(t + k * G, c0, c1);
+    issue(t + k * G, k, c0, c1);
+  }
+  load_ucols(t + (NS - 1) * G, c0, c1);
   const int lane = tid % TILE_T, rl = tid / TILE_T;
-  for (int s = 0; t < a.ntiles; t += gridDim.x, s ^= 1) {
-    // one tile ahead: entries by TMA, x union by cp.async; two tiles ahead: the union column ids into registers
-    issue(t + gridDim.x, s ^ 1, c0, c1);
-    load_ucols(t + 2 * gridDim.x, c0, c1);
+  for (int it = 0; t < a.ntiles; t += G, ++it) {
+    const int s = it % NS;
+    // NS - 1 tiles ahead: entries by TMA, x union by cp.async; NS tiles ahead: the union column ids into registers
+    issue(t + (NS - 1) * G, (it + NS - 1) % NS, c0, c1);
+    load_ucols(t + NS * G, c0, c1);
     // this tile's row data (global, coalesced) while its stage completes
     const int row0 = a.desc[t * TILE_DESC + 0], nr = a.desc[t * TILE_DESC + 1];
     int eb = 0, ee = 0, row = -1;
@@ -169,10 +239,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_spmm(const TileArgs a)
       if (DOT == 3 || a.mask) xd = a.x[dof];
       if (a.mask) masked = a.mask[dof] != 0;
     }
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    cp_async_wait<NS - 1>();
     __syncthreads();  // every thread's part of the x union has landed
-    mbar_wait(&bar[s], (phasebits >> s) & 1u);
-    phasebits ^= 1u << s;
+    mbar_wait(&bar[s], (uint32_t)(it / NS) & 1u);
     const double *vs = stage_val(s);
     const double *xs = stage_x(s);
     const uint16_t *is = stage_idx(s);
@@ -207,7 +276,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_tile_spmm(const TileArgs a)
     }
     __syncthreads();  // stage s is free again (it is refilled at the top of the next iteration)
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  cp_async_wait<0>();
   if (DOT >= 1) {
     if (DOT == 1) {
       double v1[1] = {d[0]};
@@ -228,25 +297,36 @@ __global__ void k_tile_pack(int64_t nent, const int *__restrict__ src, const dou
   }
 }
 
-template <int NC, int DOT>
+template <int NC, int DOT, class CFG>
 void launch_tile(fb_ctx *ctx, const TileArgs &a) {
-  using L = TileSmem<NC>;
+  using L = TileSmem<NC, CFG>;
   static bool configured = false;
   if (!configured) {
-    FB_CUDA(cudaFuncSetAttribute(k_tile_spmm<NC, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    FB_CUDA(cudaFuncSetAttribute(k_tile_spmm<NC, DOT, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  const int grid = std::min(a.ntiles, ctx->dev->sm_count);
-  k_tile_spmm<NC, DOT><<<grid, TILE_THREADS, L::TOTAL, ctx->dev->stream>>>(a);
+  const int grid = std::min(a.ntiles, ctx->dev->sm_count * CFG::CTAS);
+  k_tile_spmm<NC, DOT, CFG><<<grid, CFG::THREADS, L::TOTAL, ctx->dev->stream>>>(a);
   ctx->launches++;
 }
 
+template <int NC, class CFG>
+void launch_tile_dot(fb_ctx *ctx, const TileArgs &a, int dot_mode) {
+  if (dot_mode == 0) launch_tile<NC, 0, CFG>(ctx, a);
+  else if (dot_mode == 1) launch_tile<NC, 1, CFG>(ctx, a);
+  else if (dot_mode == 2) launch_tile<NC, 2, CFG>(ctx, a);
+  else launch_tile<NC, 3, CFG>(ctx, a);
+}
+
 template <int NC>
-void launch_tile_nc(fb_ctx *ctx, const TileArgs &a, int dot_mode) {
-  if (dot_mode == 0) launch_tile<NC, 0>(ctx, a);
-  else if (dot_mode == 1) launch_tile<NC, 1>(ctx, a);
-  else if (dot_mode == 2) launch_tile<NC, 2>(ctx, a);
-  else launch_tile<NC, 3>(ctx, a);
+void launch_tile_nc(fb_ctx *ctx, const TileArgs &a, int dot_mode, int cfg) {
+  switch (cfg) {
+    case 0: return launch_tile_dot<NC, TileCfg<0>>(ctx, a, dot_mode);
+    case 1: return launch_tile_dot<NC, TileCfg<1>>(ctx, a, dot_mode);
+    case 2: return launch_tile_dot<NC, TileCfg<2>>(ctx, a, dot_mode);
+    case 3: return launch_tile_dot<NC, TileCfg<3>>(ctx, a, dot_mode);
+    default: return launch_tile_dot<NC, TileCfg<4>>(ctx, a, dot_mode);
+  }
 }
 
 inline uint64_t spread3(uint64_t v) {  // 21 bits -> every third bit
@@ -275,6 +355,13 @@ bool tile_enabled() {
   return on != 0;
 }
 
+// kernel configuration of the formats built from now on (FB_TILE_CFG, experiments; default: see TileCfg)
+static int tile_default_cfg() {
+  const char *e = getenv("FB_TILE_CFG");
+  const int c = e ? atoi(e) : 1;
+  return (c >= 0 && c < TILE_NCFG) ? c : 1;
+}
+
 // Host side of the format: tiles of the owned rows of s's node pattern (pure host code, once per space).
 struct HostTile {
   std::vector<int> desc, order, rptr, ucol, src;
@@ -282,7 +369,8 @@ struct HostTile {
   int ntiles = 0;
 };
 
-static void tile_format_build_host(fb_space *s, HostTile &h) {
+static void tile_format_build_host(fb_space *s, HostTile &h, const TileCaps &cap) {
+  const int TILE_RCAP = cap.threads / TILE_T, TILE_ECAP = cap.ecap, TILE_UCAP = cap.ucap;
   fb_space_build_pattern(s);
   const int dim = s->mesh->dim;
   const int64_t n = s->n_owned, nn = s->nnodes;
@@ -317,67 +405,146 @@ static void tile_format_build_host(fb_space *s, HostTile &h) {
   std::vector<int> &desc = h.desc, &rptr = h.rptr, &ucol = h.ucol, &src = h.src;
   std::vector<uint16_t> &lidx = h.lidx;
   rptr.reserve((size_t)n + n / 128 + 16);
-  src.reserve(ix.size() + ix.size() / 64);
-  lidx.reserve(ix.size() + ix.size() / 64);
+  // ---- phase 1 (sequential): tiles = runs of rows in Morton order, grown until one of the caps binds
   std::vector<int> mark((size_t)nn, -1);
-  std::vector<uint16_t> lid((size_t)nn, 0);
   std::vector<int> ulist;
   ulist.reserve(TILE_UCAP);
-  int64_t pos = 0;
+  int64_t pos = 0, etotal = 0;
   int tile = 0;
   while (pos < n) {
-    // grow the tile row by row in Morton order until one of the caps binds
     ulist.clear();
-    int nr = 0, ne = 0;
+    int nr = 0, ne = 0, n_even = 0, n_odd = 0;
     const int64_t row0 = pos;
     while (pos < n && nr < TILE_RCAP) {
       const int r = order[pos];
       const int len = (int)(ip[r + 1] - ip[r]);
-      if (len > TILE_ECAP || len > TILE_UCAP) throw fb_cuda_error(FB_EINVAL, "tile format: matrix row too long");
-      if (ne + len > TILE_ECAP) break;
-      int fresh = 0;
-      for (int64_t k = ip[r]; k < ip[r + 1]; ++k) fresh += mark[ix[k]] != tile;
-      if ((int)ulist.size() + fresh > TILE_UCAP) break;
+      if (len > TILE_ECAP || len > TILE_UCAP || len > 256) throw fb_cuda_error(FB_EINVAL, "tile format: matrix row too long");
+      if (ne + ((len + 3) & ~3) > TILE_ECAP) break;
+      // slots keep the parity of their column (16-byte gathers, see gather_node): the union occupies
+      // 2 * max(#even, #odd) slots
+      int fe = 0, fo = 0;
+      for (int64_t k = ip[r]; k < ip[r + 1]; ++k)
+        if (mark[ix[k]] != tile) (ix[k] & 1) ? ++fo : ++fe;
+      if (2 * std::max(n_even + fe, n_odd + fo) > TILE_UCAP) break;
+      n_even += fe;
+      n_odd += fo;
       for (int64_t k = ip[r]; k < ip[r + 1]; ++k)
         if (mark[ix[k]] != tile) {
           mark[ix[k]] = tile;
           ulist.push_back(ix[k]);
         }
-      ne += len;
+      ne += (len + 3) & ~3;
       ++nr;
       ++pos;
     }
     std::sort(ulist.begin(), ulist.end());
-    for (size_t j = 0; j < ulist.size(); ++j) lid[ulist[j]] = (uint16_t)j;
-    const int e0 = (int)lidx.size();
+    {  // even columns -> even slots, odd columns -> odd slots (ascending within each class), -1 in unused slots
+      std::vector<int> slots((size_t)2 * std::max(n_even, n_odd), -1);
+      int se = 0, so = 1;
+      for (int c : ulist) {
+        if (c & 1) {
+          slots[so] = c;
+          so += 2;
+        } else {
+          slots[se] = c;
+          se += 2;
+        }
+      }
+      ulist.swap(slots);
+    }
+    // rows of similar length next to each other: the TILE_T lanes of 8 rows share a warp and run the longest row's
+    // trip count (vertex rows of a P2 pattern are ~3x longer than edge rows)
+    std::stable_sort(order.begin() + row0, order.begin() + row0 + nr,
+                     [&](int a, int b) { return ip[a + 1] - ip[a] > ip[b + 1] - ip[b]; });
+    // rows are padded to a multiple of 4 entries (their 32-byte value segments stay aligned), tiles to 8 (TMA)
     int off = 0;
     for (int i = 0; i < nr; ++i) {
       const int r = order[row0 + i];
       rptr.push_back(off);
-      for (int64_t k = ip[r]; k < ip[r + 1]; ++k) {
-        lidx.push_back(lid[ix[k]]);
-        src.push_back((int)k);
-      }
-      off += (int)(ip[r + 1] - ip[r]);
+      off += ((int)(ip[r + 1] - ip[r]) + 3) & ~3;
     }
     rptr.push_back(off);
     const int ne_pad = (off + 7) & ~7;
-    for (int k = off; k < ne_pad; ++k) {
-      lidx.push_back(0);
-      src.push_back(-1);
-    }
-    const int d8[TILE_DESC] = {(int)row0, nr, e0, ne_pad, (int)ucol.size(), (int)ulist.size(), 0, 0};
+    const int d8[TILE_DESC] = {(int)row0, nr, (int)etotal, ne_pad, (int)ucol.size(), (int)ulist.size(), 0, 0};
     desc.insert(desc.end(), d8, d8 + TILE_DESC);
     ucol.insert(ucol.end(), ulist.begin(), ulist.end());
+    etotal += ne_pad;
     ++tile;
-    if ((int64_t)lidx.size() > (int64_t)INT32_MAX - TILE_ECAP) throw fb_cuda_error(FB_EINVAL, "tile format: too many entries");
+    if (etotal > (int64_t)INT32_MAX - TILE_ECAP) throw fb_cuda_error(FB_EINVAL, "tile format: too many entries");
+  }
+  mark.clear();
+  mark.shrink_to_fit();
+  lidx.assign((size_t)etotal, 0);
+  src.assign((size_t)etotal, -1);
+  // ---- phase 2 (parallel over tiles): entries.
+  // Entry order inside the rows.  A warp holds TILE_T lanes of 8 consecutive rows; at step s lane l of row i reads
+  // entry 4 s + l of its row and gathers x from shared memory at slot * NC * 8 bytes.  Shared memory serves 16
+  // distinct 8-byte bank pairs per wavefront, and (NC * slot + c) mod 16 is a bijection of slot mod 16 for NC = 1, 3,
+  // so the 32 gathers of one instruction need the minimum of 2 wavefronts iff every residue class slot mod 16 is
+  // used exactly twice.  The sum over a row does not depend on the order of its entries: the rows of each group of
+  // 8 are emitted step by step, every lane taking the remaining entry of its row whose class is used least so far
+  // in that step (CSR order: 3.8-way conflicts measured).  Padding entries: zero value, slot of the row's first entry.
+#pragma omp parallel
+  {
+    std::vector<uint16_t> lid((size_t)nn, 0);
+#pragma omp for schedule(dynamic, 16)
+    for (int t = 0; t < tile; ++t) {
+      const int *d = &desc[(size_t)t * TILE_DESC];
+      const int row0 = d[0], nr = d[1], e0 = d[2], u0 = d[4], nu = d[5];
+      for (int j = 0; j < nu; ++j)
+        if (ucol[u0 + j] >= 0) lid[ucol[u0 + j]] = (uint16_t)j;
+      const int *rp = &rptr[(size_t)row0 + t];
+      for (int i0 = 0; i0 < nr; i0 += 8) {
+        const int i1 = std::min(nr, i0 + 8);
+        int ent[8][256], cls[8][256], left[8], maxpad = 0;  // remaining entries of the 8 rows (CSR slot, class)
+        for (int i = i0; i < i1; ++i) {
+          const int r = order[row0 + i];
+          int m = 0;
+          for (int64_t k = ip[r]; k < ip[r + 1]; ++k, ++m) {
+            ent[i - i0][m] = (int)k;
+            cls[i - i0][m] = lid[ix[k]] & 15;
+          }
+          left[i - i0] = m;
+          maxpad = std::max(maxpad, rp[i + 1] - rp[i]);
+        }
+        for (int st4 = 0; st4 < maxpad; st4 += 4) {
+          int count[16] = {0};
+          for (int i = i0; i < i1; ++i) {
+            const int q = i - i0, r = order[row0 + i];
+            for (int l = 0; l < 4; ++l) {
+              const int p = st4 + l;
+              if (p >= rp[i + 1] - rp[i]) continue;
+              const size_t at = (size_t)e0 + rp[i] + p;
+              if (left[q] == 0) {  // padding
+                const int fs = lid[ix[ip[r]]];
+                lidx[at] = (uint16_t)fs;
+                src[at] = -1;
+                count[fs & 15]++;
+                continue;
+              }
+              int best = 0;
+              for (int m = 1; m < left[q]; ++m)
+                if (count[cls[q][m]] < count[cls[q][best]]) best = m;
+              const int k = ent[q][best];
+              lidx[at] = lid[ix[k]];
+              src[at] = k;
+              count[cls[q][best]]++;
+              ent[q][best] = ent[q][left[q] - 1];
+              cls[q][best] = cls[q][left[q] - 1];
+              --left[q];
+            }
+          }
+        }
+      }
+    }
   }
   h.ntiles = tile;
 }
 
 void tile_format_build(fb_space *s, TileFormat &tf, cudaStream_t st) {
   HostTile h;
-  tile_format_build_host(s, h);
+  tf.cfg = tile_default_cfg();
+  tile_format_build_host(s, h, tile_caps(tf.cfg));
   tf.nrows = s->n_owned;
   tf.ntiles = h.ntiles;
   tf.nent = (int64_t)h.lidx.size();
@@ -398,7 +565,9 @@ extern "C" int fb_space_tile_check(fb_space *s, int64_t *stats) {
   if (!s) return FB_EINVAL;
   try {
     HostTile h;
-    tile_format_build_host(s, h);
+    const TileCaps cap = tile_caps(tile_default_cfg());
+    const int TILE_RCAP = cap.threads / TILE_T, TILE_ECAP = cap.ecap, TILE_UCAP = cap.ucap;
+    tile_format_build_host(s, h, cap);
     const int64_t n = s->n_owned;
     std::vector<uint8_t> seen((size_t)n, 0);
     int64_t max_r = 0, max_e = 0, max_u = 0, rp = 0;
@@ -407,19 +576,31 @@ extern "C" int fb_space_tile_check(fb_space *s, int64_t *stats) {
       const int row0 = d[0], nr = d[1], e0 = d[2], ne = d[3], u0 = d[4], nu = d[5];
       if (nr < 1 || nr > TILE_RCAP || ne > TILE_ECAP || nu > TILE_UCAP || (e0 & 7) || (ne & 7)) return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: caps/alignment");
       if (rp != row0 + t) return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: rptr layout");
-      for (int j = 1; j < nu; ++j)
-        if (h.ucol[u0 + j - 1] >= h.ucol[u0 + j]) return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: union not ascending");
+      for (int j = 0; j < nu; ++j) {  // slot parity == column parity, ascending within each parity class, gaps are -1
+        const int c = h.ucol[u0 + j];
+        if (c >= 0 && ((c ^ j) & 1)) return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: slot parity");
+        if (c >= 0 && j >= 2 && h.ucol[u0 + j - 2] >= c) return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: union order");
+      }
       for (int i = 0; i < nr; ++i) {
         const int r = h.order[row0 + i];
         if (r < 0 || r >= n || seen[r]) return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: row covered twice");
         seen[r] = 1;
         const int eb = h.rptr[rp + i], ee = h.rptr[rp + i + 1];
-        if (ee - eb != (int)(s->indptr[r + 1] - s->indptr[r])) return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: row length");
+        const int len = (int)(s->indptr[r + 1] - s->indptr[r]);
+        if ((eb & 3) || ee - eb != ((len + 3) & ~3)) return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: row length / alignment");
+        std::vector<int> slots_seen;
         for (int k = eb; k < ee; ++k) {
-          const int64_t slot = s->indptr[r] + (k - eb);
-          if (h.src[e0 + k] != (int)slot || h.lidx[e0 + k] >= nu || h.ucol[u0 + h.lidx[e0 + k]] != s->indices[slot])
+          const int sl = h.src[e0 + k], li = h.lidx[e0 + k];
+          if (li >= nu || h.ucol[u0 + li] < 0) return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: entry points at an empty slot");
+          if (sl < 0) continue;  // padding: zero value, any gathered slot
+          if (sl < s->indptr[r] || sl >= s->indptr[r + 1] || h.ucol[u0 + li] != s->indices[sl])
             return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: entry mismatch");
+          slots_seen.push_back(sl);
         }
+        std::sort(slots_seen.begin(), slots_seen.end());
+        if ((int)slots_seen.size() != len || (len > 0 && (slots_seen.front() != (int)s->indptr[r] || slots_seen.back() != (int)s->indptr[r + 1] - 1)) ||
+            std::adjacent_find(slots_seen.begin(), slots_seen.end()) != slots_seen.end())
+          return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: row entries are not a permutation of the CSR row");
       }
       rp += nr + 1;
       max_r = std::max<int64_t>(max_r, nr);
@@ -429,6 +610,9 @@ extern "C" int fb_space_tile_check(fb_space *s, int64_t *stats) {
     for (int64_t i = 0; i < n; ++i)
       if (!seen[i]) return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: row missing");
     if (stats) {
+      stats[6] = TILE_RCAP;
+      stats[7] = TILE_ECAP;
+      stats[8] = TILE_UCAP;
       stats[0] = h.ntiles;
       stats[1] = (int64_t)h.lidx.size();
       stats[2] = (int64_t)h.ucol.size();
@@ -471,9 +655,9 @@ void tile_spmm(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_
   a.slot = slot;
   a.flag = flag;
   switch (A.ncomp) {
-    case 1: return launch_tile_nc<1>(ctx, a, dot_mode);
-    case 2: return launch_tile_nc<2>(ctx, a, dot_mode);
-    case 3: return launch_tile_nc<3>(ctx, a, dot_mode);
+    case 1: return launch_tile_nc<1>(ctx, a, dot_mode, tf.cfg);
+    case 2: return launch_tile_nc<2>(ctx, a, dot_mode, tf.cfg);
+    case 3: return launch_tile_nc<3>(ctx, a, dot_mode, tf.cfg);
     default: throw fb_cuda_error(FB_EINVAL, "tile_spmm: ncomp must be 1..3");
   }
 }

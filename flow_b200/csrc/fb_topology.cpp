@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <array>
 #include <cstring>
+#include <cstdlib>
 #include <numeric>
 
 #include "fb_internal.h"
@@ -371,4 +372,45 @@ int fb_space_build_pattern(fb_space *s) {
   }
   s->indptr.swap(cnt);
   return FB_OK;
+}
+
+
+// ---- device storage order of the cells ------------------------------------------------------------------------------
+static inline uint64_t fb_spread_bits(uint64_t v, int dim) {
+  uint64_t out = 0;
+  const int bits = dim == 3 ? 21 : 31;
+  for (int b = 0; b < bits; ++b) out |= ((v >> b) & 1ull) << (dim * b);
+  return out;
+}
+
+const std::vector<int32_t> &fb_mesh_cell_order(fb_mesh *m) {
+  if ((int64_t)m->cell_order.size() == m->nc) return m->cell_order;
+  m->cell_order.resize((size_t)m->nc);
+  std::iota(m->cell_order.begin(), m->cell_order.end(), 0);
+  const char *e = getenv("FB_CELL_ORDER");
+  if (e && atoi(e) == 0) return m->cell_order;
+  const int d = m->dim, nv = d + 1;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int64_t v = 0; v < m->nv; ++v)
+    for (int k = 0; k < d; ++k) {
+      lo[k] = std::min(lo[k], m->xyz[v * d + k]);
+      hi[k] = std::max(hi[k], m->xyz[v * d + k]);
+    }
+  double ext = 0.0;
+  for (int k = 0; k < d; ++k) ext = std::max(ext, hi[k] - lo[k]);
+  if (!(ext > 0.0)) ext = 1.0;
+  const double scale = (double)((1ull << (d == 3 ? 21 : 31)) - 1) / ext;
+  std::vector<uint64_t> key((size_t)m->nc);
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < m->nc; ++c) {
+    uint64_t code = 0;
+    for (int k = 0; k < d; ++k) {
+      double x = 0.0;
+      for (int v = 0; v < nv; ++v) x += m->xyz[(int64_t)m->cells[c * nv + v] * d + k];
+      code |= fb_spread_bits((uint64_t)((x / nv - lo[k]) * scale), d) << k;
+    }
+    key[c] = code;
+  }
+  std::stable_sort(m->cell_order.begin(), m->cell_order.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+  return m->cell_order;
 }

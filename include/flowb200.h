@@ -142,7 +142,8 @@ int fb_mat_solve_cg(fb_mat *mat, int ncomp, const double *b, double *x, int64_t 
 enum fb_format { FB_FORMAT_CSR = 0, FB_FORMAT_TILE = 1 };
 int fb_mat_set_format(fb_mat *mat, int format);
 /* host-only self check of the tile format of a space's pattern (no device needed): the format must reproduce the CSR
- * pattern exactly.  stats[6]: tiles, entries incl. padding, sum of union sizes, max rows / entries / union per tile */
+ * pattern exactly.  stats[9]: tiles, entries incl. padding, sum of union sizes, max rows / entries / union per tile, and
+ * the row / entry / union caps of the kernel configuration */
 int fb_space_tile_check(fb_space *space, int64_t *stats);
 int fb_mat_format_info(fb_mat *mat, int *format, int64_t *ntiles, int64_t *entries, int64_t *union_columns);
 /* SpMV micro-benchmark on resident data: runs `reps` products, returns avg ms and algorithmic bytes */

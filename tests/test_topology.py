@@ -125,12 +125,12 @@ def test_tile_format_reproduces_csr_pattern(dim, degree):
 
     mesh = d.UnitSquareMesh(37, 29, "crossed") if dim == 2 else d.UnitCubeMesh(11, 9, 13)
     V = d.FunctionSpace(mesh, "CG", degree)
-    stats = np.zeros(6, dtype=np.int64)
+    stats = np.zeros(9, dtype=np.int64)
     _lib.check(_lib.lib.fb_space_tile_check(V.handle(), _lib.as_pi64(stats)), mesh.ctx, "fb_space_tile_check")
-    nt, nent, usum, max_r, max_e, max_u = [int(x) for x in stats]
+    nt, nent, usum, max_r, max_e, max_u, cap_r, cap_e, cap_u = [int(x) for x in stats]
     nnz = _lib.i64()
     _lib.lib.fb_space_pattern(V.handle(), C.byref(nnz), None, None)
-    assert nt >= 1 and nnz.value <= nent < nnz.value + 8 * nt
-    assert max_r <= 256 and max_e <= 6144 and max_u <= 1280
+    assert nt >= 1 and nnz.value <= nent < nnz.value + 8 * nt + 3 * V.dim()  # rows padded to 4 entries, tiles to 8
+    assert max_r <= cap_r and max_e <= cap_e and max_u <= cap_u
     # locality: a tile's column union stays far below one column per entry (this is what the format buys)
-    assert usum < 0.45 * nnz.value or nt == 1
+    assert usum < 0.5 * nnz.value or nt == 1
