@@ -9,9 +9,9 @@
 struct TileFormat {
   int64_t nrows = 0, ntiles = 0, nent = 0, union_total = 0;
   int cfg = 0;           // kernel configuration the tiles were sized for (fb_tile.cu TileCfg)
-  DBuf<int> desc;        // ntiles * 8: row0, nr, e0, ne_pad, u0, nu, -, -
+  DBuf<int> desc;        // ntiles * 8: row0, nr, e0, ne, u0, nu, g0, ng
   DBuf<int> rowid;       // tile-order row -> canonical row
-  DBuf<int> rptr;        // per tile nr + 1 entry offsets relative to e0
+  DBuf<int> gptr;        // per tile ng + 1 entry offsets of its 8-row groups, relative to e0
   DBuf<int> ucol;        // column unions (canonical node ids)
   DBuf<uint16_t> lidx;   // nent
   DBuf<int> src;         // nent: CSR slot of the entry (-1: padding) -- used to (re)pack values

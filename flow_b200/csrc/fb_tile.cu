@@ -3,16 +3,22 @@
 // (pressure_correction.py:451-464 velocity correction, and the inner solves of the momentum preconditioner).
 //
 // Why a second format.  The row-wise CSR kernel (k_spmm_u) gathers x[col] straight from global memory: ~29 gathers of
-// 24 bytes per row, each a separate 32-byte sector.  ncu showed it bound by L1 wavefronts (L1/TEX 89 % busy, DRAM 41 %),
-// not by HBM.  Here the rows are grouped into TILES of spatially close nodes (Morton order of the node coordinates,
-// a private row order of this format -- x and y keep the canonical numbering of the ABI):
-//   * the union of the columns a tile touches (~3 nodes per row instead of 29) is gathered ONCE into shared memory
-//     with cp.async (LDGSTS), one tile ahead;
-//   * the entries are stored tile by tile as fp64 value + 16-bit index into that union (10 bytes per entry instead
-//     of 12) and streamed into shared memory by the TMA unit (cp.async.bulk + mbarrier), one tile ahead, with an
-//     L2 evict-first policy so that x stays L2 resident;
-//   * the products run from shared memory; L1 only serves the union gather.
-// One persistent CTA per SM, two stages.  Algorithmic bytes stay those of scalar CSR.
+// 24 bytes per row, each a separate 32-byte sector.  ncu showed it bound by the L1 data pipe (L1/TEX 89 % busy, DRAM
+// 41 %), not by HBM.  Here the rows are grouped into TILES of spatially close nodes (Morton order of the node
+// coordinates, a private row order of this format -- x and y keep the canonical numbering of the ABI):
+//   * the union of the columns a tile touches (3.5 - 4.5 nodes per row instead of 29) is gathered ONCE into shared
+//     memory with cp.async (LDGSTS, 16 + 8 bytes per node), one tile ahead;
+//   * entries are (fp64 value, 16-bit slot in that union): 10 bytes instead of 12.  Inside a tile the rows are sorted
+//     by length and stored in groups of 8 rows x 4 lanes, step-major (SELL-8x4): step s of a group is 32 consecutive
+//     entries, one per lane of the warp that owns the group -> the value / index streams are perfectly coalesced and
+//     a warp's trip count is uniform;
+//   * the entries of each row are ordered so that the 32 shared-memory gathers of one step spread evenly over the
+//     16 bank pairs (see tile_format_build_host): ~2.3 wavefronts per gather instruction instead of 4.5;
+//   * the entry stream reaches the SM either through the TMA unit (cp.async.bulk + mbarrier into a shared-memory
+//     stage, evict-first in L2) or by coalesced streaming loads (ld.global.cs) -- TileCfg::TMA.  Measured on B200
+//     (profiles/r2_tile_spmm_*.txt): the TMA writes into shared memory occupy the same L1 data pipe as the loads that
+//     read them back, so which one wins is decided by measurement, not by principle.
+// Algorithmic bytes stay those of scalar CSR.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -24,41 +30,44 @@
 namespace {
 
 constexpr int TILE_T = 4;      // lanes per row
-constexpr int TILE_DESC = 8;   // ints per tile descriptor
+constexpr int TILE_G = 8;      // rows per group (one warp)
+constexpr int TILE_DESC = 8;   // ints per tile descriptor: row0, nr, e0, ne, u0, nu, g0, ng
 
-// Kernel configurations (threads per CTA, entry / union caps per tile, pipeline stages, CTAs per SM).  A tile is one
-// pass of the block: at most THREADS / TILE_T rows.  What bounds the kernel is the number of bytes in flight per SM
-// (HBM needs ~45 KB per SM outstanding at all times), i.e. (stages - 1) x CTAs per SM tile loads.
+// Kernel configurations.  A tile is one pass of the block: at most THREADS / TILE_T rows, one warp per group of 8.
 template <int ID>
 struct TileCfg;
 template <>
-struct TileCfg<0> {  // one big CTA per SM, one tile ahead
-  static constexpr int THREADS = 1024, ECAP = 6144, UCAP = 1280, NSTAGE = 2, CTAS = 1;
+struct TileCfg<0> {  // TMA-streamed entries, two CTAs per SM, one tile ahead each
+  static constexpr int THREADS = 512, ECAP = 3328, UCAP = 768, NSTAGE = 2, CTAS = 2, TMA = 1;
 };
 template <>
-struct TileCfg<1> {  // two CTAs per SM, one tile ahead each
-  static constexpr int THREADS = 512, ECAP = 3072, UCAP = 768, NSTAGE = 2, CTAS = 2;
+struct TileCfg<1> {  // streaming loads, two CTAs per SM
+  static constexpr int THREADS = 512, ECAP = 1 << 20, UCAP = 768, NSTAGE = 2, CTAS = 2, TMA = 0;
 };
 template <>
-struct TileCfg<2> {  // one CTA per SM, three tiles ahead
-  static constexpr int THREADS = 512, ECAP = 3072, UCAP = 768, NSTAGE = 4, CTAS = 1;
+struct TileCfg<2> {  // streaming loads, three CTAs per SM
+  static constexpr int THREADS = 512, ECAP = 1 << 20, UCAP = 768, NSTAGE = 2, CTAS = 3, TMA = 0;
 };
 template <>
-struct TileCfg<3> {  // four small CTAs per SM
-  static constexpr int THREADS = 256, ECAP = 1536, UCAP = 448, NSTAGE = 2, CTAS = 4;
+struct TileCfg<3> {  // streaming loads, one big CTA per SM (smallest column unions)
+  static constexpr int THREADS = 1024, ECAP = 1 << 20, UCAP = 1280, NSTAGE = 2, CTAS = 1, TMA = 0;
 };
 template <>
-struct TileCfg<4> {  // two CTAs per SM, two tiles ahead each
-  static constexpr int THREADS = 256, ECAP = 1792, UCAP = 512, NSTAGE = 3, CTAS = 2;
+struct TileCfg<4> {  // streaming loads, six small CTAs per SM
+  static constexpr int THREADS = 256, ECAP = 1 << 20, UCAP = 448, NSTAGE = 2, CTAS = 6, TMA = 0;
 };
-constexpr int TILE_NCFG = 5;
+template <>
+struct TileCfg<5> {  // TMA-streamed entries, one big CTA per SM
+  static constexpr int THREADS = 1024, ECAP = 6656, UCAP = 1280, NSTAGE = 2, CTAS = 1, TMA = 1;
+};
+constexpr int TILE_NCFG = 6;
 
 struct TileCaps {
-  int threads, ecap, ucap, nstage, ctas;
+  int threads, ecap, ucap, nstage, ctas, tma;
 };
 template <int ID>
 constexpr TileCaps caps_of() {
-  return TileCaps{TileCfg<ID>::THREADS, TileCfg<ID>::ECAP, TileCfg<ID>::UCAP, TileCfg<ID>::NSTAGE, TileCfg<ID>::CTAS};
+  return TileCaps{TileCfg<ID>::THREADS, TileCfg<ID>::ECAP, TileCfg<ID>::UCAP, TileCfg<ID>::NSTAGE, TileCfg<ID>::CTAS, TileCfg<ID>::TMA};
 }
 inline TileCaps tile_caps(int id) {
   switch (id) {
@@ -66,7 +75,8 @@ inline TileCaps tile_caps(int id) {
     case 1: return caps_of<1>();
     case 2: return caps_of<2>();
     case 3: return caps_of<3>();
-    default: return caps_of<4>();
+    case 4: return caps_of<4>();
+    default: return caps_of<5>();
   }
 }
 
@@ -102,14 +112,17 @@ __device__ __forceinline__ void cp_async8(void *dst, const void *src) {
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 // the NC values of node `col` -> xs[slot * NC ..]; NC = 3: 24 bytes at a multiple of 24, i.e. one 16-byte and one
-// 8-byte piece in an order that depends on the parity of the node (source and destination have the same parity
-// only if col and slot do: otherwise three 8-byte pieces)
+// 8-byte piece whose order depends on the parity of the node; slot parity == column parity by construction
 template <int NC>
 __device__ __forceinline__ void gather_node(double *xs, int slot, const double *x, int col) {
   double *dst = xs + slot * NC;
   const double *src = x + (int64_t)col * NC;
-  if (NC == 3) {  // slot parity == column parity by construction (tile_format_build_host)
+  if (NC == 3) {
     if (col & 1) {
       cp_async8(dst, src);
       cp_async16(dst + 1, src + 1);
@@ -120,22 +133,17 @@ __device__ __forceinline__ void gather_node(double *xs, int slot, const double *
   } else if (NC == 2) {
     cp_async16(dst, src);
   } else {
-#pragma unroll
-    for (int c = 0; c < NC; ++c) cp_async8(dst + c, src + c);
+    cp_async8(dst, src);
   }
-}
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 struct TileArgs {
   int ntiles;
-  const int *desc;          // ntiles * TILE_DESC: row0, nr, e0, ne_pad, u0, nu, -, -
+  const int *desc;          // ntiles * TILE_DESC
   const int *rowid;         // tile-order row -> canonical row
-  const int *rptr;          // per tile nr + 1 offsets relative to e0, stored at row0 + tile
-  const int *ucol;          // union column lists
-  const uint16_t *lidx;     // entries: index into the tile's union
+  const int *gptr;          // per tile ng + 1 entry offsets of its row groups, relative to e0 (multiples of 32)
+  const int *ucol;          // union column lists (-1: unused slot)
+  const uint16_t *lidx;     // entries: slot in the tile's union
   const double *tval;       // entries: values (packed from the CSR values, see k_tile_pack)
   const uint8_t *mask;      // per dof: identity row (may be null)
   const double *x;
@@ -150,9 +158,9 @@ struct TileArgs {
 
 template <int NC, class CFG>
 struct TileSmem {
-  static constexpr int VAL_BYTES = CFG::ECAP * 8;
+  static constexpr int VAL_BYTES = CFG::TMA ? CFG::ECAP * 8 : 0;
   static constexpr int X_BYTES = CFG::UCAP * NC * 8;
-  static constexpr int IDX_BYTES = CFG::ECAP * 2;
+  static constexpr int IDX_BYTES = CFG::TMA ? CFG::ECAP * 2 : 0;
   static constexpr int STAGE = (VAL_BYTES + X_BYTES + IDX_BYTES + 127) / 128 * 128;
   static constexpr int TOTAL = CFG::NSTAGE * STAGE + 64;
 };
@@ -163,18 +171,21 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::CTAS) k_tile_spmm(const Til
   extern __shared__ __align__(128) unsigned char smem[];
   using L = TileSmem<NC, CFG>;
   constexpr int NS = CFG::NSTAGE, THREADS = CFG::THREADS;
+  constexpr bool TMA = CFG::TMA != 0;
   static_assert(CFG::UCAP <= 2 * THREADS, "two union columns per thread");
   if (a.flag && *a.flag) return;
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + NS * L::STAGE);
   const int tid = threadIdx.x;
-  if (tid == 0) {
+  if (TMA) {
+    if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < NS; ++s) mbar_init(&bar[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      for (int s = 0; s < NS; ++s) mbar_init(&bar[s], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  uint64_t policy;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  uint64_t policy = 0;
+  if (TMA) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
 
   auto stage_val = [&](int s) { return reinterpret_cast<double *>(smem + s * L::STAGE); };
   auto stage_x = [&](int s) { return reinterpret_cast<double *>(smem + s * L::STAGE + L::VAL_BYTES); };
@@ -189,10 +200,10 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::CTAS) k_tile_spmm(const Til
       if (tid + THREADS < nu) c1 = a.ucol[u0 + tid + THREADS];
     }
   };
-  // start the loads of tile t into stage s: TMA for the entries, cp.async gather for the x union
+  // start the loads of tile t into stage s: TMA for the entries (if staged), cp.async gather for the x union
   auto issue = [&](int t, int s, int c0, int c1) {
     if (t < a.ntiles) {
-      if (tid == 0) {
+      if (TMA && tid == 0) {
         const int e0 = a.desc[t * TILE_DESC + 2], ne = a.desc[t * TILE_DESC + 3];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of this stage are done
         mbar_expect_tx(&bar[s], (uint32_t)ne * 10u);
@@ -217,20 +228,21 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::CTAS) k_tile_spmm(const Til
     issue(t + k * G, k, c0, c1);
   }
   load_ucols(t + (NS - 1) * G, c0, c1);
-  const int lane = tid % TILE_T, rl = tid / TILE_T;
+  const int lane32 = tid & 31, warp = tid >> 5, lane = tid % TILE_T, rl = tid / TILE_T;
   for (int it = 0; t < a.ntiles; t += G, ++it) {
     const int s = it % NS;
     // NS - 1 tiles ahead: entries by TMA, x union by cp.async; NS tiles ahead: the union column ids into registers
     issue(t + (NS - 1) * G, (it + NS - 1) % NS, c0, c1);
     load_ucols(t + NS * G, c0, c1);
     // this tile's row data (global, coalesced) while its stage completes
-    const int row0 = a.desc[t * TILE_DESC + 0], nr = a.desc[t * TILE_DESC + 1];
-    int eb = 0, ee = 0, row = -1;
-    if (rl < nr) {
-      eb = a.rptr[row0 + t + rl];
-      ee = a.rptr[row0 + t + rl + 1];
-      row = a.rowid[row0 + rl];
+    const int *dsc = a.desc + t * TILE_DESC;
+    const int row0 = dsc[0], nr = dsc[1], e0 = dsc[2], g0 = dsc[6], ng = dsc[7];
+    int kb = 0, ke = 0, row = -1;
+    if (warp < ng) {
+      kb = a.gptr[g0 + warp];
+      ke = a.gptr[g0 + warp + 1];
     }
+    if (rl < nr) row = a.rowid[row0 + rl];
     double wv = 0.0, xd = 0.0;
     bool masked = false;
     if (row >= 0 && lane < NC) {
@@ -241,19 +253,31 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::CTAS) k_tile_spmm(const Til
     }
     cp_async_wait<NS - 1>();
     __syncthreads();  // every thread's part of the x union has landed
-    mbar_wait(&bar[s], (uint32_t)(it / NS) & 1u);
-    const double *vs = stage_val(s);
+    if (TMA) mbar_wait(&bar[s], (uint32_t)(it / NS) & 1u);
     const double *xs = stage_x(s);
-    const uint16_t *is = stage_idx(s);
     double acc[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+    if (TMA) {
+      const double *vs = stage_val(s);
+      const uint16_t *is = stage_idx(s);
 #pragma unroll 4
-    for (int k = eb + lane; k < ee; k += TILE_T) {
-      const double av = vs[k];
-      const int j = is[k];
+      for (int k = kb + lane32; k < ke; k += 32) {
+        const double av = vs[k];
+        const int j = is[k];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) acc[c] += av * xs[j * NC + c];
+        for (int c = 0; c < NC; ++c) acc[c] += av * xs[j * NC + c];
+      }
+    } else {
+      const double *vg = a.tval + e0;
+      const uint16_t *ig = a.lidx + e0;
+#pragma unroll 4
+      for (int k = kb + lane32; k < ke; k += 32) {
+        const double av = __ldcs(vg + k);
+        const int j = __ldcs(ig + k);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] += av * xs[j * NC + c];
+      }
     }
 #pragma unroll
     for (int c = 0; c < NC; ++c)
@@ -325,7 +349,8 @@ void launch_tile_nc(fb_ctx *ctx, const TileArgs &a, int dot_mode, int cfg) {
     case 1: return launch_tile_dot<NC, TileCfg<1>>(ctx, a, dot_mode);
     case 2: return launch_tile_dot<NC, TileCfg<2>>(ctx, a, dot_mode);
     case 3: return launch_tile_dot<NC, TileCfg<3>>(ctx, a, dot_mode);
-    default: return launch_tile_dot<NC, TileCfg<4>>(ctx, a, dot_mode);
+    case 4: return launch_tile_dot<NC, TileCfg<4>>(ctx, a, dot_mode);
+    default: return launch_tile_dot<NC, TileCfg<5>>(ctx, a, dot_mode);
   }
 }
 
@@ -364,7 +389,7 @@ static int tile_default_cfg() {
 
 // Host side of the format: tiles of the owned rows of s's node pattern (pure host code, once per space).
 struct HostTile {
-  std::vector<int> desc, order, rptr, ucol, src;
+  std::vector<int> desc, order, gptr, ucol, src;
   std::vector<uint16_t> lidx;
   int ntiles = 0;
 };
@@ -402,40 +427,61 @@ static void tile_format_build_host(fb_space *s, HostTile &h, const TileCaps &cap
   key.clear();
   key.shrink_to_fit();
 
-  std::vector<int> &desc = h.desc, &rptr = h.rptr, &ucol = h.ucol, &src = h.src;
+  std::vector<int> &desc = h.desc, &gptr = h.gptr, &ucol = h.ucol, &src = h.src;
   std::vector<uint16_t> &lidx = h.lidx;
-  rptr.reserve((size_t)n + n / 128 + 16);
+  auto rowlen = [&](int r) { return (int)(ip[r + 1] - ip[r]); };
+  // entries of a tile whose rows (sorted by length, descending) are order[row0 .. row0 + nr): groups of 8 rows, each
+  // padded to the steps of its longest row
+  auto tile_entries = [&](int64_t row0, int nr) {
+    int total = 0;
+    for (int i = 0; i < nr; i += TILE_G) total += 32 * ((rowlen(order[row0 + i]) + TILE_T - 1) / TILE_T);
+    return total;
+  };
   // ---- phase 1 (sequential): tiles = runs of rows in Morton order, grown until one of the caps binds
   std::vector<int> mark((size_t)nn, -1);
   std::vector<int> ulist;
   ulist.reserve(TILE_UCAP);
   int64_t pos = 0, etotal = 0;
-  int tile = 0;
+  int tile = 0, stamp = 0;
   while (pos < n) {
-    ulist.clear();
-    int nr = 0, ne = 0, n_even = 0, n_odd = 0;
     const int64_t row0 = pos;
-    while (pos < n && nr < TILE_RCAP) {
-      const int r = order[pos];
-      const int len = (int)(ip[r + 1] - ip[r]);
-      if (len > TILE_ECAP || len > TILE_UCAP || len > 256) throw fb_cuda_error(FB_EINVAL, "tile format: matrix row too long");
-      if (ne + ((len + 3) & ~3) > TILE_ECAP) break;
-      // slots keep the parity of their column (16-byte gathers, see gather_node): the union occupies
-      // 2 * max(#even, #odd) slots
-      int fe = 0, fo = 0;
-      for (int64_t k = ip[r]; k < ip[r + 1]; ++k)
-        if (mark[ix[k]] != tile) (ix[k] & 1) ? ++fo : ++fe;
-      if (2 * std::max(n_even + fe, n_odd + fo) > TILE_UCAP) break;
-      n_even += fe;
-      n_odd += fo;
-      for (int64_t k = ip[r]; k < ip[r + 1]; ++k)
-        if (mark[ix[k]] != tile) {
-          mark[ix[k]] = tile;
-          ulist.push_back(ix[k]);
-        }
-      ne += (len + 3) & ~3;
-      ++nr;
-      ++pos;
+    int rcap = TILE_RCAP, nr = 0, n_even = 0, n_odd = 0;
+    for (;;) {  // (re)grow with a smaller row cap until the padded entries fit the stage
+      ulist.clear();
+      nr = n_even = n_odd = 0;
+      pos = row0;
+      int ne = 0;
+      ++stamp;
+      while (pos < n && nr < rcap) {
+        const int r = order[pos];
+        const int len = rowlen(r);
+        if (len > TILE_UCAP || len > 256 || 32 * ((len + 3) / 4) > TILE_ECAP) throw fb_cuda_error(FB_EINVAL, "tile format: matrix row too long");
+        if (ne + ((len + 3) & ~3) > TILE_ECAP) break;
+        // slots keep the parity of their column (16-byte gathers, see gather_node): the union occupies
+        // 2 * max(#even, #odd) slots
+        int fe = 0, fo = 0;
+        for (int64_t k = ip[r]; k < ip[r + 1]; ++k)
+          if (mark[ix[k]] != stamp) (ix[k] & 1) ? ++fo : ++fe;
+        if (2 * std::max(n_even + fe, n_odd + fo) > TILE_UCAP) break;
+        n_even += fe;
+        n_odd += fo;
+        for (int64_t k = ip[r]; k < ip[r + 1]; ++k)
+          if (mark[ix[k]] != stamp) {
+            mark[ix[k]] = stamp;
+            ulist.push_back(ix[k]);
+          }
+        ne += (len + 3) & ~3;
+        ++nr;
+        ++pos;
+      }
+      // rows of similar length next to each other: a warp runs the trip count of the longest of its 8 rows
+      // (vertex rows of a P2 pattern are ~3x longer than edge rows)
+      std::stable_sort(order.begin() + row0, order.begin() + row0 + nr, [&](int a, int b) { return rowlen(a) > rowlen(b); });
+      if (tile_entries(row0, nr) <= TILE_ECAP || nr <= TILE_G) break;
+      // undo the sort's effect on later attempts: the run is re-sorted by Morton position implicitly because the
+      // retry takes a PREFIX of the same rows only if they are back in Morton order
+      std::stable_sort(order.begin() + row0, order.begin() + row0 + nr, [&](int a, int b) { return a < b; });
+      rcap = std::max(TILE_G, (nr - TILE_G) & ~(TILE_G - 1));
     }
     std::sort(ulist.begin(), ulist.end());
     {  // even columns -> even slots, odd columns -> odd slots (ascending within each class), -1 in unused slots
@@ -452,74 +498,72 @@ static void tile_format_build_host(fb_space *s, HostTile &h, const TileCaps &cap
       }
       ulist.swap(slots);
     }
-    // rows of similar length next to each other: the TILE_T lanes of 8 rows share a warp and run the longest row's
-    // trip count (vertex rows of a P2 pattern are ~3x longer than edge rows)
-    std::stable_sort(order.begin() + row0, order.begin() + row0 + nr,
-                     [&](int a, int b) { return ip[a + 1] - ip[a] > ip[b + 1] - ip[b]; });
-    // rows are padded to a multiple of 4 entries (their 32-byte value segments stay aligned), tiles to 8 (TMA)
+    const int ng = (nr + TILE_G - 1) / TILE_G;
+    const int g0 = (int)gptr.size();
     int off = 0;
-    for (int i = 0; i < nr; ++i) {
-      const int r = order[row0 + i];
-      rptr.push_back(off);
-      off += ((int)(ip[r + 1] - ip[r]) + 3) & ~3;
+    for (int g = 0; g < ng; ++g) {
+      gptr.push_back(off);
+      off += 32 * ((rowlen(order[row0 + g * TILE_G]) + TILE_T - 1) / TILE_T);
     }
-    rptr.push_back(off);
-    const int ne_pad = (off + 7) & ~7;
-    const int d8[TILE_DESC] = {(int)row0, nr, (int)etotal, ne_pad, (int)ucol.size(), (int)ulist.size(), 0, 0};
+    gptr.push_back(off);
+    const int d8[TILE_DESC] = {(int)row0, nr, (int)etotal, off, (int)ucol.size(), (int)ulist.size(), g0, ng};
     desc.insert(desc.end(), d8, d8 + TILE_DESC);
     ucol.insert(ucol.end(), ulist.begin(), ulist.end());
-    etotal += ne_pad;
+    etotal += off;
     ++tile;
-    if (etotal > (int64_t)INT32_MAX - TILE_ECAP) throw fb_cuda_error(FB_EINVAL, "tile format: too many entries");
+    if (etotal > (int64_t)INT32_MAX - (1 << 22)) throw fb_cuda_error(FB_EINVAL, "tile format: too many entries");
   }
   mark.clear();
   mark.shrink_to_fit();
   lidx.assign((size_t)etotal, 0);
   src.assign((size_t)etotal, -1);
-  // ---- phase 2 (parallel over tiles): entries.
-  // Entry order inside the rows.  A warp holds TILE_T lanes of 8 consecutive rows; at step s lane l of row i reads
-  // entry 4 s + l of its row and gathers x from shared memory at slot * NC * 8 bytes.  Shared memory serves 16
-  // distinct 8-byte bank pairs per wavefront, and (NC * slot + c) mod 16 is a bijection of slot mod 16 for NC = 1, 3,
-  // so the 32 gathers of one instruction need the minimum of 2 wavefronts iff every residue class slot mod 16 is
-  // used exactly twice.  The sum over a row does not depend on the order of its entries: the rows of each group of
-  // 8 are emitted step by step, every lane taking the remaining entry of its row whose class is used least so far
-  // in that step (CSR order: 3.8-way conflicts measured).  Padding entries: zero value, slot of the row's first entry.
+  // ---- phase 2 (parallel over tiles): entries, step-major inside each group of 8 rows: entry (step s, row i, lane l)
+  // of a group sits at 32 s + 4 i + l, i.e. at the lane of the warp that reads it.
+  // Entry order inside the rows.  At step s lane l of row i gathers x from shared memory at slot * NC * 8 bytes.
+  // Shared memory serves 16 distinct 8-byte bank pairs per wavefront, and (NC * slot + c) mod 16 is a bijection of
+  // slot mod 16 for NC = 1, 3, so the 32 gathers of one instruction need the minimum of 2 wavefronts iff every residue
+  // class slot mod 16 is used exactly twice.  The sum over a row does not depend on the order of its entries: the
+  // rows of a group are emitted step by step, every lane taking the remaining entry of its row whose class is used
+  // least so far in that step (CSR order: 3.8-way conflicts measured).  Padding entries: zero value, a gathered slot.
 #pragma omp parallel
   {
     std::vector<uint16_t> lid((size_t)nn, 0);
 #pragma omp for schedule(dynamic, 16)
     for (int t = 0; t < tile; ++t) {
       const int *d = &desc[(size_t)t * TILE_DESC];
-      const int row0 = d[0], nr = d[1], e0 = d[2], u0 = d[4], nu = d[5];
+      const int row0 = d[0], nr = d[1], e0 = d[2], u0 = d[4], nu = d[5], g0 = d[6], ng = d[7];
+      int any_slot = 0;
       for (int j = 0; j < nu; ++j)
-        if (ucol[u0 + j] >= 0) lid[ucol[u0 + j]] = (uint16_t)j;
-      const int *rp = &rptr[(size_t)row0 + t];
-      for (int i0 = 0; i0 < nr; i0 += 8) {
-        const int i1 = std::min(nr, i0 + 8);
-        int ent[8][256], cls[8][256], left[8], maxpad = 0;  // remaining entries of the 8 rows (CSR slot, class)
-        for (int i = i0; i < i1; ++i) {
-          const int r = order[row0 + i];
+        if (ucol[u0 + j] >= 0) {
+          lid[ucol[u0 + j]] = (uint16_t)j;
+          any_slot = j;
+        }
+      for (int g = 0; g < ng; ++g) {
+        const int i0 = g * TILE_G, i1 = std::min(nr, i0 + TILE_G);
+        const int gb = gptr[g0 + g], nsteps = (gptr[g0 + g + 1] - gb) / 32;
+        int ent[TILE_G][256], cls[TILE_G][256], left[TILE_G], pad_slot[TILE_G];
+        for (int q = 0; q < TILE_G; ++q) {
+          left[q] = 0;
+          pad_slot[q] = any_slot;
+          if (i0 + q >= i1) continue;
+          const int r = order[row0 + i0 + q];
           int m = 0;
           for (int64_t k = ip[r]; k < ip[r + 1]; ++k, ++m) {
-            ent[i - i0][m] = (int)k;
-            cls[i - i0][m] = lid[ix[k]] & 15;
+            ent[q][m] = (int)k;
+            cls[q][m] = lid[ix[k]] & 15;
           }
-          left[i - i0] = m;
-          maxpad = std::max(maxpad, rp[i + 1] - rp[i]);
+          left[q] = m;
+          if (m) pad_slot[q] = lid[ix[ip[r]]];
         }
-        for (int st4 = 0; st4 < maxpad; st4 += 4) {
+        for (int st = 0; st < nsteps; ++st) {
           int count[16] = {0};
-          for (int i = i0; i < i1; ++i) {
-            const int q = i - i0, r = order[row0 + i];
-            for (int l = 0; l < 4; ++l) {
-              const int p = st4 + l;
-              if (p >= rp[i + 1] - rp[i]) continue;
-              const size_t at = (size_t)e0 + rp[i] + p;
+          for (int q = 0; q < TILE_G; ++q)
+            for (int l = 0; l < TILE_T; ++l) {
+              const size_t at = (size_t)e0 + gb + 32 * st + TILE_T * q + l;
               if (left[q] == 0) {  // padding
-                const int fs = lid[ix[ip[r]]];
-                lidx[at] = (uint16_t)fs;
+                lidx[at] = (uint16_t)pad_slot[q];
                 src[at] = -1;
-                count[fs & 15]++;
+                count[pad_slot[q] & 15]++;
                 continue;
               }
               int best = 0;
@@ -533,7 +577,6 @@ static void tile_format_build_host(fb_space *s, HostTile &h, const TileCaps &cap
               cls[q][best] = cls[q][left[q] - 1];
               --left[q];
             }
-          }
         }
       }
     }
@@ -551,7 +594,7 @@ void tile_format_build(fb_space *s, TileFormat &tf, cudaStream_t st) {
   tf.union_total = (int64_t)h.ucol.size();
   tf.desc.upload(h.desc.data(), h.desc.size(), st);
   tf.rowid.upload(h.order.data(), h.order.size(), st);
-  tf.rptr.upload(h.rptr.data(), h.rptr.size(), st);
+  tf.gptr.upload(h.gptr.data(), h.gptr.size(), st);
   tf.ucol.upload(h.ucol.data(), h.ucol.size(), st);
   tf.lidx.upload(h.lidx.data(), h.lidx.size(), st);
   tf.src.upload(h.src.data(), h.src.size(), st);
@@ -559,8 +602,9 @@ void tile_format_build(fb_space *s, TileFormat &tf, cudaStream_t st) {
 }
 
 // Host-only self check (works in a context without a device): build the format and verify that it is the CSR pattern
-// -- every owned row exactly once, ucol[lidx] == CSR columns in CSR order, src == CSR slots, caps and TMA alignment
-// respected.  stats: ntiles, entries incl. padding, sum of union sizes, max rows, max entries, max union.
+// -- every owned row exactly once, each row's entries a permutation of its CSR row (ucol[lidx] == CSR column,
+// src == CSR slot) at the positions its lanes read, padding only zero-valued, caps and TMA alignment respected.
+// stats: ntiles, entries incl. padding, sum of union slots, max rows, max entries, max union, row / entry / union caps.
 extern "C" int fb_space_tile_check(fb_space *s, int64_t *stats) {
   if (!s) return FB_EINVAL;
   try {
@@ -569,56 +613,67 @@ extern "C" int fb_space_tile_check(fb_space *s, int64_t *stats) {
     const int TILE_RCAP = cap.threads / TILE_T, TILE_ECAP = cap.ecap, TILE_UCAP = cap.ucap;
     tile_format_build_host(s, h, cap);
     const int64_t n = s->n_owned;
+    fb_ctx *ctx = s->mesh->ctx;
     std::vector<uint8_t> seen((size_t)n, 0);
-    int64_t max_r = 0, max_e = 0, max_u = 0, rp = 0;
+    int64_t max_r = 0, max_e = 0, max_u = 0, rows = 0;
     for (int t = 0; t < h.ntiles; ++t) {
       const int *d = &h.desc[(size_t)t * TILE_DESC];
-      const int row0 = d[0], nr = d[1], e0 = d[2], ne = d[3], u0 = d[4], nu = d[5];
-      if (nr < 1 || nr > TILE_RCAP || ne > TILE_ECAP || nu > TILE_UCAP || (e0 & 7) || (ne & 7)) return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: caps/alignment");
-      if (rp != row0 + t) return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: rptr layout");
+      const int row0 = d[0], nr = d[1], e0 = d[2], ne = d[3], u0 = d[4], nu = d[5], g0 = d[6], ng = d[7];
+      if (nr < 1 || nr > TILE_RCAP || ne > TILE_ECAP || nu > TILE_UCAP || (e0 & 31) || (ne & 31)) return fb_fail(ctx, FB_EINVAL, "tile check: caps/alignment");
+      if (row0 != rows || ng != (nr + TILE_G - 1) / TILE_G || h.gptr[g0] != 0 || h.gptr[g0 + ng] != ne) return fb_fail(ctx, FB_EINVAL, "tile check: layout");
       for (int j = 0; j < nu; ++j) {  // slot parity == column parity, ascending within each parity class, gaps are -1
         const int c = h.ucol[u0 + j];
-        if (c >= 0 && ((c ^ j) & 1)) return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: slot parity");
-        if (c >= 0 && j >= 2 && h.ucol[u0 + j - 2] >= c) return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: union order");
+        if (c >= 0 && ((c ^ j) & 1)) return fb_fail(ctx, FB_EINVAL, "tile check: slot parity");
+        if (c >= 0 && j >= 2 && h.ucol[u0 + j - 2] >= c) return fb_fail(ctx, FB_EINVAL, "tile check: union order");
       }
       for (int i = 0; i < nr; ++i) {
         const int r = h.order[row0 + i];
-        if (r < 0 || r >= n || seen[r]) return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: row covered twice");
+        if (r < 0 || r >= n || seen[r]) return fb_fail(ctx, FB_EINVAL, "tile check: row covered twice");
         seen[r] = 1;
-        const int eb = h.rptr[rp + i], ee = h.rptr[rp + i + 1];
+        const int g = i / TILE_G, q = i % TILE_G;
+        const int gb = h.gptr[g0 + g], nsteps = (h.gptr[g0 + g + 1] - gb) / 32;
         const int len = (int)(s->indptr[r + 1] - s->indptr[r]);
-        if ((eb & 3) || ee - eb != ((len + 3) & ~3)) return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: row length / alignment");
         std::vector<int> slots_seen;
-        for (int k = eb; k < ee; ++k) {
-          const int sl = h.src[e0 + k], li = h.lidx[e0 + k];
-          if (li >= nu || h.ucol[u0 + li] < 0) return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: entry points at an empty slot");
-          if (sl < 0) continue;  // padding: zero value, any gathered slot
-          if (sl < s->indptr[r] || sl >= s->indptr[r + 1] || h.ucol[u0 + li] != s->indices[sl])
-            return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: entry mismatch");
-          slots_seen.push_back(sl);
-        }
+        for (int st = 0; st < nsteps; ++st)
+          for (int l = 0; l < TILE_T; ++l) {
+            const size_t at = (size_t)e0 + gb + 32 * st + TILE_T * q + l;
+            const int sl = h.src[at], li = h.lidx[at];
+            if (li >= nu || h.ucol[u0 + li] < 0) return fb_fail(ctx, FB_EINVAL, "tile check: entry points at an empty slot");
+            if (sl < 0) continue;  // padding: zero value, any gathered slot
+            if (sl < s->indptr[r] || sl >= s->indptr[r + 1] || h.ucol[u0 + li] != s->indices[sl]) return fb_fail(ctx, FB_EINVAL, "tile check: entry mismatch");
+            slots_seen.push_back(sl);
+          }
         std::sort(slots_seen.begin(), slots_seen.end());
-        if ((int)slots_seen.size() != len || (len > 0 && (slots_seen.front() != (int)s->indptr[r] || slots_seen.back() != (int)s->indptr[r + 1] - 1)) ||
-            std::adjacent_find(slots_seen.begin(), slots_seen.end()) != slots_seen.end())
-          return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: row entries are not a permutation of the CSR row");
+        if ((int)slots_seen.size() != len || std::adjacent_find(slots_seen.begin(), slots_seen.end()) != slots_seen.end())
+          return fb_fail(ctx, FB_EINVAL, "tile check: row entries are not a permutation of the CSR row");
       }
-      rp += nr + 1;
+      // lanes of rows that do not exist (last group of the tile) only hold padding
+      for (int i = nr; i < ng * TILE_G; ++i) {
+        const int g = i / TILE_G, q = i % TILE_G;
+        const int gb = h.gptr[g0 + g], nsteps = (h.gptr[g0 + g + 1] - gb) / 32;
+        for (int st = 0; st < nsteps; ++st)
+          for (int l = 0; l < TILE_T; ++l) {
+            const size_t at = (size_t)e0 + gb + 32 * st + TILE_T * q + l;
+            if (h.src[at] >= 0 || h.lidx[at] >= nu || h.ucol[u0 + h.lidx[at]] < 0) return fb_fail(ctx, FB_EINVAL, "tile check: padding lane");
+          }
+      }
+      rows += nr;
       max_r = std::max<int64_t>(max_r, nr);
       max_e = std::max<int64_t>(max_e, ne);
       max_u = std::max<int64_t>(max_u, nu);
     }
     for (int64_t i = 0; i < n; ++i)
-      if (!seen[i]) return fb_fail(s->mesh->ctx, FB_EINVAL, "tile check: row missing");
+      if (!seen[i]) return fb_fail(ctx, FB_EINVAL, "tile check: row missing");
     if (stats) {
-      stats[6] = TILE_RCAP;
-      stats[7] = TILE_ECAP;
-      stats[8] = TILE_UCAP;
       stats[0] = h.ntiles;
       stats[1] = (int64_t)h.lidx.size();
       stats[2] = (int64_t)h.ucol.size();
       stats[3] = max_r;
       stats[4] = max_e;
       stats[5] = max_u;
+      stats[6] = TILE_RCAP;
+      stats[7] = TILE_ECAP;
+      stats[8] = TILE_UCAP;
     }
   } catch (const std::exception &e) {
     return fb_fail(s->mesh->ctx, FB_EINVAL, e.what());
@@ -641,7 +696,7 @@ void tile_spmm(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_
   a.ntiles = (int)tf.ntiles;
   a.desc = tf.desc.p;
   a.rowid = tf.rowid.p;
-  a.rptr = tf.rptr.p;
+  a.gptr = tf.gptr.p;
   a.ucol = tf.ucol.p;
   a.lidx = tf.lidx.p;
   a.tval = A.tval;
