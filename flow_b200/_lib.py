@@ -60,6 +60,7 @@ class NSOpts(C.Structure):
         ("momentum_inner_its", C.c_int),
         ("inner_fp32", C.c_int),
         ("newton_overshoot", C.c_double),
+        ("inner_chebyshev", C.c_int),
     ]
 
 

@@ -441,6 +441,7 @@ struct fb_ns {
   // FGMRES path (opts.momentum_solver == FB_GMRES): scalar operator S = M + theta dt mu/rho K of the inner CG
   fb_mat Ku;                 // scalar P2 stiffness (assembled on first use)
   DBuf<double> Sval, dinv_S, Sval_t;
+  ChebWork cheb;             // Chebyshev preconditioner on S (opts.inner_chebyshev)
   double S_key = -1.0;       // theta dt mu / rho of the current Sval
   uint64_t S_bc_hash = 0;
   FgmresWork fw;
@@ -565,6 +566,7 @@ int fb_ns_opts_default(fb_ns_opts *o) {
   o->momentum_inner_its = 4;
   o->inner_fp32 = 0;
   o->newton_overshoot = 1e-3;
+  o->inner_chebyshev = 1;
   return FB_OK;
 }
 
@@ -927,6 +929,12 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
         if (ns->Mu.tval.p) {  // same operator in tile order
           ns->Sval_t.alloc((size_t)ns->W->tile->nent);
           tile_pack(ctx, *ns->W->tile, ns->Sval.p, ns->Sval_t.p);
+          if (o.inner_chebyshev) {  // spectrum of D^-1 S for the polynomial preconditioner (set-up: S changed)
+            LinOp Sop = make_linop(ns->Mu, D, n_ubc > 0 ? ns->mask_u.p : nullptr);
+            Sop.val = ns->Sval.p;
+            Sop.tval = ns->Sval_t.p;
+            cheb_estimate_spectrum(ctx, Sop, ns->dinv_S.p, 12, &ns->cheb.lmin, &ns->cheb.lmax);
+          }
         }
         ns->S_key = c2;
         ns->S_bc_hash = bc_hash;
@@ -979,6 +987,23 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
           Inner32Call *c32 = static_cast<Inner32Call *>(self);
           inner32_apply(c32->ctx, *c32->in, v, z);
           *ii = c32->in->its;
+          return FB_OK;
+        };
+      }
+      struct ChebCall {
+        fb_ctx *ctx;
+        LinOp S;
+        const double *dinv;
+        ChebWork *w;
+        int degree;
+      } cheb{ctx, inner.S, ns->dinv_S.p, &ns->cheb, o.chebyshev_degree > 0 ? o.chebyshev_degree : 4};
+      if (o.inner_chebyshev && inner.S.tile && inner.S.tval && ns->cheb.lmax > 0.0 && !(o.inner_fp32 && ns->Sval32.p)) {
+        // fixed polynomial in S instead of CG iterations: degree - 1 products, each one fused kernel
+        pc.self = &cheb;
+        pc.apply = [](void *self, const double *v, double *z, int *ii) -> int {
+          ChebCall *c = static_cast<ChebCall *>(self);
+          cheb_apply(c->ctx, c->S, c->dinv, c->w->lmin, c->w->lmax, c->degree, v, z, *c->w);
+          *ii = c->degree - 1;
           return FB_OK;
         };
       }

@@ -702,3 +702,124 @@ int krylov_fgmres(fb_ctx *ctx, const LinOp &A, const FgmresPrecond &pc, const do
   if (inner_iters) *inner_iters = inner_total;
   return converged ? FB_OK : FB_ENOCONV_KRYLOV;
 }
+
+
+// ---------------------------------------------------------------- Chebyshev polynomial preconditioner
+namespace {
+__global__ void k_cheb_start(int64_t n, double inv_theta, const double *__restrict__ dinv, const double *__restrict__ v,
+                             double *__restrict__ d0, double *__restrict__ z) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double d = inv_theta * dinv[i] * v[i];
+    d0[i] = d;
+    if (z) z[i] = d;
+  }
+}
+__global__ void k_lanczos_seed(int64_t n, const uint8_t *__restrict__ mask, double *__restrict__ r) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    // deterministic pseudo-random start with all frequencies (hash of the index), zero on constrained dofs
+    uint64_t h = (uint64_t)i * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 29;
+    h *= 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 32;
+    r[i] = (mask && mask[i]) ? 0.0 : ((double)(h & 0xFFFFFF) / 8388608.0 - 1.0);
+  }
+}
+double dot_sync(fb_ctx *ctx, const double *x, const double *y, int64_t n) {
+  fb_device_state *dv = ctx->dev;
+  vec_dot(ctx, x, y, n, 44);
+  fb_allreduce_slots(ctx, 44, 1);
+  FB_CUDA(cudaMemcpyAsync(dv->host_pinned + 40, dv->red + 44, sizeof(double), cudaMemcpyDeviceToHost, dv->stream));
+  FB_CUDA(cudaStreamSynchronize(dv->stream));
+  return dv->host_pinned[40];
+}
+// number of eigenvalues of the symmetric tridiagonal (a, b) below x (Sturm sequence)
+int sturm_count(const std::vector<double> &a, const std::vector<double> &b, double x) {
+  int cnt = 0;
+  double q = 1.0;
+  for (size_t i = 0; i < a.size(); ++i) {
+    q = a[i] - x - (i > 0 ? b[i - 1] * b[i - 1] / (q != 0.0 ? q : 1e-300) : 0.0);
+    if (q < 0.0) ++cnt;
+  }
+  return cnt;
+}
+}  // namespace
+
+// Extreme eigenvalues of D^-1 A from `steps` iterations of preconditioned CG (Lanczos tridiagonal, host scalars; set-up
+// only).  The largest Ritz value converges fast and from below, the smallest from above: the returned interval is
+// widened by 5 % / 15 %.
+void cheb_estimate_spectrum(fb_ctx *ctx, const LinOp &A, const double *dinv, int steps, double *lmin, double *lmax) {
+  const int64_t n = A.ndofs(), nl = A.nlocal_dofs();
+  DBuf<double> r, z, p, Ap;
+  r.alloc((size_t)nl);
+  z.alloc((size_t)nl);
+  p.alloc((size_t)nl);
+  Ap.alloc((size_t)nl);
+  p.zero(ctx->dev->stream);
+  FB_LAUNCH(ctx, k_lanczos_seed, vgrid(ctx, n), 256, 0, n, A.mask, r.p);
+  // z = dinv .* r
+  FB_LAUNCH(ctx, k_cheb_start, vgrid(ctx, n), 256, 0, n, 1.0, dinv, r.p, z.p, (double *)nullptr);
+  vec_axpby(ctx, p.p, 1.0, z.p, 0.0, z.p, n);
+  double rz = dot_sync(ctx, r.p, z.p, n);
+  std::vector<double> alpha, beta;
+  for (int k = 0; k < steps && rz > 0.0; ++k) {
+    spmv(ctx, A, p.p, Ap.p);
+    const double pAp = dot_sync(ctx, p.p, Ap.p, n);
+    if (!(pAp > 0.0)) break;
+    const double al = rz / pAp;
+    vec_axpy(ctx, r.p, -al, Ap.p, n);
+    FB_LAUNCH(ctx, k_cheb_start, vgrid(ctx, n), 256, 0, n, 1.0, dinv, r.p, z.p, (double *)nullptr);
+    const double rz_new = dot_sync(ctx, r.p, z.p, n);
+    const double be = rz_new / rz;
+    alpha.push_back(al);
+    beta.push_back(be);
+    vec_axpby(ctx, p.p, 1.0, z.p, be, p.p, n);
+    if (!(rz_new > 1e-28 * rz)) break;
+    rz = rz_new;
+  }
+  const size_t m = alpha.size();
+  if (m == 0) throw fb_cuda_error(FB_ENAN, "cheb_estimate_spectrum: operator is not positive definite");
+  std::vector<double> a(m), b(m > 0 ? m - 1 : 0);
+  for (size_t j = 0; j < m; ++j) {
+    a[j] = 1.0 / alpha[j] + (j > 0 ? beta[j - 1] / alpha[j - 1] : 0.0);
+    if (j + 1 < m) b[j] = std::sqrt(beta[j]) / alpha[j];
+  }
+  double lo = 0.0, hi = 0.0;
+  for (size_t j = 0; j < m; ++j) {  // Gershgorin bracket of the tridiagonal
+    const double rad = (j > 0 ? std::fabs(b[j - 1]) : 0.0) + (j + 1 < m ? std::fabs(b[j]) : 0.0);
+    hi = std::max(hi, a[j] + rad);
+    lo = j == 0 ? a[j] - rad : std::min(lo, a[j] - rad);
+  }
+  auto kth = [&](int k) {  // k-th smallest eigenvalue by bisection
+    double x0 = lo, x1 = hi;
+    for (int it = 0; it < 200; ++it) {
+      const double xm = 0.5 * (x0 + x1);
+      if (sturm_count(a, b, xm) > k) x1 = xm; else x0 = xm;
+    }
+    return 0.5 * (x0 + x1);
+  };
+  const double emin = kth(0), emax = kth((int)m - 1);
+  *lmax = 1.05 * emax;
+  *lmin = std::max(0.85 * emin, 1e-6 * emax);
+}
+
+void cheb_apply(fb_ctx *ctx, const LinOp &A, const double *dinv, double lmin, double lmax, int degree, const double *v, double *z,
+                ChebWork &w) {
+  if (!A.tile || !A.tval) throw fb_cuda_error(FB_EINVAL, "cheb_apply: operator is not in tile format");
+  const int64_t n = A.ndofs(), nl = A.nlocal_dofs();
+  w.r.alloc((size_t)nl);
+  w.d0.alloc((size_t)nl);
+  w.d1.alloc((size_t)nl);
+  const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+  if (degree < 1) degree = 1;
+  FB_LAUNCH(ctx, k_cheb_start, vgrid(ctx, n), 256, 0, n, 1.0 / theta, dinv, v, w.d0.p, degree == 1 ? z : (double *)nullptr);
+  double rho_prev = 1.0 / sigma;
+  double *dk = w.d0.p, *dn = w.d1.p;
+  for (int k = 0; k + 1 < degree; ++k) {
+    const double rho = 1.0 / (2.0 * sigma - rho_prev);
+    if (A.halo) halo_exchange(ctx, *A.halo, dk, A.dofs_per_node());
+    tile_cheb_step(ctx, A, dk, k == 0 ? v : w.r.p, w.r.p, k == 0 ? nullptr : z, z, dn, dinv, rho * rho_prev, 2.0 * rho / delta,
+                   k + 2 == degree);
+    std::swap(dk, dn);
+    rho_prev = rho;
+  }
+}

@@ -95,6 +95,8 @@ void tile_format_build(fb_space *s, TileFormat &tf, cudaStream_t st);
 void tile_pack(fb_ctx *ctx, const TileFormat &tf, const double *val, double *tval);  // tval[k] = val[src[k]]
 void tile_spmm(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_mode, const double *w, int slot,
                const int *flag);
+void tile_cheb_step(fb_ctx *ctx, const LinOp &A, const double *d, const double *rin, double *rout, const double *zin, double *zout,
+                    double *dout, const double *dinv, double cdd, double cr, bool last);
 // build the space's tile format if needed and pack m's values for it; mat_repack after m.val changed
 void mat_enable_tile(fb_ctx *ctx, fb_mat &m);
 void mat_repack(fb_ctx *ctx, fb_mat &m);
@@ -201,6 +203,17 @@ struct FgmresWork {
 };
 int krylov_fgmres(fb_ctx *ctx, const LinOp &A, const FgmresPrecond &pc, const double *b, double *x, double atol, int maxit,
                   int m, FgmresWork &fw, int *iters, int *inner_iters);
+
+// Chebyshev polynomial preconditioner z = p_m(D^-1 A) D^-1 v for an SPD operator in tile format (fb_krylov.cu):
+// m - 1 products, each ONE kernel (the vector updates of the iteration live in the product's epilogue), no inner
+// products, no host synchronisation.  [lmin, lmax] bound the spectrum of D^-1 A (cheb_estimate_spectrum).
+struct ChebWork {
+  DBuf<double> r, d0, d1;
+  double lmin = 0.0, lmax = 0.0;
+};
+void cheb_estimate_spectrum(fb_ctx *ctx, const LinOp &A, const double *dinv, int lanczos_steps, double *lmin, double *lmax);
+void cheb_apply(fb_ctx *ctx, const LinOp &A, const double *dinv, double lmin, double lmax, int degree, const double *v, double *z,
+                ChebWork &w);
 
 // fp32 inner solver of the momentum preconditioner (fb_inner32.cu)
 struct Inner32 {

@@ -154,6 +154,12 @@ struct TileArgs {
   double *red;
   int slot;
   const int *flag;
+  // Chebyshev epilogue (DOT == 4): x = d_k; r' = r - A d_k; d' = c_dd d_k + c_r dinv r'; z' = z + d_k (+ d' in the
+  // last step); y is not written
+  const double *ch_rin = nullptr, *ch_zin = nullptr, *ch_dinv = nullptr;
+  double *ch_rout = nullptr, *ch_zout = nullptr, *ch_dout = nullptr;
+  double ch_cdd = 0.0, ch_cr = 0.0;
+  int ch_last = 0;
 };
 
 template <int NC, class CFG>
@@ -247,8 +253,9 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::CTAS) k_tile_spmm(const Til
     bool masked = false;
     if (row >= 0 && lane < NC) {
       const int64_t dof = (int64_t)row * NC + lane;
-      if (DOT >= 1) wv = a.w[dof];
-      if (DOT == 3 || a.mask) xd = a.x[dof];
+      if (DOT >= 1 && DOT <= 3) wv = a.w[dof];
+      if (DOT == 4) wv = a.ch_rin[dof];
+      if (DOT >= 3 || a.mask) xd = a.x[dof];
       if (a.mask) masked = a.mask[dof] != 0;
     }
     cp_async_wait<NS - 1>();
@@ -289,7 +296,20 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::CTAS) k_tile_spmm(const Til
       for (int c = 1; c < NC; ++c)
         if (lane == c) yc = acc[c];
       if (masked) yc = xd;
-      a.y[(int64_t)row * NC + lane] = yc;
+      if (DOT == 4) {
+        const int64_t dof = (int64_t)row * NC + lane;
+        const double rn = wv - yc;
+        const double dn = a.ch_cdd * xd + a.ch_cr * a.ch_dinv[dof] * rn;
+        double z = (a.ch_zin ? a.ch_zin[dof] : 0.0) + xd;
+        if (a.ch_last) z += dn;
+        a.ch_zout[dof] = z;
+        if (!a.ch_last) {
+          a.ch_rout[dof] = rn;
+          a.ch_dout[dof] = dn;
+        }
+      } else {
+        a.y[(int64_t)row * NC + lane] = yc;
+      }
       if (DOT == 1 || DOT == 2) d[0] += wv * yc;
       if (DOT == 2) d[1] += yc * yc;
       if (DOT == 3) {
@@ -301,7 +321,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::CTAS) k_tile_spmm(const Til
     __syncthreads();  // stage s is free again (it is refilled at the top of the next iteration)
   }
   cp_async_wait<0>();
-  if (DOT >= 1) {
+  if (DOT >= 1 && DOT <= 3) {
     if (DOT == 1) {
       double v1[1] = {d[0]};
       fb_grid_reduce<1>(v1, a.partials, a.counter, a.red, a.slot);
@@ -339,7 +359,8 @@ void launch_tile_dot(fb_ctx *ctx, const TileArgs &a, int dot_mode) {
   if (dot_mode == 0) launch_tile<NC, 0, CFG>(ctx, a);
   else if (dot_mode == 1) launch_tile<NC, 1, CFG>(ctx, a);
   else if (dot_mode == 2) launch_tile<NC, 2, CFG>(ctx, a);
-  else launch_tile<NC, 3, CFG>(ctx, a);
+  else if (dot_mode == 3) launch_tile<NC, 3, CFG>(ctx, a);
+  else launch_tile<NC, 4, CFG>(ctx, a);
 }
 
 template <int NC>
@@ -522,9 +543,10 @@ static void tile_format_build_host(fb_space *s, HostTile &h, const TileCaps &cap
   // Entry order inside the rows.  At step s lane l of row i gathers x from shared memory at slot * NC * 8 bytes.
   // Shared memory serves 16 distinct 8-byte bank pairs per wavefront, and (NC * slot + c) mod 16 is a bijection of
   // slot mod 16 for NC = 1, 3, so the 32 gathers of one instruction need the minimum of 2 wavefronts iff every residue
-  // class slot mod 16 is used exactly twice.  The sum over a row does not depend on the order of its entries: the
-  // rows of a group are emitted step by step, every lane taking the remaining entry of its row whose class is used
-  // least so far in that step (CSR order: 3.8-way conflicts measured).  Padding entries: zero value, a gathered slot.
+  // class slot mod 16 is used exactly once per half-warp (64-bit accesses are served half-warp by half-warp).  The sum
+  // over a row does not depend on the order of its entries: the rows of a group are emitted step by step, every lane
+  // taking the remaining entry of its row whose class is used least so far in its half-warp (CSR order: 3.8-way
+  // conflicts measured).  Padding entries: zero value, a gathered slot.
 #pragma omp parallel
   {
     std::vector<uint16_t> lid((size_t)nn, 0);
@@ -557,7 +579,9 @@ static void tile_format_build_host(fb_space *s, HostTile &h, const TileCaps &cap
         }
         for (int st = 0; st < nsteps; ++st) {
           int count[16] = {0};
-          for (int q = 0; q < TILE_G; ++q)
+          for (int q = 0; q < TILE_G; ++q) {
+            // 64-bit shared loads are served per half-warp (16 lanes = 4 rows): the classes are balanced within each
+            if (q == TILE_G / 2) std::fill(count, count + 16, 0);
             for (int l = 0; l < TILE_T; ++l) {
               const size_t at = (size_t)e0 + gb + 32 * st + TILE_T * q + l;
               if (left[q] == 0) {  // padding
@@ -577,6 +601,7 @@ static void tile_format_build_host(fb_space *s, HostTile &h, const TileCaps &cap
               cls[q][best] = cls[q][left[q] - 1];
               --left[q];
             }
+          }
         }
       }
     }
@@ -688,8 +713,7 @@ void tile_pack(fb_ctx *ctx, const TileFormat &tf, const double *val, double *tva
   FB_LAUNCH(ctx, k_tile_pack, (int)g, 256, 0, n, tf.src.p, val, tval);
 }
 
-void tile_spmm(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_mode, const double *w, int slot,
-               const int *flag) {
+static TileArgs tile_args(fb_ctx *ctx, const LinOp &A, const double *x, double *y, const double *w, int slot, const int *flag) {
   const TileFormat &tf = *A.tile;
   fb_device_state *dv = ctx->dev;
   TileArgs a;
@@ -709,10 +733,35 @@ void tile_spmm(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_
   a.red = dv->red;
   a.slot = slot;
   a.flag = flag;
+  return a;
+}
+
+static void tile_launch(fb_ctx *ctx, const LinOp &A, const TileArgs &a, int dot_mode) {
   switch (A.ncomp) {
-    case 1: return launch_tile_nc<1>(ctx, a, dot_mode, tf.cfg);
-    case 2: return launch_tile_nc<2>(ctx, a, dot_mode, tf.cfg);
-    case 3: return launch_tile_nc<3>(ctx, a, dot_mode, tf.cfg);
+    case 1: return launch_tile_nc<1>(ctx, a, dot_mode, A.tile->cfg);
+    case 2: return launch_tile_nc<2>(ctx, a, dot_mode, A.tile->cfg);
+    case 3: return launch_tile_nc<3>(ctx, a, dot_mode, A.tile->cfg);
     default: throw fb_cuda_error(FB_EINVAL, "tile_spmm: ncomp must be 1..3");
   }
+}
+
+void tile_spmm(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_mode, const double *w, int slot,
+               const int *flag) {
+  tile_launch(ctx, A, tile_args(ctx, A, x, y, w, slot, flag), dot_mode);
+}
+
+// One Chebyshev step fused into the product (see TileArgs): the caller refreshed the ghosts of d.
+void tile_cheb_step(fb_ctx *ctx, const LinOp &A, const double *d, const double *rin, double *rout, const double *zin, double *zout,
+                    double *dout, const double *dinv, double cdd, double cr, bool last) {
+  TileArgs a = tile_args(ctx, A, d, nullptr, nullptr, 0, nullptr);
+  a.ch_rin = rin;
+  a.ch_rout = rout;
+  a.ch_zin = zin;
+  a.ch_zout = zout;
+  a.ch_dout = dout;
+  a.ch_dinv = dinv;
+  a.ch_cdd = cdd;
+  a.ch_cr = cr;
+  a.ch_last = last ? 1 : 0;
+  tile_launch(ctx, A, a, 4);
 }

@@ -49,7 +49,7 @@ enum fb_scheme { FB_FORWARD_EULER = 0, FB_BACKWARD_EULER = 1, FB_CRANK_NICOLSON 
 enum fb_flags { FB_DEVICE_PTRS = 1, FB_ROTATIONAL = 2, FB_CHORIN = 4 };
 enum fb_forcing { FB_F_NONE = 0, FB_F_CONSTANT = 1, FB_F_NODAL = 2, FB_F_LOAD = 3 };
 enum fb_krylov { FB_BICGSTAB = 0, FB_GMRES = 1, FB_CG = 2 };
-enum fb_precond { FB_JACOBI = 0, FB_BLOCK_JACOBI = 1, FB_CHEBYSHEV = 2 /* reserved: not implemented, acts as FB_JACOBI */, FB_AMG = 3 };
+enum fb_precond { FB_JACOBI = 0, FB_BLOCK_JACOBI = 1, FB_CHEBYSHEV = 2 /* see fb_ns_opts.inner_chebyshev */, FB_AMG = 3 };
 
 /* ---- context ---------------------------------------------------------- */
 int fb_version(void);
@@ -168,7 +168,7 @@ typedef struct fb_ns_opts {
   int correction_maxit;  /* default 1000 */
   int gmres_restart;     /* restart length of the FB_GMRES solver: default 30 (PETSc default), at most 20 vectors are kept */
   int check_every;       /* Krylov iterations enqueued between host convergence checks */
-  int chebyshev_degree;  /* reserved (no Chebyshev preconditioner yet); ignored */
+  int chebyshev_degree;  /* degree of the Chebyshev preconditioner (inner_chebyshev), default 4 */
   int jacobian_reuse;    /* 0 (default): the reference's Newton iteration -- Jacobian of the current iterate at every
                             iteration, first iterate with |F|_2 < newton_atol accepted, updates solved to the tolerance
                             above, so that the iterates are those of the reference's Newton + LU (pressure_correction.py:
@@ -199,6 +199,11 @@ typedef struct fb_ns_opts {
                             of the linear tolerances = newton_overshoot * newton_atol.  Chord variant: the loop also runs
                             until |F|_2 < newton_overshoot * newton_atol (an iterate below newton_atol is still accepted
                             when further updates stagnate) */
+  int inner_chebyshev;   /* 1 (default): on meshes whose P2 operators run from the tile format, the preconditioner of the
+                            FB_GMRES momentum solver is a Chebyshev polynomial of degree chebyshev_degree in the Jacobi-scaled
+                            S = M + theta dt nu K (spectrum estimated by 12 Lanczos steps whenever S changes): degree - 1
+                            products with S, each ONE kernel (vector updates in the product's epilogue), no inner products,
+                            no host synchronisation.  0: momentum_inner_its CG iterations on S */
 } fb_ns_opts;
 
 typedef struct fb_ns_stats {

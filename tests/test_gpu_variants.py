@@ -24,6 +24,8 @@ VARIANTS = {
     "bicgstab": dict(momentum_solver="bicgstab"),
     "fgmres_inner8": dict(momentum_solver="fgmres", momentum_inner_its=8),
     "fgmres_inner_fp32": dict(momentum_solver="fgmres", inner_fp32=1),
+    "inner_cg": dict(inner_chebyshev=0),
+    "chebyshev_degree6": dict(chebyshev_degree=6),
     "chord": dict(CHORD),
     "chord_within_step_only": dict(jacobian_reuse=1, jacobian_across_steps=0, adaptive_forcing=0),
     "chord_extrapolated_start": dict(CHORD, extrapolate_guess=1),
