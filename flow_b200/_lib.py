@@ -255,15 +255,18 @@ class _PinnedBlock(object):
 
 
 def pinned_empty(ctx, n):
-    """float64 numpy array of length n in page-locked memory; returned to a pool when collected."""
+    """float64 numpy array of length n in page-locked memory; the block goes back to the pool only when the LAST
+    array that refers to its memory is collected.  numpy collapses the `.base` of derived views (reshape, slices) to
+    the array that owns the buffer interface, so the finalizer sits on that owner (`base`), not on the view handed
+    out: a view taken from the returned array keeps the block alive after the array itself is dropped."""
     import weakref
 
     nbytes = int(n) * 8
     free = _pinned_pool.setdefault(nbytes, [])
     blk = free.pop() if free else _PinnedBlock(ctx, nbytes)
-    arr = np.asarray(blk).view(np.float64)
-    weakref.finalize(arr, free.append, blk)
-    return arr
+    base = np.asarray(blk)
+    weakref.finalize(base, free.append, blk)
+    return base.view(np.float64)
 
 
 def state_array(ctx, n, threshold=1 << 16, zero=True):

@@ -67,14 +67,26 @@ struct fb_comm {
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
 };
 
-static bool load_nccl(fb_comm &c) {
+// Loads libnccl and resolves the entry points; on failure `why` holds dlerror()'s text (read ONCE: dlerror() clears its
+// state) and the handle is closed again.
+static bool load_nccl(fb_comm &c, std::string &why) {
   if (c.lib) return true;
   c.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
   if (!c.lib) c.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-  if (!c.lib) return false;
-#define FB_SYM(name)                                                   \
+  if (!c.lib) {
+    const char *e = dlerror();
+    why = e ? e : "libnccl.so.2 not found";
+    return false;
+  }
+#define FB_SYM(name)                                                        \
   c.name = reinterpret_cast<decltype(c.name)>(dlsym(c.lib, "nccl" #name)); \
-  if (!c.name) return false;
+  if (!c.name) {                                                            \
+    const char *e = dlerror();                                              \
+    why = e ? e : "missing symbol nccl" #name;                              \
+    dlclose(c.lib);                                                         \
+    c.lib = nullptr;                                                        \
+    return false;                                                           \
+  }
   FB_SYM(GetUniqueId)
   FB_SYM(CommInitRank)
   FB_SYM(CommDestroy)
@@ -114,7 +126,8 @@ extern "C" {
 int fb_comm_unique_id(void *id128) {
   if (!id128) return FB_EINVAL;
   fb_comm c;
-  if (!load_nccl(c)) return FB_ENCCL;
+  std::string why;
+  if (!load_nccl(c, why)) return FB_ENCCL;
   ncclUniqueId id;
   if (c.GetUniqueId(&id) != ncclSuccess) return FB_ENCCL;
   static_assert(sizeof(ncclUniqueId) == 128, "unexpected ncclUniqueId size");
@@ -127,9 +140,10 @@ int fb_comm_init(fb_ctx *ctx, int rank, int nranks, const void *id128) {
   if (!ctx->dev) return fb_fail(ctx, FB_ENODEVICE, "fb_comm_init: host-only context");
   if (ctx->comm) return fb_fail(ctx, FB_EINVAL, "fb_comm_init: communicator already initialised");
   fb_comm *c = new fb_comm();
-  if (!load_nccl(*c)) {
+  std::string why;
+  if (!load_nccl(*c, why)) {
     delete c;
-    return fb_fail(ctx, FB_ENCCL, std::string("fb_comm_init: cannot load NCCL: ") + (dlerror() ? dlerror() : "missing symbol"));
+    return fb_fail(ctx, FB_ENCCL, "fb_comm_init: cannot load NCCL: " + why);
   }
   ncclUniqueId id;
   std::memcpy(&id, id128, sizeof(id));

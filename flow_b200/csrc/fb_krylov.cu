@@ -310,6 +310,16 @@ int krylov_pcg(fb_ctx *ctx, const LinOp &A, const double *dinv, const double *b,
   fb_device_state *dv = ctx->dev;
   const int64_t n = A.ndofs();
   const int dist = fb_is_distributed(ctx) ? 1 : 0;
+  if (dist && warm) {
+    // warm starts take the reference norm from red[S_REF] (all-reduced) PLUS the squared Dirichlet values: that term
+    // must be the global sum on every rank as well, or the ranks stop at different iterations (cold starts fold the
+    // local value into the all-reduced start reduction instead)
+    FB_CUDA(cudaMemcpyAsync(dv->red + 45, &ref_extra2, sizeof(double), cudaMemcpyHostToDevice, dv->stream));
+    fb_allreduce_slots(ctx, 45, 1);
+    FB_CUDA(cudaMemcpyAsync(dv->host_pinned + 41, dv->red + 45, sizeof(double), cudaMemcpyDeviceToHost, dv->stream));
+    FB_CUDA(cudaStreamSynchronize(dv->stream));
+    ref_extra2 = dv->host_pinned[41];
+  }
   w.ensure(4, A.nlocal_dofs());
   double *r = w.v[0].p, *z = w.v[1].p, *p = w.v[2].p, *Ap = w.v[3].p;
   const int g = vgrid(ctx, n);

@@ -325,7 +325,9 @@ class Vector(object):
         self.a = array
 
     def __getitem__(self, k):
-        return self.a[k]
+        # DOLFIN's vector()[:] / get_local() hand out copies; a view would alias the (pooled, pinned) state buffer
+        r = self.a[k]
+        return r.copy() if isinstance(r, np.ndarray) else r
 
     def __setitem__(self, k, v):
         self.a[k] = v.a if isinstance(v, Vector) else v
@@ -434,7 +436,11 @@ class Function(object):
         raise NotImplementedError("point evaluation is not part of the hot path")
 
     def nodal(self):
-        """(nnodes, ncomp) view."""
+        """(nnodes, ncomp) copy of the nodal values."""
+        return self._vec.reshape(self.V.nodes.nnodes, self.V.ncomp).copy()
+
+    def nodal_view(self):
+        """(nnodes, ncomp) writable view of the nodal values (valid while this Function is alive)."""
         return self._vec.reshape(self.V.nodes.nnodes, self.V.ncomp)
 
 

@@ -13,25 +13,36 @@ class Heat(object):
     vertex-lumped mass matrix of heat.py:39-45."""
 
     def __init__(self, V, conv, kappa, rho, cp, bcs, source, supg_stabilization=False):
+        if isinstance(source, (int, float)):  # the reference's `source * v * dx` accepts plain numbers
+            source = Constant(float(source))
+        constant_source = isinstance(source, Constant)
         if supg_stabilization:
             assert conv is not None  # heat.py:74
-            if source is not None and not isinstance(source, (Constant, float, int)):
+            if source is not None and not constant_source:
                 raise NotImplementedError("SUPG with a non-constant source term")
         self.V = V
         self.bcs = bcs
         mesh, ns = V.mesh(), V.nodes
         src = None
-        if source is not None and not (isinstance(source, Constant) and float(source) == 0.0):
-            fn = source
-            deg = source.degree() if isinstance(source, (Expression, Constant)) else 2
+        if source is not None and not (constant_source and float(source) == 0.0):
+            if constant_source:
+                c0 = float(source)
+                fn, deg = (lambda X: np.full(X.shape[0], c0)), 0
+            elif isinstance(source, Function):
+                # P_k nodal function: integrate its interpolant (the load of a Function coefficient)
+                raise NotImplementedError("Function source terms: pass an Expression or a Constant")
+            else:
+                fn = source
+                deg = source.degree() if isinstance(source, Expression) else 2
             src = hostfem.load_vector(mesh.coordinates(), mesh.cells(), ns.cell_nodes, ns.nnodes, ns.degree, 1,
                                       lambda X: np.asarray(fn(X)).reshape(-1, 1), deg)
+        source_value = float(source) if constant_source else 0.0  # enters the SUPG residual term only
         h = _lib.vp()
         Wh = conv.function_space().handle() if conv is not None else None
         cv = _lib.as_pd(_lib.f64(conv._vec)) if conv is not None else None
         _lib.check(lib.fb_heat_create_supg(V.handle(), Wh, cv, float(kappa), float(rho), float(cp),
                                            _lib.as_pd(src) if src is not None else None, 1 if supg_stabilization else 0,
-                                           float(source) if source is not None else 0.0, C.byref(h)), mesh.ctx, "Heat")
+                                           source_value, C.byref(h)), mesh.ctx, "Heat")
         self._h = h
 
     def __del__(self):

@@ -117,3 +117,32 @@ def test_msh_reader(tmp_path):
     m2 = d.MshMesh(str(f))
     assert np.array_equal(m.cells(), m2.cells())
     assert m.node_space(2).nnodes == 5 + 8 and m.node_space(1).on_boundary.sum() == 4
+
+
+def test_pinned_block_outlives_views_of_a_dropped_function(monkeypatch):
+    """views derived from a pooled pinned array (numpy collapses their .base to the buffer owner) must keep
+    the block out of the pool; vector()[:] and nodal() hand out copies like DOLFIN."""
+    import gc
+
+    from flow_b200 import _lib
+
+    class FakeBlock(object):  # stands in for _PinnedBlock on a machine without a GPU
+        def __init__(self, ctx, nbytes):
+            self._mem = np.zeros(nbytes, dtype=np.uint8)
+            self.ptr, self.nbytes = None, nbytes
+            self.__array_interface__ = self._mem.__array_interface__
+
+    monkeypatch.setattr(_lib, "_PinnedBlock", FakeBlock)
+    monkeypatch.setattr(_lib, "_pinned_pool", {})
+    a = _lib.pinned_empty(None, 100)
+    a[:] = 1.0
+    view = a.reshape(50, 2)[:, 0]
+    del a
+    gc.collect()
+    assert _lib._pinned_pool[800] == []      # the view keeps the block alive
+    b = _lib.pinned_empty(None, 100)         # must be a different block
+    b[:] = 2.0
+    assert (view == 1.0).all()
+    del view
+    gc.collect()
+    assert len(_lib._pinned_pool[800]) == 1  # now it is back in the pool

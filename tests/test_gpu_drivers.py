@@ -167,7 +167,7 @@ def compute_boussinesq(target_time, nx=10, supg=False):
             u_bcs = [d.DirichletBC(W, (0.0, 0.0), "on_boundary")]
             # f = rho(theta_prev) * g, a nodal P2 vector field (theta lives on the same nodes as u)
             fvec = d.Function(W)
-            fvec.nodal()[:, 1] = rho(theta_prev.vector().get_local()) * g
+            fvec.nodal_view()[:, 1] = rho(theta_prev.vector().get_local()) * g
             try:
                 u1, p1 = ns.step(d.Constant(dt), {0: u0}, p0, u_bcs, [], rho(room_temp), d.Constant(mu), f={0: fvec, 1: fvec},
                                  verbose=False, tol=1.0e-10)

@@ -132,7 +132,7 @@ def boussinesq(steps):
         theta1 = stepper.step(theta, t, dt)
         t_heat += time.perf_counter() - th0
         f = d.Function(W)
-        f.nodal()[:, 1] = rho(theta.vector().get_local()) * g
+        f.nodal_view()[:, 1] = rho(theta.vector().get_local()) * g
         u, p = st.step(d.Constant(dt), {0: u}, p, ubcs, [], RHO_WATER, d.Constant(MU_WATER), {0: f, 1: f}, verbose=False)
         theta = theta1
         t += dt
