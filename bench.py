@@ -174,6 +174,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the opt-in variants")
     ap.add_argument("--variants", default="chord,inner_fp32", help="comma-separated opt-in variants to time beside the headline")
+    ap.add_argument("--partition", default="auto", choices=["auto", "rcb", "structured"],
+                    help="multi-GPU set-up: rcb = generic partition of the global mesh on every rank + replicated global pressure AMG; "
+                         "structured = per-rank cut-out of the lattice, no global arrays, per-rank AMG (auto: structured for n >= 100)")
     ap.add_argument("--node-order", default="canonical", choices=["canonical", "lexicographic"],
                     help="experimental: number the nodes by coordinate for cache locality (single GPU; default: the canonical "
                          "numbering of the oracle and the parity tests)")
@@ -211,17 +214,23 @@ def main():
     # ---- setup (untimed): mesh, spaces, patterns, constant operators
     t_setup = time.perf_counter()
     n = args.n
-    mesh = d.UnitCubeMesh(n, n, n)
-    if args.node_order != "canonical" and world == 1:
-        mesh.node_order = args.node_order
-    nu_global, np_global = 3 * mesh.node_space(2).nnodes, mesh.node_space(1).nnodes
+    nu_global, np_global = dof_counts(n)
+    partition = args.partition if args.partition != "auto" else ("structured" if n >= 100 else "rcb")
+    if world == 1 or partition == "rcb":
+        mesh = d.UnitCubeMesh(n, n, n)
+        if args.node_order != "canonical" and world == 1:
+            mesh.node_order = args.node_order
+        assert (3 * mesh.node_space(2).nnodes, mesh.node_space(1).nnodes) == (nu_global, np_global)
     if world > 1:
         # strong scaling: the SAME cavity, cells split by recursive coordinate bisection, one ghost-cell layer,
-        # halo exchange + all-reduced dots over NCCL (flow_b200/parallel.py, csrc/fb_comm.cu)
+        # halo exchange + all-reduced dots over NVLink peer memory / NCCL (flow_b200/parallel.py, csrc/fb_comm.cu).
+        # "rcb": every rank partitions the global mesh (and the pressure AMG is the replicated global hierarchy);
+        # "structured": every rank builds its part from a cut-out of the lattice, no global arrays (80 M dofs),
+        # pressure AMG per rank (additive Schwarz)
         from flow_b200 import parallel
 
         p2p = parallel.init_comm(ctx, rank, world, parallel.torch_broadcast(local_rank))
-        mesh = parallel.distributed_mesh(mesh, rank, world)
+        mesh = parallel.distributed_mesh(mesh, rank, world) if partition == "rcb" else parallel.structured_cube_mesh(n, rank, world)
     W = d.VectorFunctionSpace(mesh, "CG", 2)
     P = d.FunctionSpace(mesh, "CG", 1)
     bcs = cavity_bcs(d, W)
@@ -325,7 +334,7 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         which = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_kernel_traffic.json")))
         except Exception:
             tj = {}
         h = _lib.vp()
@@ -333,9 +342,14 @@ def main():
         avg_ = lambda k: float(np.mean([hh[k] for hh in timed]))  # noqa: E731
         cands = []
         # (kernel label, matrix index, ncomp, launches per step, key of the ncu traffic record)
-        specs = (("k_spmm_u<3,8,*,2> (scalar P2 operator x 3 components: inner CG of the momentum preconditioner, "
-                  "velocity-correction CG, mass products)", 1, 3,
-                  avg_("momentum_inner_its") + avg_("correction_its") + 2.0, "k_spmm_u<3,8,*,2>"),
+        lib.fb_ns_matrix(ns, 1, C.byref(h))
+        fmt = C.c_int()
+        lib.fb_mat_format_info(h, C.byref(fmt), None, None, None)
+        tiled = fmt.value == _lib.FORMAT_TILE
+        p2_kernel = "k_tile_spmm<3,*> (tile-CSR, TMA-streamed entries, x staged in shared memory)" if tiled else "k_spmm_u<3,8,*,2> (row-wise CSR)"
+        specs = ((p2_kernel + ": scalar P2 operator x 3 components -- Chebyshev / CG products of the momentum preconditioner, "
+                  "velocity-correction CG, mass products", 1, 3,
+                  avg_("momentum_inner_its") + avg_("correction_its") + 2.0, "k_tile_spmm<3>" if tiled else "k_spmm_u<3,8,*,2>"),
                  ("k_bspmv_u<3,16,*,4,1> (momentum Jacobian, row-planar block CSR)", 2, 1,
                   avg_("momentum_its") + avg_("newton_its") + 1.0 if avg_("momentum_inner_its") > 0
                   else 2.0 * avg_("momentum_its") + avg_("newton_its") + 1.0, "k_bspmv_u<3,16,*,4,1>"))
@@ -424,9 +438,11 @@ def main():
             "config": {
                 "workload": workload_string(n),
                 "node_order": args.node_order if world == 1 else "canonical",
-                "parallelism": "single GPU" if world == 1 else "mesh partitioned over %d GPUs (RCB, 1 ghost-cell layer, halo exchange + one all-reduce per "
+                "parallelism": "single GPU" if world == 1 else "mesh partitioned over %d GPUs (%s, 1 ghost-cell layer, halo exchange + one all-reduce per "
                                "Krylov reduction over %s); rank 0 holds %d local dofs"
-                               % (world, "NVLink peer-memory windows (own kernels)" if p2p else "NCCL", nu + npp),
+                               % (world, "generic RCB of the global mesh, replicated pressure AMG" if partition == "rcb" else
+                                  "lattice-aligned bisection built per rank without global arrays, per-rank pressure AMG",
+                                  "NVLink peer-memory windows (own kernels)" if p2p else "NCCL", nu + npp),
                 "l2_policy": "working set (Jacobian %.1f GB, scalar P2 operators 1.2 GB each) far exceeds the 126 MB L2"
                              % (6.9 * nu / 9923847.0),
             },

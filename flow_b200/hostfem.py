@@ -60,6 +60,12 @@ def structured_box(a, b, nx, ny, nz):
     xs = a[0] + (b[0] - a[0]) * np.arange(nx + 1) / nx
     ys = a[1] + (b[1] - a[1]) * np.arange(ny + 1) / ny
     zs = a[2] + (b[2] - a[2]) * np.arange(nz + 1) / nz
+    return structured_box_lattice(xs, ys, zs)
+
+
+def structured_box_lattice(xs, ys, zs):
+    """The same mesh on given lattice coordinates (a cut-out of a larger box keeps the larger box's coordinates)."""
+    nx, ny, nz = len(xs) - 1, len(ys) - 1, len(zs) - 1
     npl = (nx + 1) * (ny + 1)
     pts = np.empty((npl * (nz + 1), 3))
     pts[:, 0] = np.tile(xs, (ny + 1) * (nz + 1))

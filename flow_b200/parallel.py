@@ -53,7 +53,10 @@ class SpacePlan(object):
 class Partition(object):
     """Everything rank `rank` of `nranks` needs to build its local problem."""
 
-    def __init__(self, gmesh, rank, nranks, part=None):
+    def __init__(self, gmesh, rank, nranks, part=None, boundary_facet_filter=None):
+        """`boundary_facet_filter(vertex coordinates (nf, dim, dim)) -> bool mask` keeps only the facets of gmesh's
+        boundary that lie on the boundary of the DOMAIN; needed when gmesh is a cut-out of a larger mesh
+        (structured_cube_mesh), whose artificial cut faces are not boundary."""
         pts, cells = gmesh.coordinates(), gmesh.cells()
         self.rank, self.nranks = rank, nranks
         if part is None:
@@ -84,6 +87,12 @@ class Partition(object):
         g2l_cell = np.full(cells.shape[0], -1, dtype=np.int64)
         g2l_cell[self.local_cells] = np.arange(self.local_cells.size)
         keep = g2l_cell[bc_] >= 0
+        if boundary_facet_filter is not None and nb.value:
+            nvc = cells.shape[1]
+            # facet l of a cell: all its (ascending) vertices but the l-th
+            sel = np.arange(nvc)[None, :] != bl_[:, None]
+            fverts = cells[bc_][sel].reshape(nb.value, nvc - 1)
+            keep &= np.asarray(boundary_facet_filter(pts[fverts]), dtype=bool)
         self.bf_cell = g2l_cell[bc_[keep]].astype(np.int32)
         self.bf_local = bl_[keep].astype(np.int32).copy()
         self.plans = {2: self._plan(nodes2, owner2, lcn2, lown, lambda n: n),
@@ -133,6 +142,82 @@ def distributed_mesh(gmesh, rank, nranks, device=None, part=None):
                m.ctx, "fb_mesh_set_boundary_facets")
     m.partition = P
     m.global_mesh = gmesh
+    return m
+
+
+def cube_blocks(n, nparts):
+    """Recursive bisection of the n^3 hexahedra of UnitCubeMesh(n) into `nparts` index boxes aligned with the
+    hexahedra (all six tetrahedra of a hexahedron stay together): list of ((i0, j0, k0), (i1, j1, k1)), part p = p-th
+    box.  Same recursion as `rcb` (longest extent first, parts split nl : n - nl), but cut on lattice planes, so that
+    every rank can name the owner of any cell from its index alone -- no global arrays."""
+    out = []
+
+    def split(lo, hi, p0, m):
+        if m == 1:
+            out.append((p0, lo, hi))
+            return
+        ext = [hi[a] - lo[a] for a in range(3)]
+        axis = int(np.argmax(ext))
+        ml = m // 2
+        cut = lo[axis] + (ext[axis] * ml + m // 2) // m
+        cut = min(max(cut, lo[axis] + 1), hi[axis] - 1) if ext[axis] > 1 else lo[axis]
+        hi_l, lo_r = list(hi), list(lo)
+        hi_l[axis] = cut
+        lo_r[axis] = cut
+        split(lo, tuple(hi_l), p0, ml)
+        split(tuple(lo_r), hi, p0 + ml, m - ml)
+
+    split((0, 0, 0), (n, n, n), 0, nparts)
+    out.sort()
+    return [(lo, hi) for _, lo, hi in out]
+
+
+def cube_cell_part(n, nparts, i, j, k):
+    """Part of the hexahedra with lattice indices (i, j, k) under `cube_blocks`."""
+    part = np.full(np.shape(i), -1, dtype=np.int32)
+    for p, (lo, hi) in enumerate(cube_blocks(n, nparts)):
+        inside = (i >= lo[0]) & (i < hi[0]) & (j >= lo[1]) & (j < hi[1]) & (k >= lo[2]) & (k < hi[2])
+        part[inside] = p
+    return part
+
+
+def structured_cube_mesh(n, rank, nranks, device=None, layers=2):
+    """Rank-local mesh of the partitioned UnitCubeMesh(n) built WITHOUT the global mesh (80 M dofs and beyond: the
+    global P2 dof map alone is 0.8 GB per rank).  Every rank generates the cut-out of the lattice that covers its
+    block of hexahedra plus `layers` = 2 layers around it -- enough to know every cell that touches one of its nodes
+    (1 layer) and every cell that touches one of THOSE cells' nodes (2 layers, needed for the owners of its ghost
+    nodes) -- and runs the generic `Partition` on that cut-out with the analytic cell -> part map.  Vertex and edge
+    numbers of the cut-out are order-isomorphic to the global ones, so the halo lists of neighbouring ranks, each
+    sorted by its own cut-out numbers, line up.  Same result as distributed_mesh(UnitCubeMesh(n), part = the same
+    map), array for array (tests/test_parallel.py)."""
+    from . import hostfem
+    from .dolfin import Mesh
+
+    lo, hi = cube_blocks(n, nranks)[rank]
+    e0 = [max(0, lo[a] - layers) for a in range(3)]
+    e1 = [min(n, hi[a] + layers) for a in range(3)]
+    nx, ny, nz = (e1[a] - e0[a] for a in range(3))
+    # the generator on the sub-lattice, with the coordinates of the global generator (0.0 + 1.0 * i / n, bit for bit)
+    lat = [0.0 + (1.0 - 0.0) * np.arange(e0[a], e1[a] + 1) / n for a in range(3)]
+    pts, cells = hostfem.structured_box_lattice(lat[0], lat[1], lat[2])
+    idx = np.arange(nx * ny * nz)
+    kk, rem = np.divmod(idx, nx * ny)
+    jj, ii = np.divmod(rem, nx)
+    part = np.repeat(cube_cell_part(n, nranks, ii + e0[0], jj + e0[1], kk + e0[2]), 6)
+    sub = Mesh(pts, cells, device=device)
+
+    def on_domain_boundary(X):  # X: (nf, 3 vertices, 3 coordinates)
+        flat0 = (X == 0.0).all(axis=1).any(axis=1)
+        flat1 = (X == 1.0).all(axis=1).any(axis=1)
+        return flat0 | flat1
+
+    P = Partition(sub, rank, nranks, part=part, boundary_facet_filter=on_domain_boundary)
+    m = Mesh(P.points, P.cells, device=device)
+    _lib.check(lib.fb_mesh_set_boundary_facets(m.handle, P.bf_cell.size, _lib.as_pi32(P.bf_cell), _lib.as_pi32(P.bf_local)),
+               m.ctx, "fb_mesh_set_boundary_facets")
+    m.partition = P
+    m.global_mesh = None   # no replicated global operators: the pressure AMG is per rank (additive Schwarz)
+    m.global_counts = {"cells": 6 * n ** 3, "vertices": (n + 1) ** 3}
     return m
 
 

@@ -135,3 +135,37 @@ def test_halo_plans_move_ghosts_gloo_world2(tmp_path):
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+@pytest.mark.parametrize("n,R", [(5, 2), (6, 4), (7, 8), (5, 3)])
+def test_structured_cube_mesh_equals_generic_partition(n, R):
+    """parallel.structured_cube_mesh builds every rank's local problem from a cut-out of the lattice (no global
+    mesh); it must be, array for array, what the generic Partition makes of the global mesh with the same cell -> part
+    map: same local mesh, same numbering, same halo plans, same boundary facets."""
+    from flow_b200 import dolfin as d
+    from flow_b200 import parallel
+
+    blocks = parallel.cube_blocks(n, R)
+    cover = np.zeros((n, n, n), dtype=int)
+    for lo, hi in blocks:
+        cover[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] += 1
+    assert (cover == 1).all() and len(blocks) == R
+    sizes = [np.prod([hi[a] - lo[a] for a in range(3)]) for lo, hi in blocks]
+    assert max(sizes) <= 1.01 * (-(-n // 2) / (n // 2)) ** 3 * min(sizes) or R == 3  # cuts fall on lattice planes
+
+    g = d.UnitCubeMesh(n, n, n)
+    idx = np.arange(n ** 3)
+    kk, rem = np.divmod(idx, n * n)
+    jj, ii = np.divmod(rem, n)
+    part = np.repeat(parallel.cube_cell_part(n, R, ii, jj, kk), 6)
+    for r in range(R):
+        a = parallel.distributed_mesh(g, r, R, part=part)
+        b = parallel.structured_cube_mesh(n, r, R)
+        assert np.array_equal(a.coordinates(), b.coordinates()) and np.array_equal(a.cells(), b.cells())
+        assert np.array_equal(a.partition.bf_cell, b.partition.bf_cell) and np.array_equal(a.partition.bf_local, b.partition.bf_local)
+        for deg in (1, 2):
+            pa, pb = a.node_space(deg).plan, b.node_space(deg).plan
+            assert pa.n_owned == pb.n_owned
+            for name in ("perm", "ranks", "send_ptr", "send_nodes", "recv_ptr"):
+                assert np.array_equal(getattr(pa, name), getattr(pb, name)), (r, deg, name)
+            assert np.array_equal(a.node_space(deg).on_boundary, b.node_space(deg).on_boundary)
