@@ -166,7 +166,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=74, help="cells per edge of the unit cube (74 -> 10.3 M dofs)")
+    ap.add_argument("--n", "--cube-n", dest="n", type=int, default=74,
+                    help="cells per edge of the unit cube (74 -> 10.3 M dofs); under torchrun use --cube-n (torchrun's own parser "
+                         "takes --n for an abbreviation of its options)")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="stepping time the CPU arm may spend (it stops after the step that exceeds it)")
     ap.add_argument("--cpu-warmup", type=int, default=1, help="warm-up steps of the CPU arm (at most --warmup)")
     ap.add_argument("--cpu-sample-steps", type=int, default=1, help="timed steps of the cpu_baseline leg of the b200 arm")

@@ -61,6 +61,7 @@ class NSOpts(C.Structure):
         ("inner_fp32", C.c_int),
         ("newton_overshoot", C.c_double),
         ("inner_chebyshev", C.c_int),
+        ("semi_implicit", C.c_int),
     ]
 
 

@@ -567,6 +567,7 @@ int fb_ns_opts_default(fb_ns_opts *o) {
   o->inner_fp32 = 0;
   o->newton_overshoot = 1e-3;
   o->inner_chebyshev = 1;
+  o->semi_implicit = 0;
   return FB_OK;
 }
 
@@ -795,6 +796,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
   // ---- tentative velocity: Newton on F1(ui) = 0 (pressure_correction.py:147-255)
   FB_CUDA(cudaMemcpyAsync(ns->ui.p, ns->u0.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));  // :220
   MomentumArgs ma{dt, rho, mu, theta, ns->ui.p, ns->u0.p, ns->p0.p, ns->P->cell_nodes.p};
+  if (o.semi_implicit) ma.adv = ns->u0.p;  // (u0 . grad) ui: the step is linear in ui (pressure_correction.py:96-101)
   ns_build_Fconst(ns, ma, have_load);
   // A Jacobian from an earlier step is kept as the chord operator while nothing it depends on (other than the
   // linearisation point) changed and it still contracts as well as a fresh one did

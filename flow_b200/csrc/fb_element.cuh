@@ -123,8 +123,10 @@ FB_HD double fb_p2_mean(int a) {
 //                    + c1 ( phi_a phi_b d_j u_i - d_j phi_a phi_b u_i ) + c2 d_i phi_b d_j phi_a }
 // with c1 = theta*dt/2 and c2 = theta*dt*mu/rho   (derivative(F1, ui), pressure_correction.py:202)
 template <int D>
+// c1t: coefficient of the two terms that differentiate the ADVECTING velocity, ((grad u) delta, v) - ((grad v) delta, u);
+// c1t = c1 for the reference's fully implicit convection, 0 for the semi-implicit linearisation (u = advecting field)
 FB_HD void fb_jac_point(double w, double c1, double c2, double pa, double pb, const double ga[D], const double gb[D],
-                        const double u[D], const double gu[D][D], double J[D][D]) {
+                        const double u[D], const double gu[D][D], double J[D][D], double c1t_over_c1 = 1.0) {
   double uga = 0.0, ugb = 0.0, gab = 0.0;
   for (int k = 0; k < D; ++k) {
     uga += u[k] * ga[k];
@@ -133,7 +135,7 @@ FB_HD void fb_jac_point(double w, double c1, double c2, double pa, double pb, co
   }
   const double m = w * pa * pb;
   const double dg = m + w * (c1 * (ugb * pa - uga * pb) + c2 * gab);
-  const double c1m = c1 * m, c1wb = c1 * w * pb, c2w = c2 * w;
+  const double c1m = c1 * c1t_over_c1 * m, c1wb = c1 * c1t_over_c1 * w * pb, c2w = c2 * w;
   for (int i = 0; i < D; ++i)
     for (int j = 0; j < D; ++j) {
       double v = c1m * gu[i][j] - c1wb * ga[j] * u[i] + c2w * gb[i] * ga[j];
@@ -172,7 +174,8 @@ FB_HD void fb_p2_vertex_grad(int a, int w, const double glam[D + 1][D], double g
 template <int D>
 FB_HD void fb_jac_pair(double vol, double c1, double c2, const double *GA, const double *SA, const double *GB,
                        const double *SB, const double *WA, const double *WB, const double *GU, const double *m3,
-                       double J[D][D]) {
+                       double J[D][D], double c1t = -1.0) {
+  if (c1t < 0.0) c1t = c1;  // coefficient of T2 - T3 (terms differentiating the advecting velocity); 0: semi-implicit
   constexpr int NV = D + 1;
   const double lm = 1.0 / ((D + 1) * (D + 2));
   double gb[NV * D], wb[NV * D], mv[NV], sb[D];  // trial-node operands in registers (shared memory on the device)
@@ -223,7 +226,7 @@ FB_HD void fb_jac_pair(double vol, double c1, double c2, const double *GA, const
       }
       g *= lm;
       if (i == j) kab += g;
-      J[i][j] = c1 * (t2 - t3) + c2 * g;
+      J[i][j] = c1t * (t2 - t3) + c2 * g;
     }
   }
   const double dg = mab + c1 * (cab - cba) + c2 * kab;
@@ -242,12 +245,14 @@ FB_HD void fb_jac_pair(double vol, double c1, double c2, const double *GA, const
 //   R = -rho/2 [ ((grad u)u)_i phi_a - (u.grad phi_a) u_i ] - 2 mu eps(u)_ik d_k phi_a + p0 d_i phi_a
 // (pressure_correction.py:138-141).  Returns the value for component i.
 template <int D>
+// adv: advecting velocity at the point (null: u itself, the reference's form; semi-implicit linearisation: u0)
 FB_HD double fb_rhs_point(int i, double rho, double mu, double pa, const double ga[D], const double u[D],
-                          const double gu[D][D], double p0) {
+                          const double gu[D][D], double p0, const double *adv = nullptr) {
+  const double *wv = adv ? adv : u;
   double conv = 0.0, uga = 0.0, visc = 0.0;
   for (int k = 0; k < D; ++k) {
-    conv += gu[i][k] * u[k];
-    uga += u[k] * ga[k];
+    conv += gu[i][k] * wv[k];
+    uga += wv[k] * ga[k];
     visc += (gu[i][k] + gu[k][i]) * ga[k];
   }
   return -0.5 * rho * (conv * pa - uga * u[i]) - mu * visc + p0 * ga[i];

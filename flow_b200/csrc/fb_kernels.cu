@@ -1210,7 +1210,7 @@ __global__ void __launch_bounds__(128)
     k_momentum_F_thread(int64_t nc, const int *__restrict__ cell_nodes, const int *__restrict__ cells,
                         const double *__restrict__ xyz, double dt, double rho, double mu, const double *__restrict__ u,
                         const double *__restrict__ p0, const int *__restrict__ pcn, double cm, double cr,
-                        double *__restrict__ F) {
+                        double *__restrict__ F, const double *__restrict__ adv) {
   constexpr int NL = Elem<D>::NL2, NQ = Q5<D>::NQ;
   const double cdt = cr * dt / rho;
   const bool need_R = (cr != 0.0);
@@ -1235,12 +1235,22 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
       for (int m = 0; m <= D; ++m) lam[m] = Q5<D>::lam(q, m);
       const double w = Q5<D>::w(q) * vol;
-      double uq[D], gu[D][D], pq = 0.0;
+      double uq[D], gu[D][D], pq = 0.0, wq[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) {
         uq[i] = 0.0;
+        wq[i] = 0.0;
 #pragma unroll
         for (int k = 0; k < D; ++k) gu[i][k] = 0.0;
+      }
+      if (adv && need_R) {  // advecting velocity of the semi-implicit linearisation at the point
+#pragma unroll
+        for (int a = 0; a < NL; ++a) {
+          const double pa = fb_p2_phi<D>(a, lam);
+          const int64_t node = cn[a];
+#pragma unroll
+          for (int i = 0; i < D; ++i) wq[i] += adv[node * D + i] * pa;
+        }
       }
 #pragma unroll
       for (int v = 0; v <= D; ++v) pq += p0e[v] * lam[v];
@@ -1266,7 +1276,7 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
         for (int i = 0; i < D; ++i) {
           double v = cm * w * pa * uq[i];
-          if (need_R) v -= cdt * w * fb_rhs_point<D>(i, rho, mu, pa, ga, uq, gu, pq);
+          if (need_R) v -= cdt * w * fb_rhs_point<D>(i, rho, mu, pa, ga, uq, gu, pq, adv ? wq : nullptr);
           acc[a][i] += v;
         }
       }
@@ -1282,14 +1292,14 @@ __global__ void __launch_bounds__(128)
 
 template <int D>
 static void momentum_F_cells(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, const double *u, double cm, double cr,
-                             double *F) {
+                             double *F, const double *adv = nullptr) {
   static const int variant = getenv("FB_F_KERNEL") ? atoi(getenv("FB_F_KERNEL")) : 1;  // 0: warp per cell, 1: thread per cell
-  if (variant == 0) {
+  if (variant == 0 && !adv) {
     const int g = grid_for(W.nc * 32, MOM_WARPS * 32, ctx->dev->sm_count * 16);
     FB_LAUNCH(ctx, k_momentum_F<D>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, a.dt, a.rho, a.mu, u, a.p0, a.pcn, cm, cr, F);
   } else {
     const int g = grid_for(W.nc, 128, ctx->dev->sm_count * 16);
-    FB_LAUNCH(ctx, k_momentum_F_thread<D>, g, 128, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, a.dt, a.rho, a.mu, u, a.p0, a.pcn, cm, cr, F);
+    FB_LAUNCH(ctx, k_momentum_F_thread<D>, g, 128, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, a.dt, a.rho, a.mu, u, a.p0, a.pcn, cm, cr, F, adv);
   }
 }
 
@@ -1306,10 +1316,10 @@ void assemble_momentum_F_old_state(fb_ctx *ctx, const DevSpace &W, const Momentu
 void assemble_momentum_F_new_state(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F) {
   const int gf = grid_for(W.nbf * W.nl * W.dim, 128, ctx->dev->sm_count * 16);
   if (W.dim == 2) {
-    momentum_F_cells<2>(ctx, W, a, a.ui, 1.0, a.theta, F);
+    momentum_F_cells<2>(ctx, W, a, a.ui, 1.0, a.theta, F, a.adv);
     if (W.nbf) FB_LAUNCH(ctx, k_momentum_F_facets<2>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.cells.p, W.xyz.p, a, F);
   } else {
-    momentum_F_cells<3>(ctx, W, a, a.ui, 1.0, a.theta, F);
+    momentum_F_cells<3>(ctx, W, a, a.ui, 1.0, a.theta, F, a.adv);
     if (W.nbf) FB_LAUNCH(ctx, k_momentum_F_facets<3>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.cells.p, W.xyz.p, a, F);
   }
 }
@@ -1334,7 +1344,7 @@ __global__ void __launch_bounds__(MOM_WARPS * 32)
   for (int64_t c = warp0; c < nc; c += nwarps) {
     const int *cn = cell_nodes + c * NL;
     const double vol = mom_geometry<D>(s, wid, lane, cells + c * (D + 1), xyz);
-    mom_phase_a<D>(s, wid, lane, cn, a.ui, true, true);
+    mom_phase_a<D>(s, wid, lane, cn, a.adv ? a.adv : a.ui, true, true);
     double acc[R][D][D];
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -1362,7 +1372,7 @@ __global__ void __launch_bounds__(MOM_WARPS * 32)
             ga[k] = s.g[wid][q][pa_i][k];
             gb[k] = s.g[wid][q][pb_i][k];
           }
-          fb_jac_point<D>(w, c1, c2, s.phi[q][pa_i], s.phi[q][pb_i], ga, gb, u, gu, acc[r]);
+          fb_jac_point<D>(w, c1, c2, s.phi[q][pa_i], s.phi[q][pb_i], ga, gb, u, gu, acc[r], a.adv ? 0.0 : 1.0);
         }
       }
     }
@@ -1436,7 +1446,9 @@ __global__ void __launch_bounds__(MOM_WARPS * 32)
     // ---- phase A
     double glam[D + 1][D], vol;
     cell_geometry<D>(cells + c * (D + 1), xyz, glam, vol);  // every lane: broadcast loads, no staging
-    if (lane < NL * D) s.U[wid][lane / D][lane % D] = a.ui[(int64_t)cn[lane / D] * D + lane % D];
+    // semi-implicit linearisation: the Jacobian only sees the advecting field (and drops the terms that
+    // differentiate it: c1t = 0)
+    if (lane < NL * D) s.U[wid][lane / D][lane % D] = (a.adv ? a.adv : a.ui)[(int64_t)cn[lane / D] * D + lane % D];
     for (int t = lane; t < NL * NV; t += 32) {
       const int n = t / NV, w = t - n * NV;
       double g[D];
@@ -1483,7 +1495,8 @@ __global__ void __launch_bounds__(MOM_WARPS * 32)
         if (tb < NL) {
           const int slot = smap[c * NP + ta * NL + tb];  // issued before the block's arithmetic
           double J[D][D];
-          fb_jac_pair<D>(vol, c1, c2, GA, SA, s.GV[wid][tb], s.S[wid][tb], WA, s.WT[wid][tb], s.GU[wid], &s.M3[(ta * NL + tb) * NV], J);
+          fb_jac_pair<D>(vol, c1, c2, GA, SA, s.GV[wid][tb], s.S[wid][tb], WA, s.WT[wid][tb], s.GU[wid], &s.M3[(ta * NL + tb) * NV], J,
+                         a.adv ? 0.0 : c1);
           double *base = val + (int64_t)r0 * (D * D) + (int64_t)(slot - r0) * D;
 #pragma unroll
           for (int i = 0; i < D; ++i)

@@ -134,6 +134,7 @@ struct MomentumArgs {
   double dt, rho, mu, theta;
   const double *ui, *u0, *p0;
   const int *pcn;  // cell -> P1 dofs of the pressure space
+  const double *adv = nullptr;  // semi-implicit linearisation: advecting velocity of the new-state convection (null: ui)
 };
 void assemble_momentum_F(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F);  // zero + both parts
 void assemble_momentum_F_old_state(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F);  // += u0 part

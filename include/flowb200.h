@@ -204,6 +204,12 @@ typedef struct fb_ns_opts {
                             S = M + theta dt nu K (spectrum estimated by 12 Lanczos steps whenever S changes): degree - 1
                             products with S, each ONE kernel (vector updates in the product's epilogue), no inner products,
                             no host synchronisation.  0: momentum_inner_its CG iterations on S */
+  int semi_implicit;     /* 0 (default): the reference's fully implicit convection ((grad ui) ui, v) - ((grad v) ui, ui).
+                            1: semi-implicit linearisation ((grad ui) u0, v) - ((grad v) u0, ui), the (u^k . grad) u^{k+1}
+                            treatment the reference's notes recommend (pressure_correction.py:96-101, :204-219) but do not
+                            implement: the tentative-velocity system becomes linear in ui (one assembly and one linear
+                            solve per step) and keeps the skew-symmetric form; an O(dt) different discretisation, NOT the
+                            reference's numbers (parity: oracle variant of the same form) */
 } fb_ns_opts;
 
 typedef struct fb_ns_stats {

@@ -107,7 +107,7 @@ def _facet_rule(dim, degree):
     return out, fw
 
 
-def momentum_residual_jacobian(W, P, ui, u0, p0, load, dt, rho, mu, theta, want_J=True):
+def momentum_residual_jacobian(W, P, ui, u0, p0, load, dt, rho, mu, theta, want_J=True, semi_implicit=False):
     """F1 (pressure_correction.py:169-190) and J = derivative(F1, ui) (:202).
 
     theta = 0 / 1 / 0.5 for forward Euler / backward Euler / Crank-Nicolson.
@@ -128,12 +128,15 @@ def momentum_residual_jacobian(W, P, ui, u0, p0, load, dt, rho, mu, theta, want_
     vol = m.vol
     p0q = _es("qa,ca->cq", psi, p0[P.cell_nodes])
 
-    def cell_R(u):
+    def cell_R(u, adv=None):
+        # adv: advecting velocity of the convective term (None: u itself, the reference's form :138-139;
+        # semi-implicit option: u0, i.e. ((grad u) u0, v) - ((grad v) u0, u), cf. the notes at :96-101)
         U = u.reshape(-1, d)[W.cell_nodes]  # (c,a,i)
         uq = _es("qa,cai->cqi", phi, U)
         gu = _es("cqak,cai->cqik", g, U)  # d u_i / d x_k
-        conv1 = _es("cqik,cqk->cqi", gu, uq)  # (grad u) u
-        ugphi = _es("cqk,cqak->cqa", uq, g)  # u . grad phi_a
+        wq = uq if adv is None else _es("qa,cai->cqi", phi, adv.reshape(-1, d)[W.cell_nodes])
+        conv1 = _es("cqik,cqk->cqi", gu, wq)  # (grad u) w
+        ugphi = _es("cqk,cqak->cqa", wq, g)  # w . grad phi_a
         eps = 0.5 * (gu + np.swapaxes(gu, 2, 3))
         R = -rho * 0.5 * (
             _es("q,cqi,qa->cai", w, conv1, phi) - _es("q,cqa,cqi->cai", w, ugphi, uq)
@@ -148,7 +151,7 @@ def momentum_residual_jacobian(W, P, ui, u0, p0, load, dt, rho, mu, theta, want_
     Fe = _es("ab,cbi,c->cai", Mref, Ui - U0, vol)
     ctx = None
     if theta != 0.0:
-        Ri, ctx = cell_R(ui)
+        Ri, ctx = cell_R(ui, u0 if semi_implicit else None)
         Fe -= dt / rho * theta * Ri
     if theta != 1.0:
         R0, _ = cell_R(u0)
@@ -209,10 +212,11 @@ def momentum_residual_jacobian(W, P, ui, u0, p0, load, dt, rho, mu, theta, want_
         S = _es("q,cqb,qa->cab", w, ugphi, phi)
         S = (S - np.swapaxes(S, 1, 2)) * vol[:, None, None]
         Je += c1 * _es("cab,ij->caibj", S, eye)
-        # ((grad ui) delta, v): phi_a phi_b d_j ui_i
-        Je += c1 * _es("q,qa,qb,cqij,c->caibj", w, phi, phi, gu, vol)
-        # -((grad v) delta, ui): - d_j phi_a phi_b ui_i
-        Je -= c1 * _es("q,cqaj,qb,cqi,c->caibj", w, g, phi, uq, vol)
+        if not semi_implicit:  # the advecting velocity is u0: these two terms (its derivative) vanish
+            # ((grad ui) delta, v): phi_a phi_b d_j ui_i
+            Je += c1 * _es("q,qa,qb,cqij,c->caibj", w, phi, phi, gu, vol)
+            # -((grad v) delta, ui): - d_j phi_a phi_b ui_i
+            Je -= c1 * _es("q,cqaj,qb,cqi,c->caibj", w, g, phi, uq, vol)
         c2 = theta * dt / rho * mu
         # 2 eps(delta):eps(v) = delta_ij grad phi_a.grad phi_b + d_i phi_b d_j phi_a
         K = _es("q,cqak,cqbk,c->cab", w, g, g, vol)

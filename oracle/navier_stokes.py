@@ -19,8 +19,11 @@ class Stepper:
 
     order = {"velocity": 2.0, "pressure": 1.0}
 
-    def __init__(self, mesh, time_step_method="backward euler", rotational=False, chorin=False, linear="lu"):
+    def __init__(self, mesh, time_step_method="backward euler", rotational=False, chorin=False, linear="lu", semi_implicit=False):
         self.mesh = mesh
+        # semi_implicit: (u0 . grad) ui instead of (ui . grad) ui -- the linearisation the reference's notes discuss
+        # (:96-101, :204-219) but do not implement; oracle of the product's opts.semi_implicit
+        self.semi_implicit = semi_implicit
         self.linear = linear  # "lu": the reference's Newton+LU; "krylov": C/OpenMP Jacobi-Krylov (CPU timing)
         self.W = fem.Space(mesh, 2, mesh.dim)
         self.P = fem.Space(mesh, 1, 1)
@@ -45,7 +48,7 @@ class Stepper:
 
         def rj(x, want_J):
             return forms.momentum_residual_jacobian(
-                self.W, self.P, x, u0, p0, load, dt, rho, mu, theta, want_J=want_J
+                self.W, self.P, x, u0, p0, load, dt, rho, mu, theta, want_J=want_J, semi_implicit=self.semi_implicit
             )
 
         if self.linear == "tight-krylov":  # the LU iterates, computed without the (infeasible) 3D LU fill
@@ -96,8 +99,8 @@ def Chorin(mesh):
     return s
 
 
-def IPCS(mesh, time_step_method="backward euler", linear="lu"):
-    s = Stepper(mesh, time_step_method, rotational=False, linear=linear)
+def IPCS(mesh, time_step_method="backward euler", linear="lu", semi_implicit=False):
+    s = Stepper(mesh, time_step_method, rotational=False, linear=linear, semi_implicit=semi_implicit)
     s.order = {"velocity": 2.0, "pressure": 1.0}
     return s
 

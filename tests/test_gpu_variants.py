@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from oracle import fem
+from oracle import fem, forms
 from oracle import navier_stokes as ons
 
 pytestmark = pytest.mark.gpu
@@ -177,3 +177,53 @@ def test_coordinate_node_order_same_solution(gpu_ctx):
     assert np.linalg.norm(ub.reshape(-1, 3)[permW] - ua.reshape(-1, 3)) / np.linalg.norm(ua) < 1e-8
     da = pa - pa.mean()
     assert np.linalg.norm((pb - pb.mean())[permP] - da) / np.linalg.norm(da) < 1e-7
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_semi_implicit_option_matches_its_oracle_variant(gpu_ctx, dim):
+    """opts.semi_implicit = 1 ((u0 . grad) ui, the linearisation of pressure_correction.py:96-101): three steps against the
+    oracle's variant of the same form -- one Jacobian assembly and one Newton update per step, forcing and a component
+    (W.sub(0)-like full vector) Dirichlet condition included."""
+    from flow_b200 import dolfin as d
+    from flow_b200 import navier_stokes as nav
+
+    nav.reset_options()
+    nav.set_options(semi_implicit=1)
+    try:
+        if dim == 2:
+            om = fem.Mesh(*fem.unit_square_mesh(12, 10, "crossed"))
+            fvec, top = (0.3, -1.0), 1
+        else:
+            om = fem.Mesh(*fem.unit_cube_mesh(5, 4, 6))
+            fvec, top = (0.0, 0.2, -1.0), 2
+        ost = ons.IPCS(om, semi_implicit=True)
+        X = ost.W.node_coords
+        bd = ost.W.boundary_dofs()
+        g = np.zeros((ost.W.nnodes, dim))
+        lid = X[:, top] > 1.0 - 1e-12
+        g[lid, 0] = 4.0 * X[lid, 0] * (1.0 - X[lid, 0])
+        g = g.reshape(-1)
+        dt, rho, mu = 0.05, 1.2, 0.02
+        load = forms.mass_matrix(fem.Space(om, 2, 1))
+        import scipy.sparse as sp
+
+        lvec = sp.kron(load, sp.eye(dim)) @ np.tile(np.array(fvec), ost.W.nnodes)
+        m = d.Mesh(om.points, om.cells)
+        W = d.VectorFunctionSpace(m, "CG", 2)
+        P = d.FunctionSpace(m, "CG", 1)
+        bcs = [d.DirichletBC(W, d.Function(W, g.copy()), "on_boundary")]
+        f = d.Constant(fvec)
+        uo, po = np.zeros(ost.W.ndofs), np.zeros(ost.P.nnodes)
+        u, p = d.Function(W), d.Function(P)
+        for k in range(3):
+            uo, po = ost.step(dt, uo, po, (bd, g[bd]), None, rho, mu, lvec, lvec, tol=1e-11)
+            u, p = nav.IPCS().step(d.Constant(dt), {0: u}, p, bcs, [], d.Constant(rho), d.Constant(mu), {0: f, 1: f},
+                                   verbose=False, tol=1e-11)
+            s = nav.last_stats()
+            assert s["newton_its"] == 1 and s["jacobian_assemblies"] == 1, s
+            eu = np.linalg.norm(u._vec - uo) / np.linalg.norm(uo)
+            dp = (p._vec - p._vec.mean()) - (po - po.mean())
+            ep = np.linalg.norm(dp) / np.linalg.norm(po - po.mean())
+            assert eu < 1e-8 and ep < 1e-7, (dim, k, eu, ep)
+    finally:
+        nav.reset_options()

@@ -278,3 +278,29 @@ def test_scalar_operator_preconditioner_clusters_the_momentum_jacobian():
     _, info = sla.bicgstab(sla.LinearOperator(J.shape, matvec=op), b, rtol=1e-6, atol=0.0, maxiter=400)
     assert info == 0
     assert count[0] >= 3 * outer, (count[0], outer)  # measured on B200 at n = 74: 78 -> 22 Jacobian products per step
+
+
+def test_semi_implicit_linearisation_is_linear_and_consistent():
+    """Oracle variant of opts.semi_implicit ((u0 . grad) ui, pressure_correction.py:96-101): F1 is affine in ui (its
+    Jacobian does not depend on ui and one Newton update lands on the root), J = dF/dui by finite differences, and the
+    form coincides with the reference's at ui = u0."""
+    om = fem.Mesh(*fem.unit_cube_mesh(2, 2, 2))
+    W, P = fem.Space(om, 2, 3), fem.Space(om, 1, 1)
+    rng = np.random.default_rng(5)
+    u0, ua, ub = (rng.standard_normal(W.ndofs) for _ in range(3))
+    p0 = rng.standard_normal(P.nnodes)
+    load = np.zeros(W.ndofs)
+    args = (0.05, 1.3, 0.2, 1.0)
+    Fa, Ja = forms.momentum_residual_jacobian(W, P, ua, u0, p0, load, *args, semi_implicit=True)
+    Fb, Jb = forms.momentum_residual_jacobian(W, P, ub, u0, p0, load, *args, semi_implicit=True)
+    assert abs(Ja - Jb).max() < 1e-14                                    # J independent of ui
+    assert np.abs(Fb - Fa - Ja @ (ub - ua)).max() < 1e-12 * np.abs(Fb).max()  # affine
+    F0s, _ = forms.momentum_residual_jacobian(W, P, u0, u0, p0, load, *args, want_J=False, semi_implicit=True)
+    F0r, _ = forms.momentum_residual_jacobian(W, P, u0, u0, p0, load, *args, want_J=False)
+    assert np.abs(F0s - F0r).max() < 1e-13 * np.abs(F0r).max()
+    # and one step of the stepper needs exactly one Newton update
+    st = ons.IPCS(om, semi_implicit=True)
+    bd = W.boundary_dofs()
+    g = np.zeros(W.ndofs)
+    u1, p1 = st.step(0.05, 0.1 * u0, 0.1 * p0, (bd, g[bd]), None, 1.3, 0.2, None, None, tol=1e-12)
+    assert st.info["newton_its"] == 1 and np.isfinite(u1).all()

@@ -4,7 +4,7 @@ set -u
 O=gpurun_out
 mkdir -p $O
 run() { # N n tag extra
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus $1 --n $2 --steps ${STEPS:-5} --warmup 3 --no-cpu --no-variants $4 > $O/f_bench_$3.json 2> $O/f_bench_$3.err
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus $1 --cube-n $2 --steps ${STEPS:-5} --warmup 3 --no-cpu --no-variants $4 > $O/f_bench_$3.json 2> $O/f_bench_$3.err
   python - <<PY
 import json
 try:
