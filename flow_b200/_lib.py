@@ -150,6 +150,7 @@ SIGNATURES = {
         [vp, dbl, dbl, dbl, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, i64, pi64, pd, i64, pi64, pd, dbl, vp, vp,
          C.POINTER(NSStats)],
     ),
+    "fb_ns_velocity_magnitude": (C.c_int, [vp, vp, C.c_int, C.c_int, pd, pd, dbl, vp, pd, pd]),
     "fb_ns_residual": (C.c_int, [vp, dbl, dbl, dbl, dbl, pd, pd, pd, pd, pd, C.c_int]),
     "fb_ns_matrix": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
     "fb_ns_pressure_rhs": (C.c_int, [vp, dbl, dbl, dbl, C.c_int, pd, pd, pd]),

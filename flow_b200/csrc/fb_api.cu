@@ -735,6 +735,41 @@ int fb_ns_correction_rhs(fb_ns *ns, double dt, double rho, double mu, int rotati
   FB_API_END
 }
 
+int fb_ns_velocity_magnitude(fb_ns *ns, const double *u, int flags, int nq, const double *lam, const double *w, double rtol,
+                             double *unorm_out, double *linf, double *nodal_max) {
+  if (!ns || !u || !lam || !w || nq < 1 || nq > 64) return FB_EINVAL;
+  FB_API_BEGIN(ns->ctx)
+  cudaStream_t st = _ctx->dev->stream;
+  const int D = ns->D;
+  const bool dev = (flags & FB_DEVICE_PTRS) != 0;
+  ns_upload(ns, ns->tmp_u, u, ns->nu, dev);
+  halo_exchange(_ctx, *ns->W, ns->tmp_u.p, D);  // the load integrates over the ghost cells' nodes as well
+  DBuf<double> qlam, qw, b, x, dinv;
+  qlam.upload(lam, (size_t)nq * (D + 1), st);
+  qw.upload(w, (size_t)nq, st);
+  const int64_t nn = ns->W->nnodes, no = ns->W->n_owned;
+  b.alloc((size_t)nn);
+  x.alloc((size_t)nn);
+  dinv.alloc((size_t)nn);
+  assemble_magnitude_load(_ctx, *ns->W, ns->tmp_u.p, nq, qlam.p, qw.p, b.p);
+  // project(): mass-matrix solve (the reference's default LU [EXT]); Jacobi-PCG on the scalar P2 mass matrix
+  jacobi_setup_scalar(_ctx, *ns->W, ns->Mu.val.p, 1, nullptr, dinv.p);
+  int its = 0;
+  KrylovWork kw;
+  const int status = krylov_pcg(_ctx, make_linop(ns->Mu, 1, nullptr), dinv.p, b.p, x.p, rtol > 0.0 ? rtol : 1e-12, 0.0, 2000, 10, kw, &its);
+  if (status != FB_OK) return fb_fail(_ctx, status == FB_ENAN ? FB_ENAN : FB_ENOCONV_KRYLOV, "fb_ns_velocity_magnitude: mass solve failed");
+  double m[2];
+  vec_max_norms(_ctx, x.p, no, ns->tmp_u.p, no, D, m);
+  if (linf) *linf = m[0];
+  if (nodal_max) *nodal_max = m[1];
+  if (unorm_out) {
+    halo_exchange(_ctx, *ns->W, x.p, 1);
+    FB_CUDA(cudaMemcpyAsync(unorm_out, x.p, sizeof(double) * nn, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaStreamSynchronize(st));
+  }
+  FB_API_END
+}
+
 int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flags, const double *u0, const double *p0,
                int forcing, const double *f0, const double *f1, int64_t n_ubc, const int64_t *ubc_dofs,
                const double *ubc_vals, int64_t n_pbc, const int64_t *pbc_dofs, const double *pbc_vals, double tol,
@@ -793,6 +828,8 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
       if (pbc_dofs[i] < np_o) g2p += pbc_vals[i] * pbc_vals[i];
   }
 
+  FB_NVTX("fb_ns_step");
+  std::unique_ptr<fb_nvtx_range> nvtx_phase(new fb_nvtx_range("tentative velocity (Newton)"));  // popped on every exit path
   // ---- tentative velocity: Newton on F1(ui) = 0 (pressure_correction.py:147-255)
   FB_CUDA(cudaMemcpyAsync(ns->ui.p, ns->u0.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));  // :220
   MomentumArgs ma{dt, rho, mu, theta, ns->ui.p, ns->u0.p, ns->p0.p, ns->P->cell_nodes.p};
@@ -876,6 +913,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     // (chord iteration) as long as the previous update contracted the residual well -- the convergence
     // test on |F| is unchanged, only the path to it is cheaper (opts.jacobian_reuse = 0: plain Newton).
     if (!have_J || !o.jacobian_reuse || !reuse_ok) {
+      FB_NVTX("assemble Jacobian");
       assemble_momentum_J(ctx, *ns->W, ma, ns->J.val.p);
       bc_rows_identity_blocked(ctx, *ns->W, D, ns->J.val.p, ns->ubc_dofs.p, n_ubc);
       jacobi_setup_blocked(ctx, *ns->W, D, ns->J.val.p, o.momentum_precond == FB_BLOCK_JACOBI ? 1 : 0, ns->binv.p);
@@ -912,6 +950,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     }
     int its = 0;
     int status;
+    FB_NVTX("momentum linear solve");
     if (o.momentum_solver == FB_GMRES) {
       // flexible GMRES preconditioned by a few CG iterations on S (x) I, S = M + theta dt nu K (constant in time)
       const double c2 = theta * dt * mu / rho;
@@ -1047,6 +1086,8 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
   ns->J_age++;
   FB_CUDA(cudaEventRecord(dv->ev[1], st));
 
+  nvtx_phase.reset();
+  nvtx_phase.reset(new fb_nvtx_range("pressure Poisson + velocity correction"));
   // ---- pressure Poisson (pressure_correction.py:258-433)
   assemble_pressure_rhs(ctx, *ns->W, *ns->P, dt, rho, mu, rotational, ns->ui.p, ns->p0.p, ns->bp.p);
   const int p_check = o.check_every > 0 ? o.check_every : 50;

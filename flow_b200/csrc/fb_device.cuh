@@ -8,6 +8,19 @@
 
 #include "fb_internal.h"
 
+// NVTX ranges around the phases of a step (visible in Nsight Systems / ncu --nvtx; no cost without a tool attached).
+// Header-only NVTX3 from the CUDA toolkit; the library does not link libnvToolsExt.
+#include <nvtx3/nvToolsExt.h>
+struct fb_nvtx_range {
+  explicit fb_nvtx_range(const char *name) { nvtxRangePushA(name); }
+  ~fb_nvtx_range() { nvtxRangePop(); }
+  fb_nvtx_range(const fb_nvtx_range &) = delete;
+  fb_nvtx_range &operator=(const fb_nvtx_range &) = delete;
+};
+#define FB_NVTX_CAT2(a, b) a##b
+#define FB_NVTX_CAT(a, b) FB_NVTX_CAT2(a, b)
+#define FB_NVTX(name) fb_nvtx_range FB_NVTX_CAT(_fb_nvtx_, __LINE__)(name)
+
 struct fb_cuda_error : std::runtime_error {
   int status;
   fb_cuda_error(int st, const std::string &m) : std::runtime_error(m), status(st) {}

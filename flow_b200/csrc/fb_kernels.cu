@@ -1850,3 +1850,89 @@ void stokes_grad(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, const double
   else
     FB_LAUNCH(ctx, (k_stokes_div<3, 1>), g, 128, 0, W.nc, W.cell_nodes.p, W.cells.p, P.cell_nodes.p, W.xyz.p, p, out_u);
 }
+
+
+// =============================================================================
+// driver-side quantities (tests/test_karman_vortex_street.py:261-287, tests/test_sealed_box.py:134-141)
+// =============================================================================
+// b_a = int |u_h| phi_a dx with the caller's quadrature rule (the integrand is not polynomial: the rule is part of the
+// definition; the reference asks FFC for degree 4): one thread per cell
+template <int D>
+__global__ void k_magnitude_load(int64_t nc, const int *__restrict__ cell_nodes, const int *__restrict__ cells,
+                                 const double *__restrict__ xyz, const double *__restrict__ u, int nq, const double *__restrict__ qlam,
+                                 const double *__restrict__ qw, double *__restrict__ b) {
+  constexpr int NL = Elem<D>::NL2;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
+    const int *cn = cell_nodes + c * NL;
+    double glam[D + 1][D], vol;
+    cell_geometry<D>(cells + c * (D + 1), xyz, glam, vol);
+    double U[NL][D], acc[NL];
+#pragma unroll
+    for (int a = 0; a < NL; ++a) {
+      acc[a] = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) U[a][i] = u[(int64_t)cn[a] * D + i];
+    }
+    for (int q = 0; q < nq; ++q) {
+      double lam[D + 1], phi[NL], m2 = 0.0;
+#pragma unroll
+      for (int m = 0; m <= D; ++m) lam[m] = qlam[q * (D + 1) + m];
+#pragma unroll
+      for (int a = 0; a < NL; ++a) phi[a] = fb_p2_phi<D>(a, lam);
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double ui = 0.0;
+#pragma unroll
+        for (int a = 0; a < NL; ++a) ui += U[a][i] * phi[a];
+        m2 += ui * ui;
+      }
+      const double wm = qw[q] * vol * sqrt(m2);
+#pragma unroll
+      for (int a = 0; a < NL; ++a) acc[a] += wm * phi[a];
+    }
+#pragma unroll
+    for (int a = 0; a < NL; ++a) atomicAdd(&b[cn[a]], acc[a]);
+  }
+}
+
+// out[0] = max_i |x_i| over n entries; out[1] = max over nodes of the Euclidean norm of the D components of u (may be null)
+__global__ void k_max_norms(int64_t n, const double *__restrict__ x, int64_t nnodes, int D, const double *__restrict__ u,
+                            unsigned long long *out) {
+  double m0 = 0.0, m1 = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m0 = fmax(m0, fabs(x[i]));
+  if (u)
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnodes; i += (int64_t)gridDim.x * blockDim.x) {
+      double s2 = 0.0;
+      for (int k = 0; k < D; ++k) s2 += u[i * D + k] * u[i * D + k];
+      m1 = fmax(m1, sqrt(s2));
+    }
+  for (int o = 16; o > 0; o >>= 1) {
+    m0 = fmax(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+    m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+  }
+  // non-negative doubles order like their bit patterns
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&out[0], (unsigned long long)__double_as_longlong(m0));
+    atomicMax(&out[1], (unsigned long long)__double_as_longlong(m1));
+  }
+}
+
+void assemble_magnitude_load(fb_ctx *ctx, const DevSpace &W, const double *u, int nq, const double *qlam, const double *qw, double *b) {
+  FB_CUDA(cudaMemsetAsync(b, 0, sizeof(double) * W.nnodes, ctx->dev->stream));
+  const int g = grid_for(W.nc, 128, ctx->dev->sm_count * 16);
+  if (W.dim == 2)
+    FB_LAUNCH(ctx, k_magnitude_load<2>, g, 128, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, u, nq, qlam, qw, b);
+  else
+    FB_LAUNCH(ctx, k_magnitude_load<3>, g, 128, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, u, nq, qlam, qw, b);
+}
+
+void vec_max_norms(fb_ctx *ctx, const double *x, int64_t n, const double *u, int64_t nnodes, int D, double *out2_host) {
+  fb_device_state *dv = ctx->dev;
+  unsigned long long *slot = reinterpret_cast<unsigned long long *>(dv->red + 46);
+  FB_CUDA(cudaMemsetAsync(slot, 0, 2 * sizeof(unsigned long long), dv->stream));
+  FB_LAUNCH(ctx, k_max_norms, vgrid(ctx, std::max<int64_t>(n, nnodes)), 256, 0, n, x, nnodes, D, u, slot);
+  FB_CUDA(cudaMemcpyAsync(dv->host_pinned + 42, slot, 2 * sizeof(double), cudaMemcpyDeviceToHost, dv->stream));
+  FB_CUDA(cudaStreamSynchronize(dv->stream));
+  out2_host[0] = dv->host_pinned[42];
+  out2_host[1] = dv->host_pinned[43];
+}

@@ -145,6 +145,9 @@ void assemble_pressure_rhs(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, do
 // adds -dt/rho (grad phi, v) to b (which already holds M ui)
 void assemble_correction_grad(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, double dt, double rho, double mu,
                               int rotational, const double *ui, const double *p1, const double *p0, double *b);
+// driver-side quantities: load vector of |u_h| against the scalar P2 basis, max norms
+void assemble_magnitude_load(fb_ctx *ctx, const DevSpace &W, const double *u, int nq, const double *qlam, const double *qw, double *b);
+void vec_max_norms(fb_ctx *ctx, const double *x, int64_t n, const double *u, int64_t nnodes, int D, double *out2_host);
 // heat operator A (heat.py:54-58): -(kappa/rho_cp) grad u.grad v - (conv.grad u) v on V's pattern
 void assemble_heat(fb_ctx *ctx, const DevSpace &V, const DevSpace *W, const double *conv, double kdiff, double *val);
 // SUPG additions (heat.py:60-86): returns non-zero if tau exceeded 1e3 somewhere (the reference throws)

@@ -245,6 +245,16 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
                int forcing, const double *f0, const double *f1, int64_t n_ubc, const int64_t *ubc_dofs,
                const double *ubc_vals, int64_t n_pbc, const int64_t *pbc_dofs, const double *pbc_vals, double tol,
                double *u1, double *p1, fb_ns_stats *stats);
+/* Driver-side quantity of the reference's time loops, on the device: the L2 projection of the velocity magnitude onto
+ * the scalar P2 space and its max norm,
+ *     unorm = project(sqrt(ux**2 + uy**2), FunctionSpace(mesh, 'Lagrange', 2), quadrature_degree 4); norm(unorm.vector(), 'linf')
+ * (tests/test_karman_vortex_street.py:262-268 -- the CFL-like step-size control; tests/test_sealed_box.py:134-141).
+ * The integrand is not polynomial, so the quadrature rule is part of the definition: nq barycentric points
+ * lam[nq][gdim+1] and weights w (sum 1).  u: velocity dofs (host, or device with FB_DEVICE_PTRS); rtol: mass solve.
+ * unorm_out (nnodes(P2) doubles) may be NULL; nodal_max = max over the nodes of |u(x_i)| (no projection).
+ * Partitioned runs: the maxima are over the rank's owned nodes (reduce them with the launcher's max all-reduce). */
+int fb_ns_velocity_magnitude(fb_ns *ns, const double *u, int flags, int nq, const double *lam, const double *w, double rtol,
+                             double *unorm_out, double *linf, double *nodal_max);
 /* parity/debug: F1(ui) (and J if want_J) of pressure_correction.py:169-202 without BCs.
  * theta = 0, 1, 0.5; load = time-weighted load vector or NULL. */
 int fb_ns_residual(fb_ns *ns, double dt, double rho, double mu, double theta, const double *ui, const double *u0,

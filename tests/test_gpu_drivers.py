@@ -214,3 +214,50 @@ def test_boussinesq_with_supg(gpu_ctx):
     assert np.isfinite(th1.vector().get_local()).all()
     assert np.abs(th1.vector().get_local() - th0.vector().get_local()).max() < 1e-3
     assert np.abs(u1.vector().get_local() - u0.vector().get_local()).max() < 1e-6
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_velocity_magnitude_projection_on_device(gpu_ctx, dim):
+    """fb_ns_velocity_magnitude == project(|u|, P2, quadrature_degree=4) + linf norm of the oracle (same quadrature
+    rule handed through the ABI), and the controller of test_karman_vortex_street.py:270-284 on top of it."""
+    import ctypes as C
+
+    from flow_b200 import _lib, drivers
+    from flow_b200 import dolfin as d
+    from flow_b200._lib import lib
+    from flow_b200.navier_stokes.pressure_correction import _engine
+    from oracle import fem, forms
+    import scipy.sparse.linalg as spla
+
+    om = fem.Mesh(*(fem.unit_square_mesh(9, 7, "crossed") if dim == 2 else fem.unit_cube_mesh(4, 3, 5)))
+    Wo, Qo = fem.Space(om, 2, dim), fem.Space(om, 2, 1)
+    X = Wo.node_coords
+    U = np.stack([np.sin(3 * X[:, (i + 1) % dim] + 0.4 * i) * (1 + X[:, i]) for i in range(dim)], axis=1)
+    lam, w = fem.simplex_quadrature(dim, 4)
+    w = w / w.sum()
+    phi, _ = Qo.tabulate(lam)
+    Uc = U[Qo.cell_nodes]                                    # (c, a, i)
+    mag = np.sqrt((np.einsum("qa,cai->cqi", phi, Uc) ** 2).sum(axis=2))
+    be = np.einsum("q,cq,qa,c->ca", w, mag, phi, om.vol)
+    b = np.zeros(Qo.nnodes)
+    np.add.at(b, Qo.cell_nodes.ravel(), be.ravel())
+    unorm_o = spla.spsolve(forms.mass_matrix(Qo).tocsc(), b)
+
+    m = d.Mesh(om.points, om.cells)
+    W = d.VectorFunctionSpace(m, "CG", 2)
+    P = d.FunctionSpace(m, "CG", 1)
+    u = d.Function(W, U.reshape(-1).copy())
+    ns = _engine(W, P)
+    out = np.zeros(Qo.nnodes)
+    linf, nodal = C.c_double(), C.c_double()
+    lamc, wc = np.ascontiguousarray(lam), np.ascontiguousarray(w)
+    _lib.check(lib.fb_ns_velocity_magnitude(ns, u._vec.ctypes.data_as(C.c_void_p), 0, wc.size, _lib.as_pd(lamc), _lib.as_pd(wc), 1e-13,
+                                            out.ctypes.data_as(C.c_void_p), C.byref(linf), C.byref(nodal)), m.ctx, "magnitude")
+    assert np.abs(out - unorm_o).max() < 1e-10 * np.abs(unorm_o).max()
+    assert abs(linf.value - np.abs(unorm_o).max()) < 1e-10 * np.abs(unorm_o).max()
+    assert abs(nodal.value - np.sqrt((U ** 2).sum(axis=1)).max()) < 1e-13
+    # facade with its own degree-4 rule: same quantity up to the quadrature of a non-polynomial integrand
+    l2, n2 = drivers.velocity_magnitude(u, P)
+    assert abs(l2 - linf.value) < 2e-2 * linf.value and abs(n2 - nodal.value) < 1e-13
+    dt = drivers.adapt_step_size(1e-3, l2, m.hmax(), 1.0)
+    assert 1e-3 < dt <= 2e-3
