@@ -941,6 +941,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     // (first update of a step: |F| is dominated by the rows u - g of dofs whose boundary value changed)
     const double r_rhs = lifted ? vec_norm2_sync(ctx, ns->F.p, nu_o) : r;
     double atol_inner = std::max(chord ? 0.1 * target : lin_floor, o.momentum_rtol * std::min(r, r_rhs));
+    if (o.semi_implicit && !chord) atol_inner = lin_floor;  // linear in ui: one solve to the floor is the whole step
     if (chord && o.adaptive_forcing && ns->contraction > 0.0 && ns->contraction < 0.1) {
       const double predicted = ns->contraction * r;  // |F| the update can reach at best
       if (predicted < 0.5 * target)

@@ -1414,7 +1414,9 @@ struct JcfShared {
   double GU[MOM_WARPS][NV * D * D];
 };
 
-template <int D>
+// ELEM = 0: scatter-add into the matrix (fp64 atomics through smap); ELEM = 1: store the element blocks cell by cell
+// (val = element buffer, nc * NL * NL * D * D doubles) for the deterministic gather pass k_jac_gather
+template <int D, int ELEM = 0>
 __global__ void __launch_bounds__(MOM_WARPS * 32)
     k_momentum_J_cf(int64_t nc, const int *__restrict__ cell_nodes, const int *__restrict__ cells,
                     const double *__restrict__ xyz, const int *__restrict__ rowptr, const int *__restrict__ smap,
@@ -1438,7 +1440,7 @@ __global__ void __launch_bounds__(MOM_WARPS * 32)
     const int *cn = cell_nodes + c * NL;
     // scatter addresses first: their load latency hides behind phase A
     int r0 = 0, len = 0;
-    if (active) {
+    if (active && !ELEM) {
       const int I = cn[ta];
       r0 = rowptr[I];
       len = (rowptr[I + 1] - r0) * D;
@@ -1493,15 +1495,23 @@ __global__ void __launch_bounds__(MOM_WARPS * 32)
       for (int r = 0; r < ROUNDS; ++r) {
         const int tb = grp + r * NG;
         if (tb < NL) {
-          const int slot = smap[c * NP + ta * NL + tb];  // issued before the block's arithmetic
+          const int slot = ELEM ? 0 : smap[c * NP + ta * NL + tb];  // issued before the block's arithmetic
           double J[D][D];
           fb_jac_pair<D>(vol, c1, c2, GA, SA, s.GV[wid][tb], s.S[wid][tb], WA, s.WT[wid][tb], s.GU[wid], &s.M3[(ta * NL + tb) * NV], J,
                          a.adv ? 0.0 : c1);
-          double *base = val + (int64_t)r0 * (D * D) + (int64_t)(slot - r0) * D;
+          if (ELEM) {
+            double *dst = val + ((int64_t)c * NP + ta * NL + tb) * (D * D);
 #pragma unroll
-          for (int i = 0; i < D; ++i)
+            for (int i = 0; i < D; ++i)
 #pragma unroll
-            for (int j = 0; j < D; ++j) atomicAdd(base + (int64_t)i * len + j, J[i][j]);
+              for (int j = 0; j < D; ++j) __stcs(dst + i * D + j, J[i][j]);
+          } else {
+            double *base = val + (int64_t)r0 * (D * D) + (int64_t)(slot - r0) * D;
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+              for (int j = 0; j < D; ++j) atomicAdd(base + (int64_t)i * len + j, J[i][j]);
+          }
         }
       }
     }
@@ -1541,15 +1551,143 @@ __global__ void k_momentum_J_facets(int64_t nbf, const int *__restrict__ bf_cell
 }
 
 
-void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *Jval) {
+// ---- deterministic two-pass assembly of the cell part of J --------------------------------------------------------
+// Pass 1 (k_momentum_J_cf<D, 1>) stores every element block; pass 2 sums, for each block of the matrix, its element
+// contributions in a FIXED order (ascending cell) and writes the block once: no atomics (2.2 G fp64 atomicAdds at
+// n = 74, the throughput limit of the one-pass kernel), no memset, bit-reproducible values.  The gather lists are the
+// inverse of smap, built once per space.
+__global__ void k_gather_count(int64_t total, const int *__restrict__ smap, int *__restrict__ count) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&count[smap[t]], 1);
+}
+__global__ void k_gather_fill(int64_t total, const int *__restrict__ smap, const int *__restrict__ gptr, int *__restrict__ cursor,
+                              int *__restrict__ gsrc) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int s = smap[t];
+    gsrc[gptr[s] + atomicAdd(&cursor[s], 1)] = (int)t;
+  }
+}
+__global__ void k_gather_sort(int64_t nnz, const int *__restrict__ gptr, int *__restrict__ gsrc) {
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < nnz; s += (int64_t)gridDim.x * blockDim.x) {
+    const int b = gptr[s], e = gptr[s + 1];
+    for (int i = b + 1; i < e; ++i) {  // insertion sort: the lists hold a few dozen entries at most
+      const int v = gsrc[i];
+      int j = i - 1;
+      while (j >= b && gsrc[j] > v) {
+        gsrc[j + 1] = gsrc[j];
+        --j;
+      }
+      gsrc[j + 1] = v;
+    }
+  }
+}
+__global__ void k_exclusive_scan_serial(int64_t n, const int *__restrict__ in, int *__restrict__ out) {
+  // one block, blocked scan: set-up only (n = number of matrix blocks)
+  __shared__ long long carry;
+  __shared__ int part[1024];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const int v = i < n ? in[i] : 0;
+    part[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int add = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+      __syncthreads();
+      part[threadIdx.x] += add;
+      __syncthreads();
+    }
+    if (i < n) out[i] = (int)(carry + part[threadIdx.x] - v);
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += part[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = (int)carry;
+}
+
+// T lanes per block row; lane t sums the contributions of block t, t + T, ... and writes the D x D values (row-planar)
+template <int D, int T>
+__global__ void __launch_bounds__(256)
+    k_jac_gather(int64_t nrows, const int *__restrict__ rowptr, const int *__restrict__ gptr, const int *__restrict__ gsrc,
+                 const double *__restrict__ ebuf, double *__restrict__ val) {
+  const int lane = threadIdx.x % T;
+  const int64_t group = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / T;
+  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / T;
+  for (int64_t row = group; row < nrows; row += ngroups) {
+    const int r0 = rowptr[row], nb = rowptr[row + 1] - r0;
+    const int len = nb * D;
+    double *base = val + (int64_t)r0 * (D * D);
+    for (int t = lane; t < nb; t += T) {
+      const int b = gptr[r0 + t], e = gptr[r0 + t + 1];
+      double acc[D * D];
+#pragma unroll
+      for (int k = 0; k < D * D; ++k) acc[k] = 0.0;
+      for (int q = b; q < e; ++q) {
+        const double *src = ebuf + (int64_t)gsrc[q] * (D * D);
+#pragma unroll
+        for (int k = 0; k < D * D; ++k) acc[k] += __ldcs(src + k);
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) base[(int64_t)i * len + t * D + j] = acc[i * D + j];
+    }
+  }
+}
+
+static void build_gather_map(fb_ctx *ctx, DevSpace &W) {
+  const int64_t total = W.nc * W.nl * W.nl;
+  if (total > INT32_MAX) throw fb_cuda_error(FB_EINVAL, "gather map: too many element blocks for one GPU");
+  cudaStream_t st = ctx->dev->stream;
+  DBuf<int> count;
+  count.alloc((size_t)W.nnz);
+  count.zero(st);
+  W.gptr.alloc((size_t)W.nnz + 1);
+  W.gsrc.alloc((size_t)total);
+  const int g = grid_for(total, 256, ctx->dev->sm_count * 16);
+  FB_LAUNCH(ctx, k_gather_count, g, 256, 0, total, W.smap.p, count.p);
+  k_exclusive_scan_serial<<<1, 1024, 0, st>>>(W.nnz, count.p, W.gptr.p);
+  ctx->launches++;
+  count.zero(st);
+  FB_LAUNCH(ctx, k_gather_fill, g, 256, 0, total, W.smap.p, W.gptr.p, count.p, W.gsrc.p);
+  FB_LAUNCH(ctx, k_gather_sort, grid_for(W.nnz, 256, ctx->dev->sm_count * 16), 256, 0, W.nnz, W.gptr.p, W.gsrc.p);
+  FB_CUDA(cudaStreamSynchronize(st));
+}
+
+// 1 (default where the element buffer fits): two-pass deterministic assembly; 0: one-pass atomics.  FB_J_TWO_PASS overrides.
+static bool use_two_pass(const DevSpace &W) {
+  const char *e = getenv("FB_J_TWO_PASS");
+  if (e) return atoi(e) != 0;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+  const double need = (double)W.nc * W.nl * W.nl * (W.dim * W.dim * 8.0 + 4.0) + (double)W.nnz * 4.0;
+  return W.ebuf.p != nullptr || need < 0.35 * (double)free_b;  // leave room for the Krylov work vectors
+}
+
+void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W_, const MomentumArgs &a, double *Jval) {
+  DevSpace &W = const_cast<DevSpace &>(W_);
   const int D = W.dim;
-  FB_CUDA(cudaMemsetAsync(Jval, 0, sizeof(double) * W.nnz * D * D, ctx->dev->stream));
+  static const int variant0 = getenv("FB_J_KERNEL") ? atoi(getenv("FB_J_KERNEL")) : 2;
+  if (!(variant0 == 2 && use_two_pass(W)))  // the gather pass writes every block (rows without cells do not exist)
+    FB_CUDA(cudaMemsetAsync(Jval, 0, sizeof(double) * W.nnz * D * D, ctx->dev->stream));
   const int g = grid_for(W.nc * 32, MOM_WARPS * 32, ctx->dev->sm_count * 16);
   const int gf = grid_for(W.nbf * W.nl * W.nl, 128, ctx->dev->sm_count * 16);
   // 2 (default): closed form (k_momentum_J_cf); 0: degree-5 quadrature (k_momentum_J), kept as the cross-check.
   // Measured at n = 74 on B200 (2.43 M cells): 14.7 ms vs 29.8 ms per launch.
   static const int variant = getenv("FB_J_KERNEL") ? atoi(getenv("FB_J_KERNEL")) : 2;
-  if (variant == 2) {
+  if (variant == 2 && use_two_pass(W)) {
+    if (!W.gptr.p) build_gather_map(ctx, W);
+    W.ebuf.alloc((size_t)W.nc * W.nl * W.nl * D * D);
+    const int gg = grid_for(W.n_owned * 8, 256, ctx->dev->sm_count * 16);
+    if (D == 2) {
+      FB_LAUNCH(ctx, (k_momentum_J_cf<2, 1>), g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, W.ebuf.p);
+      FB_LAUNCH(ctx, (k_jac_gather<2, 8>), gg, 256, 0, W.nnodes, W.rowptr.p, W.gptr.p, W.gsrc.p, W.ebuf.p, Jval);
+    } else {
+      FB_LAUNCH(ctx, (k_momentum_J_cf<3, 1>), g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, W.ebuf.p);
+      FB_LAUNCH(ctx, (k_jac_gather<3, 8>), gg, 256, 0, W.nnodes, W.rowptr.p, W.gptr.p, W.gsrc.p, W.ebuf.p, Jval);
+    }
+  } else if (variant == 2) {
     if (D == 2)
       FB_LAUNCH(ctx, k_momentum_J_cf<2>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
     else

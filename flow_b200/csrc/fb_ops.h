@@ -33,6 +33,10 @@ struct DevSpace {
   DBuf<int> diag;           // nnodes: slot of the diagonal entry
   DBuf<int> smap;           // nc * nl * nl: CSR slot of (node_a, node_b)
   DBuf<int> bf_cell, bf_local;
+  // deterministic two-pass assembly (fb_kernels.cu): per matrix block the list of element blocks that sum into it
+  // (gptr: nnz + 1, gsrc: nc * nl * nl, ascending) and the element buffer of the last assembly
+  DBuf<int> gptr, gsrc;
+  DBuf<double> ebuf;
   // distributed: rows [0, n_owned) are computed here, [n_owned, nnodes) are ghosts (SpMV inputs only)
   int64_t n_owned = 0;
   std::vector<int> halo_ranks;

@@ -61,7 +61,7 @@ def test_b200_arm_line(gpu_ctx):
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
-    assert d["variants"]["chord"]["value"] > 0 and d["variants"]["inner_fp32"]["value"] > 0
+    assert d["variants"]["momentum_rtol_1e-5"]["value"] > 0 and d["variants"]["semi_implicit"]["value"] > 0
     assert d["iterations"]["newton"] <= 10
     assert d["scaling"] == "strong" and d["e2e"]["steps"] == 2
     assert d["checksum"]["steps_total"] == 5 and d["checksum"]["u_l2"] > 0 and d["checksum"]["p_l2_mean_free"] > 0

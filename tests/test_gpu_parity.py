@@ -261,3 +261,38 @@ def test_error_contract(gpu_ctx):
     u0._vec[:] = np.nan
     with pytest.raises(RuntimeError):
         nav.IPCS().step(d.Constant(0.1), {0: u0}, p0, [], [], d.Constant(1.0), d.Constant(1.0), f, verbose=False)
+
+
+@pytest.mark.parametrize("mesh_name", ["tri_crossed", "tet"])
+def test_two_pass_jacobian_assembly_is_deterministic_and_equals_the_atomic_one(gpu_ctx, mesh_name, monkeypatch):
+    """The default assembly of J stores the element blocks and sums them per matrix block in a fixed order
+    (k_momentum_J_cf<D,1> + k_jac_gather): bit-identical from call to call, and equal to the one-pass fp64-atomic
+    assembly (FB_J_TWO_PASS=0) up to the order of the sums."""
+    from flow_b200 import _lib
+    from flow_b200 import dolfin as d
+    from flow_b200._lib import lib
+    from flow_b200.navier_stokes.pressure_correction import _engine
+
+    om = oracle_mesh(mesh_name)
+    Wo, Po, ui, u0, p0, _ = rand_state(om, 11)
+    m = facade_mesh(om)
+    W = d.VectorFunctionSpace(m, "CG", 2)
+    P = d.FunctionSpace(m, "CG", 1)
+    ns = _engine(W, P)
+    F = np.zeros(W.dim())
+    h = _lib.vp()
+    lib.fb_ns_matrix(ns, 2, C.byref(h))
+    nrows, nnzb, blk = _lib.i64(), _lib.i64(), C.c_int()
+    lib.fb_mat_info(h, C.byref(nrows), C.byref(nnzb), C.byref(blk))
+    vals = {}
+    for mode, reps in (("1", 3), ("0", 1)):
+        monkeypatch.setenv("FB_J_TWO_PASS", mode)
+        for r in range(reps):
+            _lib.check(lib.fb_ns_residual(ns, 0.05, 1.1, 0.3, 1.0, _lib.as_pd(ui), _lib.as_pd(u0), _lib.as_pd(p0), None, _lib.as_pd(F), 1),
+                       m.ctx, "fb_ns_residual")
+            v = np.zeros(nnzb.value * blk.value ** 2)
+            _lib.check(lib.fb_mat_values(h, _lib.as_pd(v)), m.ctx, "fb_mat_values")
+            vals[(mode, r)] = v
+    assert np.array_equal(vals[("1", 0)], vals[("1", 1)]) and np.array_equal(vals[("1", 0)], vals[("1", 2)])
+    scale = np.abs(vals[("0", 0)]).max()
+    assert np.abs(vals[("1", 0)] - vals[("0", 0)]).max() < 1e-14 * scale
