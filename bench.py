@@ -160,6 +160,33 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_other_config(args):
+    """BASELINE.json configs 2-4 at their stated sizes on one GPU (tools/run_configs.py): parity-test cases, not the
+    headline -- one JSON line in the same contract, every step through the public facade with host buffers."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import run_configs
+
+    from flow_b200 import _lib
+    from flow_b200._lib import lib
+
+    name, default_steps = {2: ("cavity2d", 20), 3: ("karman", 200), 4: ("boussinesq", 10)}[args.config]
+    steps = args.steps if args.steps != 5 else default_steps
+    ctx = _lib.context()
+    c0 = _lib.i64()
+    lib.fb_ctx_launch_count(ctx, C.byref(c0))
+    out = getattr(run_configs, name)(steps)
+    c1 = _lib.i64()
+    lib.fb_ctx_launch_count(ctx, C.byref(c1))
+    v = out["steps_per_s_e2e"]
+    line = {"metric": "ipcs_timesteps_per_sec_config%d" % args.config, "value": v, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": 3,
+            "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": out["config"], "dofs": out["dofs"], "note": "BASELINE.json configs[%d]; value = e2e through the facade "
+                       "(host buffers in and out every step); not the headline configuration" % (args.config - 1)},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": int(out["dofs"] * 8), "d2h_bytes_per_step": int(out["dofs"] * 8)},
+            "gpu_launches": int(c1.value - c0.value), "details": out, "cpu_baseline": None, "roofline": None}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -172,6 +199,9 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="stepping time the CPU arm may spend (it stops after the step that exceeds it)")
     ap.add_argument("--cpu-warmup", type=int, default=1, help="warm-up steps of the CPU arm (at most --warmup)")
     ap.add_argument("--cpu-sample-steps", type=int, default=1, help="timed steps of the cpu_baseline leg of the b200 arm")
+    ap.add_argument("--config", type=int, default=5, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config: 5 = the headline 3D cavity (default); 2 = 2D cavity n = 333, 3 = Karman channel, "
+                         "4 = Boussinesq n = 667 (single GPU, through the facade)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the opt-in variants")
@@ -189,6 +219,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         return run_reference(args, rank)
+    if args.config in (2, 3, 4):
+        return run_other_config(args)
 
     import torch
     import torch.distributed as dist

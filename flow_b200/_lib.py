@@ -62,6 +62,8 @@ class NSOpts(C.Structure):
         ("newton_overshoot", C.c_double),
         ("inner_chebyshev", C.c_int),
         ("semi_implicit", C.c_int),
+        ("inner_local", C.c_int),
+        ("deterministic_assembly", C.c_int),
     ]
 
 

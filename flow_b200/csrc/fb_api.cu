@@ -568,6 +568,8 @@ int fb_ns_opts_default(fb_ns_opts *o) {
   o->newton_overshoot = 1e-3;
   o->inner_chebyshev = 1;
   o->semi_implicit = 0;
+  o->inner_local = 1;
+  o->deterministic_assembly = 0;
   return FB_OK;
 }
 
@@ -914,6 +916,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     // test on |F| is unchanged, only the path to it is cheaper (opts.jacobian_reuse = 0: plain Newton).
     if (!have_J || !o.jacobian_reuse || !reuse_ok) {
       FB_NVTX("assemble Jacobian");
+      set_deterministic_assembly(o.deterministic_assembly != 0);
       assemble_momentum_J(ctx, *ns->W, ma, ns->J.val.p);
       bc_rows_identity_blocked(ctx, *ns->W, D, ns->J.val.p, ns->ubc_dofs.p, n_ubc);
       jacobi_setup_blocked(ctx, *ns->W, D, ns->J.val.p, o.momentum_precond == FB_BLOCK_JACOBI ? 1 : 0, ns->binv.p);
@@ -1039,6 +1042,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
         ChebWork *w;
         int degree;
       } cheb{ctx, inner.S, ns->dinv_S.p, &ns->cheb, o.chebyshev_degree > 0 ? o.chebyshev_degree : 4};
+      ns->cheb.local = o.inner_local != 0 && fb_is_distributed(ctx);
       if (o.inner_chebyshev && inner.S.tile && inner.S.tval && ns->cheb.lmax > 0.0 && !(o.inner_fp32 && ns->Sval32.p)) {
         // fixed polynomial in S instead of CG iterations: degree - 1 products, each one fused kernel
         pc.self = &cheb;

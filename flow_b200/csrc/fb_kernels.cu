@@ -17,6 +17,7 @@
 
 #include "fb_element.cuh"
 #include <memory>
+#include <numeric>
 
 #include "fb_ops.h"
 
@@ -227,10 +228,21 @@ void dev_space_build(fb_space *s, DevSpace &d) {
     std::vector<int32_t> inv((size_t)m->nc), bfc(m->bf_cell.size());
     for (int64_t c = 0; c < m->nc; ++c) inv[corder[c]] = (int32_t)c;
     for (size_t k = 0; k < bfc.size(); ++k) bfc[k] = inv[m->bf_cell[k]];
-    d.bf_cell.upload(bfc.data(), bfc.size(), st);
+    // facets sorted by (cell, local facet): a cell's facets are consecutive (k_momentum_J_facets_elem)
+    std::vector<size_t> ord(bfc.size());
+    std::iota(ord.begin(), ord.end(), (size_t)0);
+    std::sort(ord.begin(), ord.end(), [&](size_t x, size_t y) {
+      return bfc[x] != bfc[y] ? bfc[x] < bfc[y] : m->bf_local[x] < m->bf_local[y];
+    });
+    std::vector<int32_t> bfc2(bfc.size()), bfl2(bfc.size());
+    for (size_t k = 0; k < ord.size(); ++k) {
+      bfc2[k] = bfc[ord[k]];
+      bfl2[k] = m->bf_local[ord[k]];
+    }
+    d.bf_cell.upload(bfc2.data(), bfc2.size(), st);
+    d.bf_local.upload(bfl2.data(), bfl2.size(), st);
     FB_CUDA(cudaStreamSynchronize(st));
   }
-  d.bf_local.upload(m->bf_local.data(), m->bf_local.size(), st);
   FB_LAUNCH(ctx, k_scatter_map, grid_for(d.nc * d.nl * d.nl, 256, 148 * 16), 256, 0, d.nc, d.nl, d.cell_nodes.p,
             d.rowptr.p, d.col.p, d.smap.p);
   FB_LAUNCH(ctx, k_diag_slot, grid_for(d.nnodes, 256, 148 * 16), 256, 0, d.nnodes, d.rowptr.p, d.col.p, d.diag.p);
@@ -1655,14 +1667,52 @@ static void build_gather_map(fb_ctx *ctx, DevSpace &W) {
   FB_CUDA(cudaStreamSynchronize(st));
 }
 
-// 1 (default where the element buffer fits): two-pass deterministic assembly; 0: one-pass atomics.  FB_J_TWO_PASS overrides.
+// Two-pass deterministic assembly: opt-in (fb_ns_opts.deterministic_assembly or FB_J_TWO_PASS=1).  Measured on B200 at
+// n = 74 (profiles/r2_jacobian_assembly.txt): element pass 12.0 ms + gather pass 10.3 ms against 17 ms for the one-pass
+// atomic kernel -- the closed-form element arithmetic (162 registers, 17 % occupancy), not the atomics, is what the
+// assembly costs, so the default stays one-pass.
+static bool g_two_pass_option = false;
+void set_deterministic_assembly(bool on) { g_two_pass_option = on; }
 static bool use_two_pass(const DevSpace &W) {
   const char *e = getenv("FB_J_TWO_PASS");
-  if (e) return atoi(e) != 0;
-  size_t free_b = 0, total_b = 0;
-  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
-  const double need = (double)W.nc * W.nl * W.nl * (W.dim * W.dim * 8.0 + 4.0) + (double)W.nnz * 4.0;
-  return W.ebuf.p != nullptr || need < 0.35 * (double)free_b;  // leave room for the Krylov work vectors
+  return e ? atoi(e) != 0 : g_two_pass_option;
+}
+
+// boundary-facet part of J added to the ELEMENT blocks (two-pass mode): the facets are sorted by cell, the thread of a
+// cell's first facet adds all of that cell's facets in order -> one writer per element block, fixed order
+template <int D>
+__global__ void k_momentum_J_facets_elem(int64_t nbf, const int *__restrict__ bf_cell, const int *__restrict__ bf_local,
+                                         const int *__restrict__ cells, const double *__restrict__ xyz, MomentumArgs a,
+                                         double *__restrict__ ebuf) {
+  constexpr int NL = Elem<D>::NL2, NP = NL * NL;
+  const int64_t total = nbf * NP;
+  const double coef = -a.theta * a.dt / a.rho * a.mu;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t fidx = t / NP;
+    const int p = (int)(t - fidx * NP);
+    const int ta = p / NL, tb = p - ta * NL;
+    const int64_t c = bf_cell[fidx];
+    if (fidx > 0 && bf_cell[fidx - 1] == c) continue;  // not the cell's first facet
+    double glam[D + 1][D], vol;
+    cell_geometry<D>(cells + c * (D + 1), xyz, glam, vol);
+    double acc[D][D];
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < D; ++j) acc[i][j] = 0.0;
+    bool any = false;
+    for (int64_t f2 = fidx; f2 < nbf && bf_cell[f2] == c; ++f2) {
+      const int f = bf_local[f2];
+      if (!fb_node_on_facet<D>(ta, f)) continue;
+      double B[D][D];
+      fb_facet_J<D>(ta, tb, f, glam, vol, QF<D>::lam_ptr(), QF<D>::w_ptr(), QF<D>::NQ, B);
+      for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) acc[i][j] += coef * B[i][j];
+      any = true;
+    }
+    if (!any) continue;
+    double *dst = ebuf + ((int64_t)c * NP + p) * (D * D);
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < D; ++j) dst[i * D + j] += acc[i][j];
+  }
 }
 
 void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W_, const MomentumArgs &a, double *Jval) {
@@ -1680,13 +1730,17 @@ void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W_, const MomentumArgs &a,
     if (!W.gptr.p) build_gather_map(ctx, W);
     W.ebuf.alloc((size_t)W.nc * W.nl * W.nl * D * D);
     const int gg = grid_for(W.n_owned * 8, 256, ctx->dev->sm_count * 16);
+    const bool facets = W.nbf && a.theta != 0.0;
     if (D == 2) {
       FB_LAUNCH(ctx, (k_momentum_J_cf<2, 1>), g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, W.ebuf.p);
+      if (facets) FB_LAUNCH(ctx, k_momentum_J_facets_elem<2>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cells.p, W.xyz.p, a, W.ebuf.p);
       FB_LAUNCH(ctx, (k_jac_gather<2, 8>), gg, 256, 0, W.nnodes, W.rowptr.p, W.gptr.p, W.gsrc.p, W.ebuf.p, Jval);
     } else {
       FB_LAUNCH(ctx, (k_momentum_J_cf<3, 1>), g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, W.ebuf.p);
+      if (facets) FB_LAUNCH(ctx, k_momentum_J_facets_elem<3>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cells.p, W.xyz.p, a, W.ebuf.p);
       FB_LAUNCH(ctx, (k_jac_gather<3, 8>), gg, 256, 0, W.nnodes, W.rowptr.p, W.gptr.p, W.gsrc.p, W.ebuf.p, Jval);
     }
+    return;  // the facet terms are in
   } else if (variant == 2) {
     if (D == 2)
       FB_LAUNCH(ctx, k_momentum_J_cf<2>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);

@@ -816,9 +816,15 @@ void cheb_apply(fb_ctx *ctx, const LinOp &A, const double *dinv, double lmin, do
                 ChebWork &w) {
   if (!A.tile || !A.tval) throw fb_cuda_error(FB_EINVAL, "cheb_apply: operator is not in tile format");
   const int64_t n = A.ndofs(), nl = A.nlocal_dofs();
-  w.r.alloc((size_t)nl);
-  w.d0.alloc((size_t)nl);
-  w.d1.alloc((size_t)nl);
+  if (w.d0.n != (size_t)nl) {
+    w.r.alloc((size_t)nl);
+    w.d0.alloc((size_t)nl);
+    w.d1.alloc((size_t)nl);
+    // ghost entries of the direction vectors: refreshed by the halo exchange, or -- rank-local polynomial
+    // (w.local) -- left at zero for ever (the kernels only write owned rows)
+    w.d0.zero(ctx->dev->stream);
+    w.d1.zero(ctx->dev->stream);
+  }
   const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
   if (degree < 1) degree = 1;
   FB_LAUNCH(ctx, k_cheb_start, vgrid(ctx, n), 256, 0, n, 1.0 / theta, dinv, v, w.d0.p, degree == 1 ? z : (double *)nullptr);
@@ -826,7 +832,7 @@ void cheb_apply(fb_ctx *ctx, const LinOp &A, const double *dinv, double lmin, do
   double *dk = w.d0.p, *dn = w.d1.p;
   for (int k = 0; k + 1 < degree; ++k) {
     const double rho = 1.0 / (2.0 * sigma - rho_prev);
-    if (A.halo) halo_exchange(ctx, *A.halo, dk, A.dofs_per_node());
+    if (A.halo && !w.local) halo_exchange(ctx, *A.halo, dk, A.dofs_per_node());
     tile_cheb_step(ctx, A, dk, k == 0 ? v : w.r.p, w.r.p, k == 0 ? nullptr : z, z, dn, dinv, rho * rho_prev, 2.0 * rho / delta,
                    k + 2 == degree);
     std::swap(dk, dn);

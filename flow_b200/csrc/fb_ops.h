@@ -144,6 +144,7 @@ void assemble_momentum_F(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, 
 void assemble_momentum_F_old_state(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F);  // += u0 part
 void assemble_momentum_F_new_state(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F);  // += ui part
 void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *Jval);
+void set_deterministic_assembly(bool on);  // two-pass, fixed summation order (process-wide switch; FB_J_TWO_PASS overrides)
 void assemble_pressure_rhs(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, double dt, double rho, double mu,
                            int rotational, const double *ui, const double *p0, double *b);
 // adds -dt/rho (grad phi, v) to b (which already holds M ui)
@@ -218,6 +219,10 @@ int krylov_fgmres(fb_ctx *ctx, const LinOp &A, const FgmresPrecond &pc, const do
 struct ChebWork {
   DBuf<double> r, d0, d1;
   double lmin = 0.0, lmax = 0.0;
+  // partitioned runs: true = polynomial of the rank's owned x owned block of the operator (couplings to ghost
+  // columns dropped, no halo exchange inside the preconditioner -- block Jacobi over the ranks); the outer flexible
+  // GMRES iteration and its operator stay global, so only the iteration count can change, not the solution
+  bool local = false;
 };
 void cheb_estimate_spectrum(fb_ctx *ctx, const LinOp &A, const double *dinv, int lanczos_steps, double *lmin, double *lmax);
 void cheb_apply(fb_ctx *ctx, const LinOp &A, const double *dinv, double lmin, double lmax, int degree, const double *v, double *z,

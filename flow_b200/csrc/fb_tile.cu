@@ -404,8 +404,8 @@ bool tile_enabled() {
 // kernel configuration of the formats built from now on (FB_TILE_CFG, experiments; default: see TileCfg)
 static int tile_default_cfg() {
   const char *e = getenv("FB_TILE_CFG");
-  const int c = e ? atoi(e) : 1;
-  return (c >= 0 && c < TILE_NCFG) ? c : 1;
+  const int c = e ? atoi(e) : 0;  // measured best on B200 at n = 74 (profiles/r2_tile_spmm_configs.txt)
+  return (c >= 0 && c < TILE_NCFG) ? c : 0;
 }
 
 // Host side of the format: tiles of the owned rows of s's node pattern (pure host code, once per space).

@@ -210,6 +210,14 @@ typedef struct fb_ns_opts {
                             implement: the tentative-velocity system becomes linear in ui (one assembly and one linear
                             solve per step) and keeps the skew-symmetric form; an O(dt) different discretisation, NOT the
                             reference's numbers (parity: oracle variant of the same form) */
+  int inner_local;       /* 1 (default): in partitioned runs the Chebyshev preconditioner is the polynomial of each rank's
+                            owned x owned block of S (no halo exchange inside the preconditioner: 3 of the 4 exchanges of
+                            an outer iteration disappear); the flexible outer iteration keeps the global operator, so the
+                            solution is unchanged.  0: global S, one halo exchange per product */
+  int deterministic_assembly; /* 0 (default): the Jacobian is scatter-added with fp64 atomics (values reproducible to rounding,
+                            not bit for bit).  1: two passes -- element blocks stored cell by cell, then every matrix block
+                            sums its contributions in a fixed order (ascending cell): bit-reproducible Jacobian, no atomics,
+                            +17.5 GB of scratch and ~1.3x the assembly time at 10 M dofs */
 } fb_ns_opts;
 
 typedef struct fb_ns_stats {
