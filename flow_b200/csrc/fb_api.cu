@@ -914,7 +914,9 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     // Jacobian: assembled at the first iteration of every step; later iterations of the step keep it
     // (chord iteration) as long as the previous update contracted the residual well -- the convergence
     // test on |F| is unchanged, only the path to it is cheaper (opts.jacobian_reuse = 0: plain Newton).
-    if (!have_J || !o.jacobian_reuse || !reuse_ok) {
+    // (semi-implicit linearisation: J does not depend on ui -- the second "Newton" update is iterative refinement of the
+    // one linear system of the step with the same matrix)
+    if (!have_J || (!o.jacobian_reuse && !o.semi_implicit) || !reuse_ok) {
       FB_NVTX("assemble Jacobian");
       set_deterministic_assembly(o.deterministic_assembly != 0);
       assemble_momentum_J(ctx, *ns->W, ma, ns->J.val.p);
@@ -944,7 +946,6 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     // (first update of a step: |F| is dominated by the rows u - g of dofs whose boundary value changed)
     const double r_rhs = lifted ? vec_norm2_sync(ctx, ns->F.p, nu_o) : r;
     double atol_inner = std::max(chord ? 0.1 * target : lin_floor, o.momentum_rtol * std::min(r, r_rhs));
-    if (o.semi_implicit && !chord) atol_inner = lin_floor;  // linear in ui: one solve to the floor is the whole step
     if (chord && o.adaptive_forcing && ns->contraction > 0.0 && ns->contraction < 0.1) {
       const double predicted = ns->contraction * r;  // |F| the update can reach at best
       if (predicted < 0.5 * target)

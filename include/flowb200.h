@@ -207,8 +207,8 @@ typedef struct fb_ns_opts {
   int semi_implicit;     /* 0 (default): the reference's fully implicit convection ((grad ui) ui, v) - ((grad v) ui, ui).
                             1: semi-implicit linearisation ((grad ui) u0, v) - ((grad v) u0, ui), the (u^k . grad) u^{k+1}
                             treatment the reference's notes recommend (pressure_correction.py:96-101, :204-219) but do not
-                            implement: the tentative-velocity system becomes linear in ui (one assembly and one linear
-                            solve per step) and keeps the skew-symmetric form; an O(dt) different discretisation, NOT the
+                            implement: the tentative-velocity system becomes linear in ui (one assembly per step, the
+                            second update -- if the first solve's tolerance leaves one -- reuses the matrix) and keeps the skew-symmetric form; an O(dt) different discretisation, NOT the
                             reference's numbers (parity: oracle variant of the same form) */
   int inner_local;       /* 1 (default): in partitioned runs the Chebyshev preconditioner is the polynomial of each rank's
                             owned x owned block of S (no halo exchange inside the preconditioner: 3 of the 4 exchanges of
