@@ -568,7 +568,7 @@ int fb_ns_opts_default(fb_ns_opts *o) {
   o->newton_overshoot = 1e-3;
   o->inner_chebyshev = 1;
   o->semi_implicit = 0;
-  o->inner_local = 1;
+  o->inner_local = 0;
   o->deterministic_assembly = 0;
   return FB_OK;
 }
@@ -1043,7 +1043,10 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
         ChebWork *w;
         int degree;
       } cheb{ctx, inner.S, ns->dinv_S.p, &ns->cheb, o.chebyshev_degree > 0 ? o.chebyshev_degree : 4};
-      ns->cheb.local = o.inner_local != 0 && fb_is_distributed(ctx);
+      {
+        const char *e = getenv("FB_INNER_LOCAL");  // experiment knob; the option is opts.inner_local
+        ns->cheb.local = (e ? atoi(e) != 0 : o.inner_local != 0) && fb_is_distributed(ctx);
+      }
       if (o.inner_chebyshev && inner.S.tile && inner.S.tval && ns->cheb.lmax > 0.0 && !(o.inner_fp32 && ns->Sval32.p)) {
         // fixed polynomial in S instead of CG iterations: degree - 1 products, each one fused kernel
         pc.self = &cheb;

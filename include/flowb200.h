@@ -210,10 +210,11 @@ typedef struct fb_ns_opts {
                             implement: the tentative-velocity system becomes linear in ui (one assembly per step, the
                             second update -- if the first solve's tolerance leaves one -- reuses the matrix) and keeps the skew-symmetric form; an O(dt) different discretisation, NOT the
                             reference's numbers (parity: oracle variant of the same form) */
-  int inner_local;       /* 1 (default): in partitioned runs the Chebyshev preconditioner is the polynomial of each rank's
-                            owned x owned block of S (no halo exchange inside the preconditioner: 3 of the 4 exchanges of
-                            an outer iteration disappear); the flexible outer iteration keeps the global operator, so the
-                            solution is unchanged.  0: global S, one halo exchange per product */
+  int inner_local;       /* 0 (default).  1: in partitioned runs the Chebyshev preconditioner is the polynomial of each rank's
+                            owned x owned block of S (no halo exchange inside the preconditioner); the flexible outer
+                            iteration keeps the global operator.  Measured at N = 2, n = 74: 33.6 instead of 29.8 outer
+                            iterations, 101 instead of 96 ms per step -- the saved exchanges do not pay for the weaker
+                            preconditioner; experimental */
   int deterministic_assembly; /* 0 (default): the Jacobian is scatter-added with fp64 atomics (values reproducible to rounding,
                             not bit for bit).  1: two passes -- element blocks stored cell by cell, then every matrix block
                             sums its contributions in a fixed order (ascending cell): bit-reproducible Jacobian, no atomics,
