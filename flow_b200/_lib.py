@@ -64,6 +64,7 @@ class NSOpts(C.Structure):
         ("semi_implicit", C.c_int),
         ("inner_local", C.c_int),
         ("deterministic_assembly", C.c_int),
+        ("momentum_amg_kappa", C.c_double),
     ]
 
 

@@ -67,6 +67,16 @@ __global__ void k_sin_fill(int64_t n, double *x) {
     x[i] = sin((double)i);
 }
 
+// component c of an interleaved vector <-> contiguous vector (AMG on the scalar operator S, component by component)
+__global__ void k_comp_gather(int64_t nnodes, int D, int c, const double *__restrict__ v, double *__restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnodes; i += (int64_t)gridDim.x * blockDim.x) out[i] = v[i * D + c];
+}
+__global__ void k_comp_scatter(int64_t nnodes, int D, int c, const double *__restrict__ in, const uint8_t *__restrict__ mask,
+                               double *__restrict__ z) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnodes; i += (int64_t)gridDim.x * blockDim.x)
+    z[i * D + c] = (mask && mask[i * D + c]) ? 0.0 : in[i];
+}
+
 static inline int vgrid(fb_ctx *ctx, int64_t n) {
   int64_t g = (n + 255) / 256;
   const int cap = ctx->dev->sm_count * 8;
@@ -454,10 +464,13 @@ struct fb_ns {
   double dt_prev = 0.0, r0_prev = 0.0;
   fb_amg *amg_p = nullptr;      // AMG hierarchy of the P1 stiffness (pure Neumann variant)
   fb_amg *amg_pbc = nullptr;    // ... of the Dirichlet-eliminated matrix, rebuilt when the constrained set changes
+  fb_amg *amg_S = nullptr;      // AMG hierarchy of S = M + theta dt nu K (diffusion-dominated steps, see fb_ns_step)
+  DBuf<double> amgS_in, amgS_out;
   std::vector<int64_t> amg_pbc_dofs;
   ~fb_ns() {
     if (amg_p) amg_destroy(amg_p);
     if (amg_pbc) amg_destroy(amg_pbc);
+    if (amg_S) amg_destroy(amg_S);
   }
 };
 
@@ -569,6 +582,7 @@ int fb_ns_opts_default(fb_ns_opts *o) {
   o->inner_chebyshev = 1;
   o->semi_implicit = 0;
   o->inner_local = 0;
+  o->momentum_amg_kappa = 60.0;
   o->deterministic_assembly = 0;
   return FB_OK;
 }
@@ -975,12 +989,35 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
         if (ns->Mu.tval.p) {  // same operator in tile order
           ns->Sval_t.alloc((size_t)ns->W->tile->nent);
           tile_pack(ctx, *ns->W->tile, ns->Sval.p, ns->Sval_t.p);
-          if (o.inner_chebyshev) {  // spectrum of D^-1 S for the polynomial preconditioner (set-up: S changed)
-            LinOp Sop = make_linop(ns->Mu, D, n_ubc > 0 ? ns->mask_u.p : nullptr);
-            Sop.val = ns->Sval.p;
-            Sop.tval = ns->Sval_t.p;
-            cheb_estimate_spectrum(ctx, Sop, ns->dinv_S.p, 12, &ns->cheb.lmin, &ns->cheb.lmax);
-          }
+        }
+        {  // spectrum of D^-1 S (set-up: S changed): Chebyshev interval, and the choice of the preconditioner
+          LinOp Sop = make_linop(ns->Mu, D, n_ubc > 0 ? ns->mask_u.p : nullptr);
+          Sop.val = ns->Sval.p;
+          if (Sop.tile) Sop.tval = ns->Sval_t.p;
+          cheb_estimate_spectrum(ctx, Sop, ns->dinv_S.p, 12, &ns->cheb.lmin, &ns->cheb.lmax);
+        }
+        // Diffusion-dominated steps (dt nu / h^2 >> 1, e.g. BASELINE.json config 2): S is stiffness-like, a fixed low-degree
+        // polynomial is a weak inverse (kappa(D^-1 S) in the hundreds) and the outer iteration count explodes.  There the
+        // preconditioner is one smoothed-aggregation AMG V-cycle on S per velocity component (what the reference would get
+        // from hypre_amg on this block, cf. the commented-out solver block at pressure_correction.py:237-251).  The
+        // mass-dominated benchmark step (kappa ~ 10) keeps the polynomial.  Single GPU only.
+        if (ns->amg_S) {
+          amg_destroy(ns->amg_S);
+          ns->amg_S = nullptr;
+        }
+        const double kappa_S = ns->cheb.lmin > 0.0 ? ns->cheb.lmax / ns->cheb.lmin : 0.0;
+        if (o.momentum_amg_kappa > 0.0 && kappa_S > o.momentum_amg_kappa && !fb_is_distributed(ctx) && ns->W->n_owned >= 4096) {
+          fb_space *Wh = ns->Wh;
+          fb_space_build_pattern(Wh);
+          const int64_t nn = Wh->nnodes, nnz = (int64_t)Wh->indices.size();
+          std::vector<int> rp(nn + 1);
+          for (int64_t i = 0; i <= nn; ++i) rp[i] = (int)Wh->indptr[i];
+          std::vector<double> val((size_t)nnz);
+          FB_CUDA(cudaStreamSynchronize(st));
+          FB_CUDA(cudaMemcpy(val.data(), ns->Sval.p, sizeof(double) * nnz, cudaMemcpyDeviceToHost));
+          ns->amg_S = amg_setup(ctx, (int)Wh->n_owned, rp.data(), Wh->indices.data(), val.data());
+          ns->amgS_in.alloc((size_t)nn);
+          ns->amgS_out.alloc((size_t)nn);
         }
         ns->S_key = c2;
         ns->S_bc_hash = bc_hash;
@@ -1054,6 +1091,27 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
           ChebCall *c = static_cast<ChebCall *>(self);
           cheb_apply(c->ctx, c->S, c->dinv, c->w->lmin, c->w->lmax, c->degree, v, z, *c->w);
           *ii = c->degree - 1;
+          return FB_OK;
+        };
+      }
+      struct AmgSCall {
+        fb_ctx *ctx;
+        fb_ns *ns;
+        const uint8_t *mask;
+      } amgS{ctx, ns, n_ubc > 0 ? ns->mask_u.p : nullptr};
+      if (ns->amg_S) {
+        pc.self = &amgS;
+        pc.apply = [](void *self, const double *v, double *z, int *ii) -> int {
+          AmgSCall *c = static_cast<AmgSCall *>(self);
+          fb_ns *n_ = c->ns;
+          const int64_t nn = n_->W->n_owned;
+          const int Dd = n_->D;
+          for (int comp = 0; comp < Dd; ++comp) {
+            FB_LAUNCH(c->ctx, k_comp_gather, vgrid(c->ctx, nn), 256, 0, nn, Dd, comp, v, n_->amgS_in.p);
+            amg_apply(n_->amg_S, n_->amgS_in.p, n_->amgS_out.p);
+            FB_LAUNCH(c->ctx, k_comp_scatter, vgrid(c->ctx, nn), 256, 0, nn, Dd, comp, n_->amgS_out.p, c->mask, z);
+          }
+          *ii = Dd;
           return FB_OK;
         };
       }

@@ -1428,8 +1428,8 @@ struct JcfShared {
 
 // ELEM = 0: scatter-add into the matrix (fp64 atomics through smap); ELEM = 1: store the element blocks cell by cell
 // (val = element buffer, nc * NL * NL * D * D doubles) for the deterministic gather pass k_jac_gather
-template <int D, int ELEM = 0>
-__global__ void __launch_bounds__(MOM_WARPS * 32)
+template <int D, int ELEM = 0, int MINB = 1>
+__global__ void __launch_bounds__(MOM_WARPS * 32, MINB)
     k_momentum_J_cf(int64_t nc, const int *__restrict__ cell_nodes, const int *__restrict__ cells,
                     const double *__restrict__ xyz, const int *__restrict__ rowptr, const int *__restrict__ smap,
                     MomentumArgs a, double *__restrict__ val) {
@@ -1742,10 +1742,18 @@ void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W_, const MomentumArgs &a,
     }
     return;  // the facet terms are in
   } else if (variant == 2) {
+    // resident blocks per SM the register allocation is bounded for (FB_J_MINB, experiments): 162 registers unbounded
+    static const int minb = getenv("FB_J_MINB") ? atoi(getenv("FB_J_MINB")) : 4;
     if (D == 2)
       FB_LAUNCH(ctx, k_momentum_J_cf<2>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
-    else
+    else if (minb <= 3)
       FB_LAUNCH(ctx, k_momentum_J_cf<3>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
+    else if (minb == 4)
+      FB_LAUNCH(ctx, (k_momentum_J_cf<3, 0, 4>), g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
+    else if (minb == 5)
+      FB_LAUNCH(ctx, (k_momentum_J_cf<3, 0, 5>), g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
+    else
+      FB_LAUNCH(ctx, (k_momentum_J_cf<3, 0, 6>), g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
   } else if (D == 2) {
     FB_LAUNCH(ctx, k_momentum_J<2>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
   } else {

@@ -219,6 +219,11 @@ typedef struct fb_ns_opts {
                             not bit for bit).  1: two passes -- element blocks stored cell by cell, then every matrix block
                             sums its contributions in a fixed order (ascending cell): bit-reproducible Jacobian, no atomics,
                             +17.5 GB of scratch and ~1.3x the assembly time at 10 M dofs */
+  double momentum_amg_kappa; /* 60 (default).  When the estimated condition number of the Jacobi-scaled S = M + theta dt nu K
+                            exceeds this (diffusion-dominated steps, dt nu / h^2 >> 1: BASELINE.json config 2), the
+                            preconditioner of the FB_GMRES momentum solver is one smoothed-aggregation AMG V-cycle on S per
+                            velocity component instead of the Chebyshev polynomial / CG iterations (single GPU, >= 4096
+                            nodes); 0: never */
 } fb_ns_opts;
 
 typedef struct fb_ns_stats {

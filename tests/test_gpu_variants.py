@@ -25,6 +25,8 @@ VARIANTS = {
     "fgmres_inner8": dict(momentum_solver="fgmres", momentum_inner_its=8),
     "fgmres_inner_fp32": dict(momentum_solver="fgmres", inner_fp32=1),
     "inner_cg": dict(inner_chebyshev=0),
+    "momentum_amg_on_S": dict(momentum_amg_kappa=1.0),   # force the AMG V-cycle on S as the FGMRES preconditioner
+    "momentum_no_amg": dict(momentum_amg_kappa=0.0),
     "chebyshev_degree6": dict(chebyshev_degree=6),
     "chord": dict(CHORD),
     "chord_within_step_only": dict(jacobian_reuse=1, jacobian_across_steps=0, adaptive_forcing=0),
