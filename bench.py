@@ -300,6 +300,8 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = launches()
+    hc0, ac0 = _lib.i64(), _lib.i64()
+    lib.fb_ctx_comm_counts(ctx, C.byref(hc0), C.byref(ac0))
     del hist[:]
     _lib.check(lib.fb_ctx_timer_start(ctx), ctx)
     for _ in range(args.steps):
@@ -310,6 +312,15 @@ def main():
     barrier()
     clocks = sampler.summary()
     gpu_launches = launches() - l0
+    comm = None
+    if world > 1:  # halo exchanges + all-reduces of the timed steps, priced with their measured latency
+        hc1, ac1 = _lib.i64(), _lib.i64()
+        lib.fb_ctx_comm_counts(ctx, C.byref(hc1), C.byref(ac1))
+        hus, aus = C.c_double(), C.c_double()
+        _lib.check(lib.fb_space_bench_comm(W.handle(), 3, 200, C.byref(hus), C.byref(aus)), ctx, "fb_space_bench_comm")
+        nh, na = (hc1.value - hc0.value) / args.steps, (ac1.value - ac0.value) / args.steps
+        comm = {"halo_exchanges_per_step": nh, "allreduces_per_step": na, "halo_us": hus.value, "allreduce_us": aus.value,
+                "comm_ms_per_step": (nh * hus.value + na * aus.value) * 1e-3}
     t = torch.tensor([ms.value], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -492,6 +503,9 @@ def main():
             "phase_ms": {"tentative": avg("ms_tentative"), "pressure": avg("ms_pressure"), "correction": avg("ms_correction"),
                          "assembly_J": avg("ms_assembly_J"), "momentum_solve": avg("ms_momentum_solve")},
             "newton_residuals_last_step": timed[-1]["newton_residuals"],
+            "comm": dict(comm, share_of_step=comm["comm_ms_per_step"] / ms_per_step,
+                         note="exchanges / reductions enqueued on rank 0 x latency of one back-to-back exchange of the velocity halo "
+                              "(3 components) / one 2-slot all-reduce, own kernels over NVLink peer memory") if comm else None,
             "checksum": checksum, "setup_s": t_setup, "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
             "other_kernels": extra, "variants": variants, "cpu_baseline": cpu,
         }

@@ -103,6 +103,8 @@ SIGNATURES = {
     "fb_last_error": (C.c_char_p, [vp]),
     "fb_status_string": (C.c_char_p, [C.c_int]),
     "fb_ctx_launch_count": (C.c_int, [vp, pi64]),
+    "fb_ctx_comm_counts": (C.c_int, [vp, pi64, pi64]),
+    "fb_space_bench_comm": (C.c_int, [vp, C.c_int, C.c_int, pd, pd]),
     "fb_ctx_timer_start": (C.c_int, [vp]),
     "fb_ctx_timer_stop": (C.c_int, [vp, pd]),
     "fb_host_alloc": (C.c_int, [vp, i64, C.POINTER(vp)]),

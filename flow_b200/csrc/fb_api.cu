@@ -172,6 +172,13 @@ int fb_ctx_launch_count(fb_ctx *ctx, int64_t *count) {
   return FB_OK;
 }
 
+int fb_ctx_comm_counts(fb_ctx *ctx, int64_t *halo_exchanges, int64_t *allreduces) {
+  if (!ctx) return FB_EINVAL;
+  if (halo_exchanges) *halo_exchanges = ctx->halo_calls;
+  if (allreduces) *allreduces = ctx->allreduce_calls;
+  return FB_OK;
+}
+
 int fb_ctx_timer_start(fb_ctx *ctx) {
   FB_NEED_DEVICE(ctx);
   FB_API_BEGIN(ctx)
@@ -263,6 +270,38 @@ int fb_space_halo_exchange(fb_space *space, int ncomp, double *x) {
   halo_exchange(_ctx, *sp, dx.p, ncomp);
   FB_CUDA(cudaMemcpyAsync(x, dx.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   FB_CUDA(cudaStreamSynchronize(st));
+  FB_API_END
+}
+
+// Latency of one halo exchange of `ncomp` interleaved components on this space and of one all-reduce of a reduction
+// slot, back to back on the context's stream (collective: every rank calls it with the same arguments)
+int fb_space_bench_comm(fb_space *space, int ncomp, int reps, double *halo_us, double *allreduce_us) {
+  if (!space || ncomp < 1 || ncomp > 3 || reps < 1) return FB_EINVAL;
+  FB_NEED_DEVICE(space->mesh->ctx);
+  FB_API_BEGIN(space->mesh->ctx)
+  DevSpace *sp = dev_space(space);
+  fb_device_state *dv = _ctx->dev;
+  DBuf<double> x;
+  x.alloc((size_t)sp->nnodes * ncomp);
+  x.zero(dv->stream);
+  const int64_t h0 = _ctx->halo_calls, a0 = _ctx->allreduce_calls;
+  float ms = 0;
+  for (int i = 0; i < 3; ++i) halo_exchange(_ctx, *sp, x.p, ncomp);
+  FB_CUDA(cudaEventRecord(dv->ev[8], dv->stream));
+  for (int i = 0; i < reps; ++i) halo_exchange(_ctx, *sp, x.p, ncomp);
+  FB_CUDA(cudaEventRecord(dv->ev[9], dv->stream));
+  FB_CUDA(cudaEventSynchronize(dv->ev[9]));
+  FB_CUDA(cudaEventElapsedTime(&ms, dv->ev[8], dv->ev[9]));
+  if (halo_us) *halo_us = 1e3 * ms / reps;
+  for (int i = 0; i < 3; ++i) fb_allreduce_slots(_ctx, 40, 2);
+  FB_CUDA(cudaEventRecord(dv->ev[8], dv->stream));
+  for (int i = 0; i < reps; ++i) fb_allreduce_slots(_ctx, 40, 2);
+  FB_CUDA(cudaEventRecord(dv->ev[9], dv->stream));
+  FB_CUDA(cudaEventSynchronize(dv->ev[9]));
+  FB_CUDA(cudaEventElapsedTime(&ms, dv->ev[8], dv->ev[9]));
+  if (allreduce_us) *allreduce_us = 1e3 * ms / reps;
+  _ctx->halo_calls = h0;  // the benchmark's own calls do not count
+  _ctx->allreduce_calls = a0;
   FB_API_END
 }
 

@@ -388,6 +388,7 @@ PeerPtrs peer_ptrs(const fb_comm *c) {
 // sum red[slot0 .. slot0+count) over all ranks (in place, on the library stream)
 void fb_allreduce_slots(fb_ctx *ctx, int slot0, int count) {
   if (!fb_is_distributed(ctx)) return;
+  ctx->allreduce_calls++;
   fb_comm *c = ctx->comm;
   double *p = ctx->dev->red + slot0;
   if (c->p2p && count <= FB_AR_MAX) {
@@ -512,6 +513,7 @@ __global__ void k_halo_pack(int64_t nsend, int ncomp, const int *__restrict__ no
 // refresh x on the ghost nodes [n_owned, nnodes) from their owners
 void halo_exchange(fb_ctx *ctx, DevSpace &sp, double *x, int ncomp) {
   if (!fb_is_distributed(ctx) || sp.halo_ranks.empty()) return;
+  ctx->halo_calls++;
   fb_comm *c = ctx->comm;
   cudaStream_t st = ctx->dev->stream;
   const int nneigh = (int)sp.halo_ranks.size();

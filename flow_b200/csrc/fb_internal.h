@@ -15,6 +15,7 @@ struct fb_ctx {
   std::string err;
   fb_device_state *dev = nullptr;  // null for host-only contexts
   int64_t launches = 0;
+  int64_t halo_calls = 0, allreduce_calls = 0;  // exchanges / reductions enqueued by partitioned runs
   fb_comm *comm = nullptr;  // null: single rank
 };
 

@@ -112,6 +112,10 @@ int fb_comm_window_create(fb_ctx *ctx, int64_t staging_bytes_per_peer, void *han
 int fb_comm_window_open(fb_ctx *ctx, const void *handles);
 int fb_comm_window_disable(fb_ctx *ctx);
 int fb_comm_uses_peer_memory(fb_ctx *ctx);
+/* partitioned runs: halo exchanges / all-reduces enqueued so far on this context, and the latency of one of each
+ * (collective micro-benchmark) -- bench.py's communication share */
+int fb_ctx_comm_counts(fb_ctx *ctx, int64_t *halo_exchanges, int64_t *allreduces);
+int fb_space_bench_comm(fb_space *space, int ncomp, int reps, double *halo_us, double *allreduce_us);
 /* refresh the ghost entries of a host vector (ncomp interleaved components) -- test/debug helper */
 int fb_space_halo_exchange(fb_space *space, int ncomp, double *x);
 
