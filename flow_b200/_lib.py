@@ -65,6 +65,7 @@ class NSOpts(C.Structure):
         ("inner_local", C.c_int),
         ("deterministic_assembly", C.c_int),
         ("momentum_amg_kappa", C.c_double),
+        ("momentum_rtol_loose", C.c_double),
     ]
 
 

@@ -479,6 +479,8 @@ struct fb_ns {
   DBuf<double> ubc_vals, pbc_vals;
   KrylovWork kw_u, kw_p;
   double contraction = 0.0;  // |F| after / before the first Newton update of the previous step
+  double quad_C = 0.0;       // |F_1| / |F_0|^2 of the previous step: constant of the quadratic convergence model
+  DBuf<double> ui_prev, F_prev;  // iterate and right-hand side of a loosely solved update (kept for its refinement)
   // chord Jacobian carried across steps: valid for (dt, rho, mu, theta, constrained set) of its assembly
   bool J_valid = false;
   double J_key[4] = {0, 0, 0, 0};
@@ -622,6 +624,7 @@ int fb_ns_opts_default(fb_ns_opts *o) {
   o->semi_implicit = 0;
   o->inner_local = 0;
   o->momentum_amg_kappa = 60.0;
+  o->momentum_rtol_loose = 1e-3;
   o->deterministic_assembly = 0;
   return FB_OK;
 }
@@ -999,6 +1002,24 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     // (first update of a step: |F| is dominated by the rows u - g of dofs whose boundary value changed)
     const double r_rhs = lifted ? vec_norm2_sync(ctx, ns->F.p, nu_o) : r;
     double atol_inner = std::max(chord ? 0.1 * target : lin_floor, o.momentum_rtol * std::min(r, r_rhs));
+    // Which updates need the tight tolerance?  Only the LAST one is part of the accepted iterate; an earlier one merely has
+    // to land in the basin where the next exact update converges to the same point (Newton maps an error e of the
+    // iterate to O(|e| |x - x*|)).  With the quadratic model |F_next| ~ C |F|^2 (C from the previous time step) an update
+    // predicted to stay above 10 atol is not the last: it is solved to momentum_rtol_loose only.  If the prediction was
+    // wrong -- the new residual comes out below 30 atol, i.e. this update decides whether the reference stops here --
+    // the SAME linear system is solved on to the tight tolerance (warm-started from the loose solution) before the
+    // acceptance test is read (see below).
+    bool loose = false;
+    if (!chord && !o.semi_implicit && o.momentum_rtol_loose > o.momentum_rtol && ns->quad_C > 0.0 &&
+        ns->quad_C * r * r > 10.0 * o.newton_atol) {
+      loose = true;
+      atol_inner = std::max(lin_floor, o.momentum_rtol_loose * std::min(r, r_rhs));
+      ns->ui_prev.alloc((size_t)nu);
+      ns->F_prev.alloc((size_t)nu);
+      FB_CUDA(cudaMemcpyAsync(ns->ui_prev.p, ns->ui.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
+      FB_CUDA(cudaMemcpyAsync(ns->F_prev.p, ns->F.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
+    }
+    const double atol_tight = std::max(lin_floor, o.momentum_rtol * std::min(r, r_rhs));
     if (chord && o.adaptive_forcing && ns->contraction > 0.0 && ns->contraction < 0.1) {
       const double predicted = ns->contraction * r;  // |F| the update can reach at best
       if (predicted < 0.5 * target)
@@ -1008,6 +1029,8 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     }
     int its = 0;
     int status;
+    bool applied = false;     // loose path: the update is already in ui and its residual known
+    double r_applied = 0.0;
     FB_NVTX("momentum linear solve");
     if (o.momentum_solver == FB_GMRES) {
       // flexible GMRES preconditioned by a few CG iterations on S (x) I, S = M + theta dt nu K (constant in time)
@@ -1155,14 +1178,31 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
         };
       }
       int inner_its = 0;
-      status = krylov_fgmres(ctx, Jop, pc, ns->F.p, ns->delta.p, atol_inner, o.momentum_maxit,
-                             std::min(o.gmres_restart > 0 ? o.gmres_restart : 20, 20), ns->fw, &its, &inner_its);
+      const int restart = std::min(o.gmres_restart > 0 ? o.gmres_restart : 20, 20);
+      status = krylov_fgmres(ctx, Jop, pc, ns->F.p, ns->delta.p, atol_inner, o.momentum_maxit, restart, ns->fw, &its, &inner_its);
       s.reserved[5] += inner_its;
+      if (status == FB_OK && loose) {
+        // tentative update; if it turns out to decide the acceptance test, finish the linear solve first
+        vec_axpby(ctx, ns->ui.p, 1.0, ns->ui_prev.p, -1.0, ns->delta.p, nu_o);
+        if (lifted) vec_axpy(ctx, ns->ui.p, -1.0, ns->xg_u.p, nu_o);
+        halo_exchange(ctx, *ns->W, ns->ui.p, D);
+        r_applied = residual();
+        applied = true;
+        if (r_applied < 30.0 * o.newton_atol) {
+          FB_CUDA(cudaMemcpyAsync(ns->F.p, ns->F_prev.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
+          int its2 = 0, inner2 = 0;
+          status = krylov_fgmres(ctx, Jop, pc, ns->F.p, ns->delta.p, atol_tight, o.momentum_maxit, restart, ns->fw, &its2, &inner2,
+                                 /*warm_start=*/true);
+          its += its2;
+          s.reserved[5] += inner2;
+          FB_CUDA(cudaMemcpyAsync(ns->ui.p, ns->ui_prev.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
+          applied = false;  // the update is applied below from the refined delta
+        }
+      }
     } else {
       status = krylov_bicgstab(ctx, Jop, ns->binv.p, ns->F.p, ns->delta.p, atol_inner, o.momentum_maxit, mom_check,
                                ns->kw_u, &its);
     }
-    if (lifted) vec_axpy(ctx, ns->delta.p, 1.0, ns->xg_u.p, nu_o);
     s.momentum_its += its;
     FB_CUDA(cudaEventRecord(dv->ev[10], st));
     if (status != FB_OK) {
@@ -1170,16 +1210,23 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
       snprintf(buf, sizeof buf, "momentum Krylov solver failed after %d iterations (%s)", its, fb_status_string(status));
       return fb_fail(ctx, status == FB_ENAN ? FB_ENAN : FB_ENOCONV_KRYLOV, buf);
     }
-    vec_axpy(ctx, ns->ui.p, -1.0, ns->delta.p, nu_o);
-    halo_exchange(ctx, *ns->W, ns->ui.p, D);  // the next assembly reads ui on ghost nodes
+    if (!applied) {
+      if (lifted) vec_axpy(ctx, ns->delta.p, 1.0, ns->xg_u.p, nu_o);
+      vec_axpy(ctx, ns->ui.p, -1.0, ns->delta.p, nu_o);
+      halo_exchange(ctx, *ns->W, ns->ui.p, D);  // the next assembly reads ui on ghost nodes
+    }
     ++newton;
-    const double r_new = residual();
+    const double r_new = applied ? r_applied : residual();
     const double ratio = r > 0.0 ? r_new / r : 0.0;
-    if (newton == 1) ns->contraction = ratio;
+    if (newton == 1) {
+      ns->contraction = ratio;
+      ns->quad_C = (r > 0.0 && r_new == r_new) ? r_new / (r * r) : 0.0;
+    }
     reuse_ok = ratio < 0.1;
     last_ratio = ratio;
     r = r_new;
     if (newton < 5) s.reserved[newton] = r;
+    FB_CUDA(cudaEventSynchronize(dv->ev[10]));  // (the loose path reads its residual before this event)
     FB_CUDA(cudaEventElapsedTime(&ms, dv->ev[4], dv->ev[5]));
     s.ms_assembly_J += ms;
     FB_CUDA(cudaEventElapsedTime(&ms, dv->ev[5], dv->ev[10]));

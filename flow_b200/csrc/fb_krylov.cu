@@ -600,7 +600,7 @@ __global__ void k_scale_to(int64_t n, double a, const double *__restrict__ in, d
 }  // namespace
 
 int krylov_fgmres(fb_ctx *ctx, const LinOp &A, const FgmresPrecond &pc, const double *b, double *x, double atol, int maxit,
-                  int m, FgmresWork &fw, int *iters, int *inner_iters) {
+                  int m, FgmresWork &fw, int *iters, int *inner_iters, bool warm_start) {
   fb_device_state *dv = ctx->dev;
   cudaStream_t st = dv->stream;
   const int64_t n = A.ndofs(), nl = A.nlocal_dofs();
@@ -611,8 +611,8 @@ int krylov_fgmres(fb_ctx *ctx, const LinOp &A, const FgmresPrecond &pc, const do
   double *hp = dv->host_pinned;
   std::vector<double> H((size_t)(m + 1) * m), cs(m), sn(m), gv(m + 1), yv(m);
   int total = 0, inner_total = 0;
-  bool converged = false, first = true;
-  FB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * nl, st));
+  bool converged = false, first = !warm_start;  // warm start: x holds an initial guess, the first cycle starts from b - A x
+  if (!warm_start) FB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * nl, st));
   double *w = fw.w.p;
   while (!converged && total < maxit) {
     // r = b - A x  (x = 0 in the first cycle)

@@ -211,7 +211,7 @@ struct FgmresWork {
   }
 };
 int krylov_fgmres(fb_ctx *ctx, const LinOp &A, const FgmresPrecond &pc, const double *b, double *x, double atol, int maxit,
-                  int m, FgmresWork &fw, int *iters, int *inner_iters);
+                  int m, FgmresWork &fw, int *iters, int *inner_iters, bool warm_start = false);
 
 // Chebyshev polynomial preconditioner z = p_m(D^-1 A) D^-1 v for an SPD operator in tile format (fb_krylov.cu):
 // m - 1 products, each ONE kernel (the vector updates of the iteration live in the product's epilogue), no inner

@@ -228,6 +228,11 @@ typedef struct fb_ns_opts {
                             preconditioner of the FB_GMRES momentum solver is one smoothed-aggregation AMG V-cycle on S per
                             velocity component instead of the Chebyshev polynomial / CG iterations (single GPU, >= 4096
                             nodes); 0: never */
+  double momentum_rtol_loose; /* 1e-3 (default).  Relative tolerance of Newton updates that are predicted NOT to be the last one
+                            (quadratic model |F_next| ~ C |F|^2 with C from the previous step, prediction > 10 newton_atol):
+                            only the last update is part of the accepted iterate.  A wrong prediction is caught: if the
+                            residual after a loosely solved update is below 30 newton_atol, the same linear system is solved
+                            on to the tight tolerance before the acceptance test is read.  <= momentum_rtol: every update tight */
 } fb_ns_opts;
 
 typedef struct fb_ns_stats {

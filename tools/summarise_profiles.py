@@ -15,7 +15,9 @@ def main(path):
     for r in rows[hdr + 2:]:
         if len(r) <= vi:
             continue
-        k = r[ki].split("(")[0]
+        k = r[ki].replace("void ", "").replace("<unnamed>::", "").replace("(anonymous namespace)::", "")
+        k = k.split("(")[0] if not k.startswith("(") else k
+        k = k.replace("(int)", "")
         agg[k][0] += 1
         agg[k][1] += float(r[vi].replace(",", "")) / 1e6
     tot = sum(v[1] for v in agg.values())
