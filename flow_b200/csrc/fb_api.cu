@@ -623,7 +623,7 @@ int fb_ns_opts_default(fb_ns_opts *o) {
   o->inner_chebyshev = 1;
   o->semi_implicit = 0;
   o->inner_local = 0;
-  o->momentum_amg_kappa = 60.0;
+  o->momentum_amg_kappa = 0.0;
   o->momentum_rtol_loose = 1e-3;
   o->deterministic_assembly = 0;
   return FB_OK;

@@ -1742,8 +1742,9 @@ void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W_, const MomentumArgs &a,
     }
     return;  // the facet terms are in
   } else if (variant == 2) {
-    // resident blocks per SM the register allocation is bounded for (FB_J_MINB, experiments): 162 registers unbounded
-    static const int minb = getenv("FB_J_MINB") ? atoi(getenv("FB_J_MINB")) : 4;
+    // resident blocks per SM the register allocation is bounded for (FB_J_MINB, experiments).  Measured at n = 74, ms per
+    // assembly: unbounded (198 registers, 3 blocks/SM) 16.2; 4 blocks (128 registers, spills) 21.2; 5 (96) 32.7; 6 (80) 49.6
+    static const int minb = getenv("FB_J_MINB") ? atoi(getenv("FB_J_MINB")) : 3;
     if (D == 2)
       FB_LAUNCH(ctx, k_momentum_J_cf<2>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
     else if (minb <= 3)

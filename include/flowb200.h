@@ -223,11 +223,12 @@ typedef struct fb_ns_opts {
                             not bit for bit).  1: two passes -- element blocks stored cell by cell, then every matrix block
                             sums its contributions in a fixed order (ascending cell): bit-reproducible Jacobian, no atomics,
                             +17.5 GB of scratch and ~1.3x the assembly time at 10 M dofs */
-  double momentum_amg_kappa; /* 60 (default).  When the estimated condition number of the Jacobi-scaled S = M + theta dt nu K
-                            exceeds this (diffusion-dominated steps, dt nu / h^2 >> 1: BASELINE.json config 2), the
+  double momentum_amg_kappa; /* 0 (default: never).  > 0: when the estimated condition number of the Jacobi-scaled
+                            S = M + theta dt nu K exceeds it (diffusion-dominated steps, BASELINE.json config 2), the
                             preconditioner of the FB_GMRES momentum solver is one smoothed-aggregation AMG V-cycle on S per
-                            velocity component instead of the Chebyshev polynomial / CG iterations (single GPU, >= 4096
-                            nodes); 0: never */
+                            velocity component (single GPU, >= 4096 nodes).  Measured on config 2 (n = 333): 90 instead of 103
+                            outer iterations per step but 47 instead of 31 ms -- what S (x) I lacks there is the viscous
+                            coupling of the components, not a better inverse of S; off by default */
   double momentum_rtol_loose; /* 1e-3 (default).  Relative tolerance of Newton updates that are predicted NOT to be the last one
                             (quadratic model |F_next| ~ C |F|^2 with C from the previous step, prediction > 10 newton_atol):
                             only the last update is part of the accepted iterate.  A wrong prediction is caught: if the
