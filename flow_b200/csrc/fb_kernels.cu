@@ -1329,10 +1329,10 @@ void assemble_momentum_F_new_state(fb_ctx *ctx, const DevSpace &W, const Momentu
   const int gf = grid_for(W.nbf * W.nl * W.dim, 128, ctx->dev->sm_count * 16);
   if (W.dim == 2) {
     momentum_F_cells<2>(ctx, W, a, a.ui, 1.0, a.theta, F, a.adv);
-    if (W.nbf) FB_LAUNCH(ctx, k_momentum_F_facets<2>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.cells.p, W.xyz.p, a, F);
+    if (W.nbf && !a.skip_facets) FB_LAUNCH(ctx, k_momentum_F_facets<2>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.cells.p, W.xyz.p, a, F);
   } else {
     momentum_F_cells<3>(ctx, W, a, a.ui, 1.0, a.theta, F, a.adv);
-    if (W.nbf) FB_LAUNCH(ctx, k_momentum_F_facets<3>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.cells.p, W.xyz.p, a, F);
+    if (W.nbf && !a.skip_facets) FB_LAUNCH(ctx, k_momentum_F_facets<3>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.cells.p, W.xyz.p, a, F);
   }
 }
 
@@ -1730,7 +1730,7 @@ void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W_, const MomentumArgs &a,
     if (!W.gptr.p) build_gather_map(ctx, W);
     W.ebuf.alloc((size_t)W.nc * W.nl * W.nl * D * D);
     const int gg = grid_for(W.n_owned * 8, 256, ctx->dev->sm_count * 16);
-    const bool facets = W.nbf && a.theta != 0.0;
+    const bool facets = W.nbf && a.theta != 0.0 && !a.skip_facets;
     if (D == 2) {
       FB_LAUNCH(ctx, (k_momentum_J_cf<2, 1>), g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, W.ebuf.p);
       if (facets) FB_LAUNCH(ctx, k_momentum_J_facets_elem<2>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cells.p, W.xyz.p, a, W.ebuf.p);
@@ -1760,7 +1760,7 @@ void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W_, const MomentumArgs &a,
   } else {
     FB_LAUNCH(ctx, k_momentum_J<3>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
   }
-  if (W.nbf && a.theta != 0.0) {
+  if (W.nbf && a.theta != 0.0 && !a.skip_facets) {
     if (D == 2)
       FB_LAUNCH(ctx, k_momentum_J_facets<2>, gf, 128, 0, W.nbf, W.bf_cell.p, W.bf_local.p, W.cell_nodes.p, W.cells.p, W.xyz.p,
                 W.rowptr.p, W.smap.p, a, Jval);

@@ -138,6 +138,7 @@ struct MomentumArgs {
   double dt, rho, mu, theta;
   const double *ui, *u0, *p0;
   const int *pcn;  // cell -> P1 dofs of the pressure space
+  bool skip_facets = false;     // every boundary dof is constrained: the exterior-facet terms only touch overwritten rows
   const double *adv = nullptr;  // semi-implicit linearisation: advecting velocity of the new-state convection (null: ui)
 };
 void assemble_momentum_F(fb_ctx *ctx, const DevSpace &W, const MomentumArgs &a, double *F);  // zero + both parts

@@ -229,11 +229,13 @@ typedef struct fb_ns_opts {
                             velocity component (single GPU, >= 4096 nodes).  Measured on config 2 (n = 333): 90 instead of 103
                             outer iterations per step but 47 instead of 31 ms -- what S (x) I lacks there is the viscous
                             coupling of the components, not a better inverse of S; off by default */
-  double momentum_rtol_loose; /* 1e-3 (default).  Relative tolerance of Newton updates that are predicted NOT to be the last one
-                            (quadratic model |F_next| ~ C |F|^2 with C from the previous step, prediction > 10 newton_atol):
-                            only the last update is part of the accepted iterate.  A wrong prediction is caught: if the
-                            residual after a loosely solved update is below 30 newton_atol, the same linear system is solved
-                            on to the tight tolerance before the acceptance test is read.  <= momentum_rtol: every update tight */
+  double momentum_rtol_loose; /* 1e-3 (default).  Upper bound of the relative tolerance of Newton updates that are predicted NOT to
+                            be the last one (quadratic model |F_next| ~ C |F|^2, C from the previous step): only the last
+                            update is part of the accepted iterate; an earlier one is solved just tightly enough that the
+                            final iterate stays within 1e-9 of the reference's (tighter when the reference's final residual
+                            is predicted close to newton_atol, see fb_api.cu).  A wrong prediction is caught: if the residual
+                            after a loosely solved update is below 30 newton_atol, the same linear system is solved on to the
+                            tight tolerance before the acceptance test is read.  <= momentum_rtol: every update tight */
 } fb_ns_opts;
 
 typedef struct fb_ns_stats {
