@@ -1531,6 +1531,145 @@ __global__ void __launch_bounds__(MOM_WARPS * 32, MINB)
   }
 }
 
+// Same closed form, other work split (experiment, FB_J_KERNEL=3): lane = (test node a, column j) -- NL * D lanes --
+// walks ALL trial nodes b and produces column j of every block (a, b).  The lane keeps only the j-slices of the
+// test-side operands in registers (GA[.][j], WA[.][j], S_a[j], GU[.][.][j]: 21 doubles instead of 27 + the block), every
+// trial-side operand is one address per warp (broadcast), M3 is read through a transposed copy (conflict free).  The
+// scalar part of the block (mass + skew convection + trace of the viscous part) needs the sum over the D lanes of a test
+// node: one quantity, two shuffles.
+template <int D>
+struct Jcf2Shared {
+  static constexpr int NL = Elem<D>::NL2, NV = D + 1;
+  double M3T[NL * NV * NL];  // [(b * NV + v) * NL + a]
+  double U[MOM_WARPS][NL][D];
+  double GV[MOM_WARPS][NL][NV * D];
+  double S[MOM_WARPS][NL][D];
+  double WT[MOM_WARPS][NL][NV * D];
+  double GU[MOM_WARPS][NV * D * D];
+};
+
+template <int D>
+__global__ void __launch_bounds__(MOM_WARPS * 32)
+    k_momentum_J_cf2(int64_t nc, const int *__restrict__ cell_nodes, const int *__restrict__ cells,
+                     const double *__restrict__ xyz, const int *__restrict__ rowptr, const int *__restrict__ smap,
+                     MomentumArgs a, double *__restrict__ val) {
+  constexpr int NL = Elem<D>::NL2, NV = D + 1, NP = NL * NL;
+  static_assert(NL * D <= 32, "one lane per (test node, column)");
+  __shared__ Jcf2Shared<D> s;
+  const double *tab = (D == 2) ? FB_M3_TRI : FB_M3_TET;
+  for (int t = threadIdx.x; t < NL * NL * NV; t += blockDim.x) {
+    const int ta = t / (NL * NV), r = t - ta * (NL * NV), tb = r / NV, v = r - tb * NV;
+    s.M3T[(tb * NV + v) * NL + ta] = tab[t];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t warp0 = blockIdx.x * (int64_t)MOM_WARPS + wid;
+  const int64_t nwarps = (int64_t)gridDim.x * MOM_WARPS;
+  const double c1 = 0.5 * a.theta * a.dt, c2 = a.theta * a.dt * a.mu / a.rho;
+  const double c1t = a.adv ? 0.0 : c1;
+  const double lm = 1.0 / ((D + 1) * (D + 2));
+  const bool active = lane < NL * D;
+  const int ta = active ? lane / D : 0, tj = active ? lane % D : 0;
+  const int lane0 = ta * D;  // first lane of this test node
+  for (int64_t c = warp0; c < nc; c += nwarps) {
+    const int *cn = cell_nodes + c * NL;
+    int r0 = 0, len = 0;
+    if (active) {
+      const int I = cn[ta];
+      r0 = rowptr[I];
+      len = (rowptr[I + 1] - r0) * D;
+    }
+    // ---- phase A (as k_momentum_J_cf)
+    double glam[D + 1][D], vol;
+    cell_geometry<D>(cells + c * (D + 1), xyz, glam, vol);
+    if (lane < NL * D) s.U[wid][lane / D][lane % D] = (a.adv ? a.adv : a.ui)[(int64_t)cn[lane / D] * D + lane % D];
+    for (int t = lane; t < NL * NV; t += 32) {
+      const int n = t / NV, w = t - n * NV;
+      double g[D];
+      fb_p2_vertex_grad<D>(n, w, glam, g);
+#pragma unroll
+      for (int k = 0; k < D; ++k) s.GV[wid][n][w * D + k] = g[k];
+    }
+    __syncwarp();
+    if (lane < NL * D) {
+      const int n = lane / D, k = lane % D;
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < NV; ++w) sum += s.GV[wid][n][w * D + k];
+      s.S[wid][n][k] = sum;
+    }
+    for (int t = lane; t < NV * D * D; t += 32) {
+      const int v = t / (D * D), i = (t / D) % D, j = t % D;
+      double sum = 0.0;
+#pragma unroll
+      for (int cc = 0; cc < NL; ++cc) sum += s.U[wid][cc][i] * s.GV[wid][cc][v * D + j];
+      s.GU[wid][t] = sum;
+    }
+    for (int t = lane; t < NL * NV * D; t += 32) {
+      const int n = t / (NV * D), w = (t / D) % NV, k = t % D;
+      double sum = 0.0;
+#pragma unroll
+      for (int cc = 0; cc < NL; ++cc) sum += s.M3T[(cc * NV + w) * NL + n] * s.U[wid][cc][k];  // M3[n][cc][w]
+      s.WT[wid][n][w * D + k] = sum;
+    }
+    __syncwarp();
+    // ---- phase B
+    double GAj[NV], WAj[NV], GUj[NV][D], SAj;
+#pragma unroll
+    for (int w = 0; w < NV; ++w) {
+      GAj[w] = s.GV[wid][ta][w * D + tj];
+      WAj[w] = s.WT[wid][ta][w * D + tj];
+#pragma unroll
+      for (int i = 0; i < D; ++i) GUj[w][i] = s.GU[wid][(w * D + i) * D + tj];
+    }
+    SAj = s.S[wid][ta][tj];
+#pragma unroll 2
+    for (int tb = 0; tb < NL; ++tb) {
+      const int slot = active ? smap[c * NP + ta * NL + tb] : 0;
+      double m3[NV], mab = 0.0;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        m3[v] = s.M3T[(tb * NV + v) * NL + ta];
+        mab += m3[v];
+      }
+      const double *GB = s.GV[wid][tb];  // [v * D + i], one address per warp
+      const double *WB = s.WT[wid][tb];
+      double Jc[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double g = s.S[wid][tb][i] * SAj, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          g += GB[v * D + i] * GAj[v];
+          t2 += m3[v] * GUj[v][i];
+          t3 += GAj[v] * WB[v * D + i];
+        }
+        Jc[i] = c1t * (t2 - t3) + c2 * lm * g;
+      }
+      // this lane's share of the scalar part: c1 (C_ab - C_ba) + c2 tr G, restricted to k = j
+      double q = s.S[wid][tb][tj] * SAj, cab = 0.0, cba = 0.0;
+#pragma unroll
+      for (int w = 0; w < NV; ++w) {
+        const double gbj = GB[w * D + tj], wbj = WB[w * D + tj];
+        q += gbj * GAj[w];
+        cab += gbj * WAj[w];
+        cba += GAj[w] * wbj;
+      }
+      q = c1 * (cab - cba) + c2 * lm * q;
+      double dg = q;
+#pragma unroll
+      for (int k = 1; k < D; ++k) dg += __shfl_sync(0xffffffffu, q, lane0 + (tj + k) % D);
+      dg += mab;
+      if (active) {
+        double *base = val + (int64_t)r0 * (D * D) + (int64_t)(slot - r0) * D + tj;
+#pragma unroll
+        for (int i = 0; i < D; ++i) atomicAdd(base + (int64_t)i * len, vol * (Jc[i] + (i == tj ? dg : 0.0)));
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // boundary-facet part of J: -theta dt/rho mu ((grad delta)^T n, v)_ds
 template <int D>
 __global__ void k_momentum_J_facets(int64_t nbf, const int *__restrict__ bf_cell, const int *__restrict__ bf_local,
@@ -1726,7 +1865,12 @@ void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W_, const MomentumArgs &a,
   // 2 (default): closed form (k_momentum_J_cf); 0: degree-5 quadrature (k_momentum_J), kept as the cross-check.
   // Measured at n = 74 on B200 (2.43 M cells): 14.7 ms vs 29.8 ms per launch.
   static const int variant = getenv("FB_J_KERNEL") ? atoi(getenv("FB_J_KERNEL")) : 2;
-  if (variant == 2 && use_two_pass(W)) {
+  if (variant == 3) {  // experiment: lane = (test node, column)
+    if (D == 2)
+      FB_LAUNCH(ctx, k_momentum_J_cf2<2>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
+    else
+      FB_LAUNCH(ctx, k_momentum_J_cf2<3>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
+  } else if (variant == 2 && use_two_pass(W)) {
     if (!W.gptr.p) build_gather_map(ctx, W);
     W.ebuf.alloc((size_t)W.nc * W.nl * W.nl * D * D);
     const int gg = grid_for(W.n_owned * 8, 256, ctx->dev->sm_count * 16);
