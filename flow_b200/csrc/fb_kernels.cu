@@ -1858,19 +1858,23 @@ void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W_, const MomentumArgs &a,
   DevSpace &W = const_cast<DevSpace &>(W_);
   const int D = W.dim;
   static const int variant0 = getenv("FB_J_KERNEL") ? atoi(getenv("FB_J_KERNEL")) : 2;
-  if (!(variant0 == 2 && use_two_pass(W)))  // the gather pass writes every block (rows without cells do not exist)
+  if (!((variant0 == 2 || variant0 == 4) && use_two_pass(W)))  // the gather pass writes every block (rows without cells do not exist)
     FB_CUDA(cudaMemsetAsync(Jval, 0, sizeof(double) * W.nnz * D * D, ctx->dev->stream));
   const int g = grid_for(W.nc * 32, MOM_WARPS * 32, ctx->dev->sm_count * 16);
   const int gf = grid_for(W.nbf * W.nl * W.nl, 128, ctx->dev->sm_count * 16);
   // 2 (default): closed form (k_momentum_J_cf); 0: degree-5 quadrature (k_momentum_J), kept as the cross-check.
   // Measured at n = 74 on B200 (2.43 M cells): 14.7 ms vs 29.8 ms per launch.
   static const int variant = getenv("FB_J_KERNEL") ? atoi(getenv("FB_J_KERNEL")) : 2;
-  if (variant == 3) {  // experiment: lane = (test node, column)
+  // closed form, lane = (test node, column): default in 3D (30 of 32 lanes; measured at n = 74: 12.4 ms per assembly
+  // against 15.5 ms for lane = (test node, trial group), 128 instead of 198 registers); in 2D only 12 lanes would work,
+  // the (test node, trial group) kernel stays.  FB_J_KERNEL=3 / 4 force the one / the other.
+  const bool column_lanes = variant == 3 || (variant == 2 && D == 3);
+  if (column_lanes && variant != 4 && !use_two_pass(W)) {
     if (D == 2)
       FB_LAUNCH(ctx, k_momentum_J_cf2<2>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
     else
       FB_LAUNCH(ctx, k_momentum_J_cf2<3>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
-  } else if (variant == 2 && use_two_pass(W)) {
+  } else if ((variant == 2 || variant == 4) && use_two_pass(W)) {
     if (!W.gptr.p) build_gather_map(ctx, W);
     W.ebuf.alloc((size_t)W.nc * W.nl * W.nl * D * D);
     const int gg = grid_for(W.n_owned * 8, 256, ctx->dev->sm_count * 16);
@@ -1885,7 +1889,7 @@ void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W_, const MomentumArgs &a,
       FB_LAUNCH(ctx, (k_jac_gather<3, 8>), gg, 256, 0, W.nnodes, W.rowptr.p, W.gptr.p, W.gsrc.p, W.ebuf.p, Jval);
     }
     return;  // the facet terms are in
-  } else if (variant == 2) {
+  } else if (variant == 2 || variant == 4) {
     // resident blocks per SM the register allocation is bounded for (FB_J_MINB, experiments).  Measured at n = 74, ms per
     // assembly: unbounded (198 registers, 3 blocks/SM) 16.2; 4 blocks (128 registers, spills) 21.2; 5 (96) 32.7; 6 (80) 49.6
     static const int minb = getenv("FB_J_MINB") ? atoi(getenv("FB_J_MINB")) : 3;
