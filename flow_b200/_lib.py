@@ -163,6 +163,7 @@ SIGNATURES = {
     "fb_ns_correction_rhs": (C.c_int, [vp, dbl, dbl, dbl, C.c_int, pd, pd, pd, pd]),
     "fb_heat_create": (C.c_int, [vp, vp, pd, dbl, dbl, dbl, pd, C.POINTER(vp)]),
     "fb_heat_create_supg": (C.c_int, [vp, vp, pd, dbl, dbl, dbl, pd, C.c_int, dbl, C.POINTER(vp)]),
+    "fb_supg_tau": (C.c_int, [vp, pd, dbl, C.c_int, pd]),
     "fb_heat_supg_mass": (C.c_int, [vp, pd]),
     "fb_heat_destroy": (C.c_int, [vp]),
     "fb_heat_eval": (C.c_int, [vp, dbl, dbl, pd, pd]),

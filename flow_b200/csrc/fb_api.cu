@@ -1434,6 +1434,21 @@ int fb_heat_create_supg(fb_space *Vsp, fb_space *Wsp, const double *conv, double
   FB_API_END
 }
 
+int fb_supg_tau(fb_space *Wsp, const double *conv, double epsilon, int p, double *tau_out) {
+  if (!Wsp || !conv || !tau_out || p < 1) return FB_EINVAL;
+  fb_ctx *ctx = Wsp->mesh->ctx;
+  FB_NEED_DEVICE(ctx);
+  if (Wsp->mesh->dim != 2 || Wsp->degree != 2 || Wsp->ncomp != 2)
+    return fb_fail(ctx, FB_EINVAL, "fb_supg_tau: triangles and a vector P2 convection field only (stabilization.py:84-92)");
+  FB_API_BEGIN(ctx)
+  DevSpace *W = dev_space(Wsp);
+  DBuf<double> dconv;
+  dconv.upload(conv, (size_t)Wsp->nnodes * 2, ctx->dev->stream);
+  if (supg_tau_values(ctx, *W, dconv.p, epsilon, p, nullptr, tau_out))
+    return fb_fail(ctx, FB_EINVAL, "fb_supg_tau: tau > 1e3 (stabilization.py:132-140 throws here)");
+  FB_API_END
+}
+
 int fb_heat_destroy(fb_heat *h) {
   delete h;
   return FB_OK;

@@ -17,6 +17,7 @@
 
 #include "fb_element.cuh"
 #include <memory>
+#include <mutex>
 #include <numeric>
 
 #include "fb_ops.h"
@@ -118,6 +119,8 @@ static void upload_mref() {
 
 int fb_clamp_grid(fb_ctx *ctx, const void *kernel, int grid, int block, size_t smem) {
   static std::unordered_map<const void *, int> cache;  // resident blocks per SM of each kernel
+  static std::mutex cache_mutex;                       // contexts of several host threads share the cache
+  std::lock_guard<std::mutex> guard(cache_mutex);
   const uint64_t key_block = (uint64_t)block;
   const void *key = (const void *)((uintptr_t)kernel ^ (key_block << 48));
   auto it = cache.find(key);
@@ -2284,4 +2287,47 @@ void vec_max_norms(fb_ctx *ctx, const double *x, int64_t n, const double *u, int
   FB_CUDA(cudaStreamSynchronize(dv->stream));
   out2_host[0] = dv->host_pinned[42];
   out2_host[1] = dv->host_pinned[43];
+}
+
+
+// tau at the three vertices of every cell (flow/stabilization.py:13-152), for inspection / parity: what k_heat_supg uses
+__global__ void k_supg_tau_values(int64_t nc, const int *__restrict__ cells, const int *__restrict__ wcell_nodes, int wnl,
+                                  const double *__restrict__ xyz, const double *__restrict__ conv, double eps, int p,
+                                  double *__restrict__ out, int *__restrict__ too_large) {
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
+    double X[6];
+    for (int v = 0; v < 3; ++v) {
+      const int node = cells[c * 3 + v];
+      X[2 * v] = xyz[(int64_t)node * 2];
+      X[2 * v + 1] = xyz[(int64_t)node * 2 + 1];
+    }
+    for (int v = 0; v < 3; ++v) {
+      const int64_t n = wcell_nodes[c * wnl + v];
+      const double cv[2] = {conv[n * 2], conv[n * 2 + 1]};
+      const double t = fb_supg_tau(X, cv, eps, p);
+      if (t < 0.0) *too_large = 1;
+      out[c * 3 + v] = t;
+    }
+  }
+}
+
+// device cells are stored in Morton order: `order` maps device position -> mesh cell for the scatter back
+int supg_tau_values(fb_ctx *ctx, const DevSpace &W, const double *conv, double eps, int p, const int *order_dev, double *out_mesh_order) {
+  DBuf<double> tmp;
+  DBuf<int> flag;
+  tmp.alloc((size_t)W.nc * 3);
+  flag.alloc(1);
+  flag.zero(ctx->dev->stream);
+  FB_LAUNCH(ctx, k_supg_tau_values, grid_for(W.nc, 256, ctx->dev->sm_count * 8), 256, 0, W.nc, W.cells.p, W.cell_nodes.p, W.nl, W.xyz.p, conv, eps, p,
+            tmp.p, flag.p);
+  std::vector<double> h((size_t)W.nc * 3);
+  int bad = 0;
+  FB_CUDA(cudaMemcpyAsync(h.data(), tmp.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, ctx->dev->stream));
+  FB_CUDA(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->dev->stream));
+  FB_CUDA(cudaStreamSynchronize(ctx->dev->stream));
+  const std::vector<int32_t> &corder = fb_mesh_cell_order(W.host->mesh);
+  for (int64_t c = 0; c < W.nc; ++c)
+    for (int v = 0; v < 3; ++v) out_mesh_order[(int64_t)corder[c] * 3 + v] = h[c * 3 + v];
+  (void)order_dev;
+  return bad;
 }

@@ -159,6 +159,7 @@ void assemble_heat(fb_ctx *ctx, const DevSpace &V, const DevSpace *W, const doub
 // SUPG additions (heat.py:60-86): returns non-zero if tau exceeded 1e3 somewhere (the reference throws)
 int assemble_heat_supg(fb_ctx *ctx, const DevSpace &V, const DevSpace &W, const double *conv, double kappa, double rho_cp,
                        double source, double *Aval, double *Mval, double *bvec);
+int supg_tau_values(fb_ctx *ctx, const DevSpace &W, const double *conv, double eps, int p, const int *order_dev, double *out_mesh_order);
 // B x and B^T y for the divergence block of stokes.py:40-42 (matrix-free)
 void stokes_div(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, const double *u, double *out_p);
 void stokes_grad(fb_ctx *ctx, const DevSpace &W, const DevSpace &P, const double *p, double *out_u);

@@ -300,7 +300,10 @@ int fb_heat_create(fb_space *V, fb_space *W, const double *conv, double kappa, d
  * source_value: the constant source entering the SUPG residual term */
 int fb_heat_create_supg(fb_space *V, fb_space *W, const double *conv, double kappa, double rho, double cp,
                         const double *source_load, int supg, double source_value, fb_heat **out);
-int fb_heat_supg_mass(fb_heat *heat, double *values_out); /* parity getter: SUPG part of M on V's pattern */
+int fb_heat_supg_mass(fb_heat *heat, double *values_out);
+/* flow.stabilization.supg (stabilization.py:13-152): tau at the 3 vertices of every cell (ncells*3 doubles, mesh cell order),
+ * evaluated by the device routine the SUPG heat kernel uses; W: vector P2 space of the convection field (triangles) */
+int fb_supg_tau(fb_space *W, const double *conv, double epsilon, int p, double *tau_out); /* parity getter: SUPG part of M on V's pattern */
 int fb_heat_destroy(fb_heat *heat);
 /* alpha*M*u + beta*(A*u + b)   (heat.py:92-101) */
 int fb_heat_eval(fb_heat *heat, double alpha, double beta, const double *u, double *out);
