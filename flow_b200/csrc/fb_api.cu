@@ -495,6 +495,7 @@ struct fb_ns {
   fb_mat Ku;                 // scalar P2 stiffness (assembled on first use)
   DBuf<double> Sval, dinv_S, Sval_t;
   ChebWork cheb;             // Chebyshev preconditioner on S (opts.inner_chebyshev)
+  int cheb_auto_degree = 4;  // degree chosen from the spectrum of D^-1 S (opts.chebyshev_degree = 0)
   double S_key = -1.0;       // theta dt mu / rho of the current Sval
   uint64_t S_bc_hash = 0;
   FgmresWork fw;
@@ -612,7 +613,7 @@ int fb_ns_opts_default(fb_ns_opts *o) {
   o->correction_maxit = 1000;
   o->gmres_restart = 30;
   o->check_every = 0;  // 0: automatic
-  o->chebyshev_degree = 4;
+  o->chebyshev_degree = 0;  // auto: from kappa(D^-1 S)
   o->jacobian_reuse = 0;
   o->adaptive_forcing = 0;
   o->jacobian_across_steps = 0;
@@ -1095,6 +1096,18 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
           Sop.val = ns->Sval.p;
           if (Sop.tile) Sop.tval = ns->Sval_t.p;
           cheb_estimate_spectrum(ctx, Sop, ns->dinv_S.p, 12, &ns->cheb.lmin, &ns->cheb.lmax);
+          ns->cheb.dinv_valid = false;  // the tile-ordered copy of dinv_S belongs to the old S
+          // degree of the polynomial preconditioner (opts.chebyshev_degree = 0).  Measured: the 3D benchmark cavity
+          // (kappa(D^-1 S) = 26) is fastest with 4 (3/5/6: profiles/r2_option_sweep.jsonl; 6: 150.8 vs 148.4 ms) -- the
+          // convection part of the Jacobian, which the polynomial does not see, limits what a better inverse of S buys;
+          // BASELINE.json config 2 (dt nu / h^2 ~ 11, kappa = 107) wants 8...16: 41 instead of 107 outer iterations, 25.6
+          // instead of 31.2 ms per step with 12 (profiles/r2_cheb_degree_config2.jsonl).  Rule: 4 up to kappa = 50, then
+          // 1.2 sqrt(kappa), at most 12.
+          const double kap = ns->cheb.lmin > 0.0 ? ns->cheb.lmax / ns->cheb.lmin : 0.0;
+          ns->cheb_auto_degree = kap <= 50.0 ? 4 : (int)std::min(12.0, std::floor(1.2 * std::sqrt(kap) + 0.5));
+          if (getenv("FB_VERBOSE"))
+            fprintf(stderr, "[flow_b200] D^-1 S spectrum [%.4g, %.4g], kappa %.3g -> Chebyshev degree %d\n", ns->cheb.lmin, ns->cheb.lmax,
+                    kap, o.chebyshev_degree > 0 ? o.chebyshev_degree : ns->cheb_auto_degree);
         }
         // Diffusion-dominated steps (dt nu / h^2 >> 1, e.g. BASELINE.json config 2): S is stiffness-like, a fixed low-degree
         // polynomial is a weak inverse (kappa(D^-1 S) in the hundreds) and the outer iteration count explodes.  There the
@@ -1179,7 +1192,7 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
         const double *dinv;
         ChebWork *w;
         int degree;
-      } cheb{ctx, inner.S, ns->dinv_S.p, &ns->cheb, o.chebyshev_degree > 0 ? o.chebyshev_degree : 4};
+      } cheb{ctx, inner.S, ns->dinv_S.p, &ns->cheb, o.chebyshev_degree > 0 ? o.chebyshev_degree : ns->cheb_auto_degree};
       {
         const char *e = getenv("FB_INNER_LOCAL");  // experiment knob; the option is opts.inner_local
         ns->cheb.local = (e ? atoi(e) != 0 : o.inner_local != 0) && fb_is_distributed(ctx);

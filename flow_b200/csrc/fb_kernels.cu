@@ -1673,6 +1673,224 @@ __global__ void __launch_bounds__(MOM_WARPS * 32)
   }
 }
 
+// Column-per-lane closed form with merged trial-side operands (FB_J_KERNEL=5).
+// ncu of k_momentum_J_cf2 (profiles/r2_k_momentum_J_cf2_ncu_details.txt): bound by the shared-memory data pipe (91 %,
+// FP64 33 %) -- 410 LDS instructions and 825 wavefronts per cell: a 16-byte broadcast load (which the compiler forms from
+// neighbouring operands) costs 4 wavefronts, an 8-byte broadcast costs 1.  Here
+//   * the trial-side operands of a block enter through ONE array E[b][v][i] = c2 lm GB[v][i] - c1t WB[v][i]
+//     (v = NV: c2 lm SB[i]), written in phase A: the column is  J[i] = sum_v m3[v] (c1t GU[v][i][j]) + sum_v GA[v][j] E[b][v][i],
+//     and, since the scalar part shares the same sums, q_j = c1 sum_w GB[w][j] WA[w][j] + (second sum at i = j)
+//     (plus - c1 sum_w GA[w][j] WB[w][j] in the semi-implicit variant, where c1t = 0);
+//   * every shared-memory operand is read by an explicit 8-byte load (lds64): 23 loads and ~36 FMAs per (lane, trial node)
+//     against 30 loads (13 of them 16-byte) and 62 FMAs;
+//   * the cell geometry is staged in shared memory (the dynamic indexing of fb_p2_vertex_grad went to local memory).
+__device__ __forceinline__ double lds64(const double *p) {
+  double v;
+  asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return v;
+}
+
+template <int D>
+struct Jcf3Shared {
+  static constexpr int NL = Elem<D>::NL2, NV = D + 1, NVP = 4;
+  double M3T[NL * NV * NL];  // [(b * NV + v) * NL + a]
+  double X[MOM_WARPS][(D + 1) * D];
+  double GL[MOM_WARPS][D + 1][D];
+  double U[MOM_WARPS][NL][D];
+  double GV[MOM_WARPS][NL][NV * D];
+  double GVT[MOM_WARPS][NL][D][NVP];  // GVT[n][k][w] = GV[n][w * D + k]
+  double WTT[MOM_WARPS][NL][D][NVP];  // WTT[n][k][w] = (1/|K|) int lambda_w phi_n u_k
+  double E[MOM_WARPS][NL][NV + 1][D];
+  double S[MOM_WARPS][NL][D];
+  double GU[MOM_WARPS][NV * D * D];
+};
+
+// The global operands of a cell (vertex ids -> coordinates, node ids -> velocities and row extents: two dependent loads
+// each) are fetched one cell ahead and held in registers, one value per lane: in the first version 16 % of all warp
+// samples waited for them at the top of a cell (ncu source page, long scoreboard) with only 4 warps per scheduler to
+// hide it.  The cell's row of the scatter map is read at the top as well (NL ints per lane), not slot by slot.
+template <int D>
+__global__ void __launch_bounds__(MOM_WARPS * 32)
+    k_momentum_J_cf3(int64_t nc, const int *__restrict__ cell_nodes, const int *__restrict__ cells,
+                     const double *__restrict__ xyz, const int *__restrict__ rowptr, const int *__restrict__ smap,
+                     MomentumArgs a, double *__restrict__ val) {
+  using SH = Jcf3Shared<D>;
+  constexpr int NL = Elem<D>::NL2, NV = D + 1, NP = NL * NL;
+  static_assert(NL * D <= 32, "one lane per (test node, column)");
+  static_assert(NL % 2 == 0, "scatter-map rows are read as int2");
+  __shared__ SH s;
+  const double *tab = (D == 2) ? FB_M3_TRI : FB_M3_TET;
+  for (int t = threadIdx.x; t < NL * NL * NV; t += blockDim.x) {
+    const int ta = t / (NL * NV), r = t - ta * (NL * NV), tb = r / NV, v = r - tb * NV;
+    s.M3T[(tb * NV + v) * NL + ta] = tab[t];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t warp0 = blockIdx.x * (int64_t)MOM_WARPS + wid;
+  const int64_t nwarps = (int64_t)gridDim.x * MOM_WARPS;
+  const double c1 = 0.5 * a.theta * a.dt, c2 = a.theta * a.dt * a.mu / a.rho;
+  const bool semi = a.adv != nullptr;
+  const double *usrc = semi ? a.adv : a.ui;
+  const double c1t = semi ? 0.0 : c1;
+  const double c2lm = c2 / ((D + 1) * (D + 2));
+  const bool active = lane < NL * D;
+  const int ta = active ? lane / D : 0, tj = active ? lane % D : 0;
+  const int lane0 = ta * D;  // first lane of this test node
+  const bool is_vertex = ta < NV;
+  const int pn = is_vertex ? ta : edge_v<D>(ta - NV, 0), qn = is_vertex ? ta : edge_v<D>(ta - NV, 1);
+  // ---- software pipeline over the cells of this warp
+  int n_vid = 0, n_node = 0, n_r0 = 0, n_r1 = 0;
+  double n_x = 0.0, n_u = 0.0;
+  auto fetch_ids = [&](int64_t cc) {
+    if (cc < nc) {
+      if (lane < D + 1) n_vid = cells[cc * (D + 1) + lane];
+      if (active) n_node = cell_nodes[cc * NL + ta];
+    }
+  };
+  auto fetch_values = [&](int64_t cc) {
+    if (cc < nc) {  // warp-uniform
+      const int vid = __shfl_sync(0xffffffffu, n_vid, (lane / D) % (D + 1));
+      if (lane < (D + 1) * D) n_x = xyz[(int64_t)vid * D + lane % D];
+      if (active) {
+        n_u = usrc[(int64_t)n_node * D + tj];
+        n_r0 = rowptr[n_node];
+        n_r1 = rowptr[n_node + 1];
+      }
+    }
+  };
+  fetch_ids(warp0);
+  fetch_values(warp0);
+  for (int64_t c = warp0; c < nc; c += nwarps) {
+    const int r0 = n_r0, len = (n_r1 - n_r0) * D;
+    if (lane < (D + 1) * D) s.X[wid][lane] = n_x;
+    if (active) s.U[wid][ta][tj] = n_u;
+    int slot[NL];
+    {
+      const int2 *row = reinterpret_cast<const int2 *>(smap + c * NP + ta * NL);
+#pragma unroll
+      for (int h = 0; h < NL / 2; ++h) {
+        const int2 v2 = row[h];
+        slot[2 * h] = v2.x;
+        slot[2 * h + 1] = v2.y;
+      }
+    }
+    fetch_ids(c + nwarps);
+    __syncwarp();
+    // ---- phase A
+    double vol;
+    {
+      double X[(D + 1) * D], glam[D + 1][D];
+#pragma unroll
+      for (int t = 0; t < (D + 1) * D; ++t) X[t] = lds64(&s.X[wid][t]);
+      fb_geometry<D>(X, glam, vol);  // every lane; one lane stages the gradients (dynamic indexing below)
+      if (lane == 0) {
+#pragma unroll
+        for (int v = 0; v < D + 1; ++v)
+#pragma unroll
+          for (int k = 0; k < D; ++k) s.GL[wid][v][k] = glam[v][k];
+      }
+    }
+    __syncwarp();
+    // vertex values of grad phi_n (fb_p2_vertex_grad), lane = (n, k): A_w glam[pn][k] + B_w glam[qn][k] with
+    // (A_w, B_w) = (3 or -1, 0) for a vertex node n = pn = qn, (4 [w == qn], 4 [w == pn]) for the edge node (pn, qn)
+    double gw[NV];
+    {
+      const double Gp = lds64(&s.GL[wid][pn][tj]), Gq = lds64(&s.GL[wid][qn][tj]);
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < NV; ++w) {
+        const double Aw = is_vertex ? (w == pn ? 3.0 : -1.0) : (w == qn ? 4.0 : 0.0);
+        const double Bw = is_vertex ? 0.0 : (w == pn ? 4.0 : 0.0);
+        gw[w] = Aw * Gp + Bw * Gq;
+        sum += gw[w];
+        if (active) {
+          s.GV[wid][ta][w * D + tj] = gw[w];
+          s.GVT[wid][ta][tj][w] = gw[w];
+        }
+      }
+      if (active) {
+        s.S[wid][ta][tj] = sum;
+        s.E[wid][ta][NV][tj] = c2lm * sum;
+      }
+    }
+    __syncwarp();
+    for (int t = lane; t < NV * D * D; t += 32) {  // GU[v][i][j] = sum_c U_c[i] GV_c[v][j], scaled by c1t
+      const int v = t / (D * D), i = (t / D) % D, j = t % D;
+      double sum = 0.0;
+#pragma unroll
+      for (int cc = 0; cc < NL; ++cc) sum += s.U[wid][cc][i] * s.GV[wid][cc][v * D + j];
+      s.GU[wid][t] = c1t * sum;
+    }
+    {  // WT[n][w][k] = sum_c M3[n][c][w] U_c[k], lane = (n, k): the U_c[k] stay in registers over the NV moments
+      double Uk[NL];
+#pragma unroll
+      for (int cc = 0; cc < NL; ++cc) Uk[cc] = lds64(&s.U[wid][cc][tj]);
+#pragma unroll
+      for (int w = 0; w < NV; ++w) {
+        double sum = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < NL; ++cc) sum += lds64(&s.M3T[(cc * NV + w) * NL + ta]) * Uk[cc];
+        if (active) {
+          s.WTT[wid][ta][tj][w] = sum;
+          s.E[wid][ta][w][tj] = c2lm * gw[w] - c1t * sum;
+        }
+      }
+    }
+    __syncwarp();
+    fetch_values(c + nwarps);  // lands during phase B
+    // ---- phase B: test-side operands of this lane (column tj of test node ta)
+    double GAj[NV], WAj[NV], GUj[NV][D], SAj;
+#pragma unroll
+    for (int w = 0; w < NV; ++w) {
+      GAj[w] = lds64(&s.GVT[wid][ta][tj][w]);
+      WAj[w] = c1 * lds64(&s.WTT[wid][ta][tj][w]);
+#pragma unroll
+      for (int i = 0; i < D; ++i) GUj[w][i] = lds64(&s.GU[wid][(w * D + i) * D + tj]);
+    }
+    SAj = lds64(&s.S[wid][ta][tj]);
+#pragma unroll
+    for (int tb = 0; tb < NL; ++tb) {
+      double m3[NV], mab = 0.0;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        m3[v] = lds64(&s.M3T[(tb * NV + v) * NL + ta]);
+        mab += m3[v];
+      }
+      const double *Eb = &s.E[wid][tb][0][0];  // one address per warp
+      double Jc[D], ytj = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double y = SAj * lds64(Eb + NV * D + i), t2 = 0.0;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          y += GAj[v] * lds64(Eb + v * D + i);
+          t2 += m3[v] * GUj[v][i];
+        }
+        if (i == tj) ytj = y;
+        Jc[i] = y + t2;
+      }
+      // this lane's share of the scalar part c1 (C_ab - C_ba) + c2 tr G (k = j): the second and third term are ytj
+      double q = ytj;
+#pragma unroll
+      for (int w = 0; w < NV; ++w) q += lds64(&s.GVT[wid][tb][tj][w]) * WAj[w];
+      if (semi) {  // c1t = 0: E carries no convection term
+#pragma unroll
+        for (int w = 0; w < NV; ++w) q -= c1 * GAj[w] * lds64(&s.WTT[wid][tb][tj][w]);
+      }
+      double dg = q;
+#pragma unroll
+      for (int k = 1; k < D; ++k) dg += __shfl_sync(0xffffffffu, q, lane0 + (tj + k) % D);
+      dg += mab;
+      if (active) {
+        double *base = val + (int64_t)r0 * (D * D) + (int64_t)(slot[tb] - r0) * D + tj;
+#pragma unroll
+        for (int i = 0; i < D; ++i) atomicAdd(base + (int64_t)i * len, vol * (Jc[i] + (i == tj ? dg : 0.0)));
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // boundary-facet part of J: -theta dt/rho mu ((grad delta)^T n, v)_ds
 template <int D>
 __global__ void k_momentum_J_facets(int64_t nbf, const int *__restrict__ bf_cell, const int *__restrict__ bf_local,
@@ -1868,11 +2086,17 @@ void assemble_momentum_J(fb_ctx *ctx, const DevSpace &W_, const MomentumArgs &a,
   // 2 (default): closed form (k_momentum_J_cf); 0: degree-5 quadrature (k_momentum_J), kept as the cross-check.
   // Measured at n = 74 on B200 (2.43 M cells): 14.7 ms vs 29.8 ms per launch.
   static const int variant = getenv("FB_J_KERNEL") ? atoi(getenv("FB_J_KERNEL")) : 2;
-  // closed form, lane = (test node, column): default in 3D (30 of 32 lanes; measured at n = 74: 12.4 ms per assembly
-  // against 15.5 ms for lane = (test node, trial group), 128 instead of 198 registers); in 2D only 12 lanes would work,
-  // the (test node, trial group) kernel stays.  FB_J_KERNEL=3 / 4 force the one / the other.
-  const bool column_lanes = variant == 3 || (variant == 2 && D == 3);
-  if (column_lanes && variant != 4 && !use_two_pass(W)) {
+  // closed form, lane = (test node, column): default in 3D (30 of 32 lanes; in 2D only 12 lanes would work, the
+  // (test node, trial group) kernel stays).  Measured at n = 74, ms per assembly (ncu): (test node, trial group) 15.5,
+  // column lanes k_momentum_J_cf2 11.70, merged trial-side operands + one-cell-ahead prefetch k_momentum_J_cf3 11.27
+  // (profiles/r2_jacobian_assembly.txt).  FB_J_KERNEL=3 / 4 / 5 force cf2 / the trial-group kernel / cf3.
+  const bool column_lanes = variant == 3 || variant == 5 || (variant == 2 && D == 3);
+  if ((variant == 5 || (variant == 2 && D == 3)) && !use_two_pass(W)) {
+    if (D == 2)
+      FB_LAUNCH(ctx, k_momentum_J_cf3<2>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
+    else
+      FB_LAUNCH(ctx, k_momentum_J_cf3<3>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
+  } else if (column_lanes && variant != 4 && !use_two_pass(W)) {
     if (D == 2)
       FB_LAUNCH(ctx, k_momentum_J_cf2<2>, g, MOM_WARPS * 32, 0, W.nc, W.cell_nodes.p, W.cells.p, W.xyz.p, W.rowptr.p, W.smap.p, a, Jval);
     else

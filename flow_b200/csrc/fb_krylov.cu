@@ -818,12 +818,20 @@ void cheb_apply(fb_ctx *ctx, const LinOp &A, const double *dinv, double lmin, do
   const int64_t n = A.ndofs(), nl = A.nlocal_dofs();
   if (w.d0.n != (size_t)nl) {
     w.r.alloc((size_t)nl);
+    w.zt.alloc((size_t)nl);
+    w.dinv_t.alloc((size_t)nl);
+    w.dinv_valid = false;
     w.d0.alloc((size_t)nl);
     w.d1.alloc((size_t)nl);
     // ghost entries of the direction vectors: refreshed by the halo exchange, or -- rank-local polynomial
     // (w.local) -- left at zero for ever (the kernels only write owned rows)
     w.d0.zero(ctx->dev->stream);
     w.d1.zero(ctx->dev->stream);
+  }
+  if (!w.dinv_valid || w.dinv_src != dinv) {  // the inverse diagonal in the row order of the tiles
+    tile_to_tile_order(ctx, *A.tile, A.dofs_per_node(), dinv, w.dinv_t.p);
+    w.dinv_src = dinv;
+    w.dinv_valid = true;
   }
   const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
   if (degree < 1) degree = 1;
@@ -832,9 +840,11 @@ void cheb_apply(fb_ctx *ctx, const LinOp &A, const double *dinv, double lmin, do
   double *dk = w.d0.p, *dn = w.d1.p;
   for (int k = 0; k + 1 < degree; ++k) {
     const double rho = 1.0 / (2.0 * sigma - rho_prev);
+    const bool last = k + 2 == degree;
     if (A.halo && !w.local) halo_exchange(ctx, *A.halo, dk, A.dofs_per_node());
-    tile_cheb_step(ctx, A, dk, k == 0 ? v : w.r.p, w.r.p, k == 0 ? nullptr : z, z, dn, dinv, rho * rho_prev, 2.0 * rho / delta,
-                   k + 2 == degree);
+    // r and the running sum z stay in tile order between the products; the input v and the result z are canonical
+    tile_cheb_step(ctx, A, dk, k == 0 ? v : w.r.p, k == 0, w.r.p, k == 0 ? nullptr : w.zt.p, last ? z : w.zt.p, dn, w.dinv_t.p,
+                   rho * rho_prev, 2.0 * rho / delta, last);
     std::swap(dk, dn);
     rho_prev = rho;
   }

@@ -99,8 +99,9 @@ void tile_format_build(fb_space *s, TileFormat &tf, cudaStream_t st);
 void tile_pack(fb_ctx *ctx, const TileFormat &tf, const double *val, double *tval);  // tval[k] = val[src[k]]
 void tile_spmm(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_mode, const double *w, int slot,
                const int *flag);
-void tile_cheb_step(fb_ctx *ctx, const LinOp &A, const double *d, const double *rin, double *rout, const double *zin, double *zout,
-                    double *dout, const double *dinv, double cdd, double cr, bool last);
+void tile_cheb_step(fb_ctx *ctx, const LinOp &A, const double *d, const double *rin, bool rin_canonical, double *rout,
+                    const double *zin, double *zout, double *dout, const double *dinv_t, double cdd, double cr, bool last);
+void tile_to_tile_order(fb_ctx *ctx, const TileFormat &tf, int ncomp, const double *x, double *xt);  // xt = x in the format's row order
 // build the space's tile format if needed and pack m's values for it; mat_repack after m.val changed
 void mat_enable_tile(fb_ctx *ctx, fb_mat &m);
 void mat_repack(fb_ctx *ctx, fb_mat &m);
@@ -219,7 +220,10 @@ int krylov_fgmres(fb_ctx *ctx, const LinOp &A, const FgmresPrecond &pc, const do
 // m - 1 products, each ONE kernel (the vector updates of the iteration live in the product's epilogue), no inner
 // products, no host synchronisation.  [lmin, lmax] bound the spectrum of D^-1 A (cheb_estimate_spectrum).
 struct ChebWork {
-  DBuf<double> r, d0, d1;
+  DBuf<double> r, d0, d1;   // r: tile order (row operand only); d0, d1: canonical (gather sources)
+  DBuf<double> zt, dinv_t;  // tile order: running sum of the directions, inverse diagonal
+  const double *dinv_src = nullptr;  // dinv_t is the permuted copy of this array ...
+  bool dinv_valid = false;           // ... and is rebuilt when the owner of the operator clears this flag
   double lmin = 0.0, lmax = 0.0;
   // partitioned runs: true = polynomial of the rank's owned x owned block of the operator (couplings to ghost
   // columns dropped, no halo exchange inside the preconditioner -- block Jacobi over the ranks); the outer flexible

@@ -8,8 +8,13 @@
 // velocity block is the assembled scalar P2 stiffness applied to the d interleaved components
 // and whose divergence/gradient blocks are applied matrix-free per cell.  The preconditioner is
 // the same block-diagonal operator as the reference's (mu K, M_p), each block inverted
-// approximately by Jacobi-PCG (the reference uses one BoomerAMG V-cycle per block).
+// approximately: the velocity block component by component by PCG preconditioned with a smoothed-aggregation AMG
+// V-cycle on mu K (fb_amg.cu; the reference uses one BoomerAMG V-cycle per block, stokes.py:59), the pressure mass
+// block by Jacobi-PCG.  Meshes below 4096 nodes keep Jacobi-PCG for the velocity block as well.
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <memory>
 #include <vector>
 
@@ -26,6 +31,16 @@ __global__ void k_scale_rsqrt_slot(double *out, const double *__restrict__ in, c
   const double a = red[0] > 0.0 ? 1.0 / sqrt(red[0]) : 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = a * in[i];
+}
+// component c of an interleaved vector <-> contiguous vector (AMG on the scalar stiffness matrix, component by component)
+__global__ void k_take_comp(int64_t nnodes, int D, int c, const double *__restrict__ v, double *__restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnodes; i += (int64_t)gridDim.x * blockDim.x) out[i] = v[i * D + c];
+}
+__global__ void k_put_comp(int64_t nnodes, int D, int c, const double *__restrict__ in, double *__restrict__ z) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnodes; i += (int64_t)gridDim.x * blockDim.x) z[i * D + c] = in[i];
+}
+__global__ void k_take_comp_mask(int64_t nnodes, int D, int c, const uint8_t *__restrict__ m, uint8_t *__restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnodes; i += (int64_t)gridDim.x * blockDim.x) out[i] = m[i * D + c];
 }
 __global__ void k_mask_zero(double *y, const uint8_t *__restrict__ mask, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -48,6 +63,21 @@ struct Stokes {
   DBuf<uint8_t> mask;  // nu + np
   DBuf<double> dinv_u, dinv_p, tmp;
   KrylovWork kw;
+  int64_t inner_k = 0, inner_m = 0;  // inner PCG iterations spent in the two blocks (FB_VERBOSE)
+  // AMG on mu K, one hierarchy per component (each with that component's Dirichlet dofs eliminated symmetrically, so that
+  // the V-cycle maps into the space the masked PCG operator works in); components with identical constraints share one
+  fb_amg *amgK[3] = {nullptr, nullptr, nullptr};
+  DBuf<uint8_t> mask_c;      // D contiguous per-component masks
+  DBuf<double> dinv_c;       // Jacobi diagonal of the per-component masked operators (unused by the AMG path of krylov_pcg)
+  DBuf<double> cin, cout;    // one component, contiguous
+  int64_t nn = 0;
+  ~Stokes() {
+    for (int c = 0; c < 3; ++c) {
+      bool shared = false;
+      for (int e = 0; e < c; ++e) shared = shared || amgK[e] == amgK[c];
+      if (amgK[c] && !shared) amg_destroy(amgK[c]);
+    }
+  }
 
   // y = (I-P) A x on free rows, 0 on constrained rows (x vanishes on constrained dofs)
   void apply(const double *x, double *y) {
@@ -63,11 +93,25 @@ struct Stokes {
   // z = blockdiag(mu K, M_p)^-1 v, each block by masked Jacobi-PCG to a loose tolerance
   int precond(const double *v, double *z, double rtol_in) {
     int its = 0;
-    LinOp Kop = make_linop(K, D, mask.p);
-    int st = krylov_pcg(ctx, Kop, dinv_u.p, v, z, rtol_in, 0.0, 2000, 25, kw, &its);
-    if (st == FB_ENAN) return st;
+    int st = FB_OK;
+    if (amgK[0]) {
+      for (int c = 0; c < D; ++c) {
+        FB_LAUNCH(ctx, k_take_comp, vgrid(ctx, nn), 256, 0, nn, D, c, v, cin.p);
+        LinOp Kc = make_linop(K, 1, mask_c.p + (size_t)c * nn);
+        st = krylov_pcg(ctx, Kc, dinv_c.p, cin.p, cout.p, rtol_in, 0.0, 200, 4, kw, &its, amgK[c]);
+        inner_k += its;
+        if (st == FB_ENAN) return st;
+        FB_LAUNCH(ctx, k_put_comp, vgrid(ctx, nn), 256, 0, nn, D, c, cout.p, z);
+      }
+    } else {
+      LinOp Kop = make_linop(K, D, mask.p);
+      st = krylov_pcg(ctx, Kop, dinv_u.p, v, z, rtol_in, 0.0, 2000, 25, kw, &its);
+      inner_k += its;
+      if (st == FB_ENAN) return st;
+    }
     LinOp Mop = make_linop(Mp, 1, mask.p + nu);
     st = krylov_pcg(ctx, Mop, dinv_p.p, v + nu, z + nu, rtol_in, 0.0, 500, 10, kw, &its);
+    inner_m += its;
     if (st == FB_ENAN) return st;
     return FB_OK;
   }
@@ -91,6 +135,7 @@ extern "C" int fb_stokes_solve(fb_space *Wsp, fb_space *Psp, double mu, int forc
   try {
     cudaStream_t st = ctx->dev->stream;
     fb_device_state *dv = ctx->dev;
+    const auto t_begin = std::chrono::steady_clock::now();
     Stokes S;
     S.ctx = ctx;
     if (!Wsp->dev) {
@@ -145,6 +190,43 @@ extern "C" int fb_stokes_solve(fb_space *Wsp, fb_space *Psp, double mu, int forc
     S.dinv_p.alloc((size_t)np);
     jacobi_setup_scalar(ctx, *S.W, S.K.val.p, D, S.mask.p, S.dinv_u.p);
     jacobi_setup_scalar(ctx, *S.P, S.Mp.val.p, 1, S.mask.p + nu, S.dinv_p.p);
+    S.nn = Wsp->nnodes;
+    // FB_STOKES_AMG_MIN: smallest mesh (P2 nodes) that gets the hierarchy (tests force it on small meshes; a huge value = Jacobi-PCG)
+    const int64_t amg_min = getenv("FB_STOKES_AMG_MIN") ? atoll(getenv("FB_STOKES_AMG_MIN")) : 4096;
+    if (Wsp->nnodes >= amg_min && !fb_is_distributed(ctx)) {
+      const int64_t nn = Wsp->nnodes;
+      fb_space_build_pattern(Wsp);
+      const int64_t nnz = (int64_t)Wsp->indices.size();
+      std::vector<int> rp((size_t)nn + 1);
+      for (int64_t i = 0; i <= nn; ++i) rp[(size_t)i] = (int)Wsp->indptr[(size_t)i];
+      std::vector<double> k0((size_t)nnz), kv;
+      FB_CUDA(cudaStreamSynchronize(st));
+      FB_CUDA(cudaMemcpy(k0.data(), S.K.val.p, sizeof(double) * nnz, cudaMemcpyDeviceToHost));
+      std::vector<int> bits((size_t)nn, 0);  // constrained components per node (a dof may be listed twice)
+      for (int64_t i = 0; i < n_ubc; ++i) bits[(size_t)(ubc_dofs[i] / D)] |= 1 << (int)(ubc_dofs[i] % D);
+      for (int c = 0; c < D; ++c) {
+        for (int e = 0; e < c && !S.amgK[c]; ++e) {  // same constraint set as an earlier component?
+          bool same = true;
+          for (int64_t i = 0; i < nn && same; ++i) same = ((bits[(size_t)i] >> c) & 1) == ((bits[(size_t)i] >> e) & 1);
+          if (same) S.amgK[c] = S.amgK[e];
+        }
+        if (S.amgK[c]) continue;
+        kv = k0;
+        for (int64_t i = 0; i < nn; ++i)
+          for (int64_t k = rp[(size_t)i]; k < rp[(size_t)i + 1]; ++k) {
+            const int64_t j = Wsp->indices[(size_t)k];
+            if (((bits[(size_t)i] >> c) & 1) || ((bits[(size_t)j] >> c) & 1)) kv[(size_t)k] = (i == j) ? 1.0 : 0.0;
+          }
+        S.amgK[c] = amg_setup(ctx, (int)nn, rp.data(), Wsp->indices.data(), kv.data());
+      }
+      S.mask_c.alloc((size_t)nn * D);
+      S.dinv_c.alloc((size_t)nn);
+      S.cin.alloc((size_t)nn);
+      S.cout.alloc((size_t)nn);
+      for (int c = 0; c < D; ++c)
+        FB_LAUNCH(ctx, k_take_comp_mask, vgrid(ctx, nn), 256, 0, nn, D, c, S.mask.p, S.mask_c.p + (size_t)c * nn);
+      FB_LAUNCH(ctx, k_take_comp, vgrid(ctx, nn), 256, 0, nn, D, 0, S.dinv_u.p, S.dinv_c.p);
+    }
 
     // right-hand side: b_u = (f, v), b_p = 0; lifted by the Dirichlet data
     DBuf<double> b, xg, x, w, tmp;
@@ -185,6 +267,8 @@ extern "C" int fb_stokes_solve(fb_space *Wsp, fb_space *Psp, double mu, int forc
       vec_zero_at(ctx, b.p, ddofs.p, nbc);
     }
 
+    FB_CUDA(cudaStreamSynchronize(st));
+    const auto t_setup = std::chrono::steady_clock::now();
     // ---- FGMRES(m)
     const int m = 30;
     std::vector<DBuf<double>> V(m + 1), Z(m);
@@ -269,6 +353,13 @@ extern "C" int fb_stokes_solve(fb_space *Wsp, fb_space *Psp, double mu, int forc
       for (int i = 0; i < j; ++i) vec_axpy(ctx, x.p, yv[i], Z[i].p, n);
     }
     if (iterations) *iterations = total;
+    if (getenv("FB_VERBOSE")) {
+      FB_CUDA(cudaStreamSynchronize(st));
+      const auto t_end = std::chrono::steady_clock::now();
+      fprintf(stderr, "[flow_b200] stokes: %lld dofs, set-up %.3f s (AMG on the velocity block: %s), FGMRES %d iterations in %.3f s, inner PCG iterations: velocity %lld, pressure mass %lld\n",
+              (long long)n, std::chrono::duration<double>(t_setup - t_begin).count(), S.amgK[0] ? "yes" : "no", total,
+              std::chrono::duration<double>(t_end - t_setup).count(), (long long)S.inner_k, (long long)S.inner_m);
+    }
     vec_axpy(ctx, x.p, 1.0, xg.p, n);
     FB_CUDA(cudaMemcpyAsync(u_out, x.p, sizeof(double) * nu, cudaMemcpyDeviceToHost, st));
     FB_CUDA(cudaMemcpyAsync(p_out, x.p + nu, sizeof(double) * np, cudaMemcpyDeviceToHost, st));

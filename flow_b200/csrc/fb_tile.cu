@@ -155,11 +155,14 @@ struct TileArgs {
   int slot;
   const int *flag;
   // Chebyshev epilogue (DOT == 4): x = d_k; r' = r - A d_k; d' = c_dd d_k + c_r dinv r'; z' = z + d_k (+ d' in the
-  // last step); y is not written
+  // last step); y is not written.  The vectors that only ever appear as ROW operands of the recurrence -- r, z, dinv --
+  // live in TILE ORDER (entry (row0 + rl) * NC + c: the rows of a tile are contiguous, the accesses coalesce); d is the
+  // gather source of the next product and keeps the canonical numbering, like the input (ch_rin of the first step:
+  // ch_rin_canonical) and the result (ch_zout of the last step).
   const double *ch_rin = nullptr, *ch_zin = nullptr, *ch_dinv = nullptr;
   double *ch_rout = nullptr, *ch_zout = nullptr, *ch_dout = nullptr;
   double ch_cdd = 0.0, ch_cr = 0.0;
-  int ch_last = 0;
+  int ch_last = 0, ch_rin_canonical = 0;
 };
 
 template <int NC, class CFG>
@@ -249,12 +252,17 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::CTAS) k_tile_spmm(const Til
       ke = a.gptr[g0 + warp + 1];
     }
     if (rl < nr) row = a.rowid[row0 + rl];
-    double wv = 0.0, xd = 0.0;
+    double wv = 0.0, xd = 0.0, dinv = 0.0, zin = 0.0;  // all row operands of the epilogue are in flight before the wait
     bool masked = false;
     if (row >= 0 && lane < NC) {
       const int64_t dof = (int64_t)row * NC + lane;
       if (DOT >= 1 && DOT <= 3) wv = a.w[dof];
-      if (DOT == 4) wv = a.ch_rin[dof];
+      if (DOT == 4) {
+        const int64_t tdof = (int64_t)(row0 + rl) * NC + lane;
+        wv = a.ch_rin[a.ch_rin_canonical ? dof : tdof];
+        dinv = a.ch_dinv[tdof];
+        if (a.ch_zin) zin = a.ch_zin[tdof];
+      }
       if (DOT >= 3 || a.mask) xd = a.x[dof];
       if (a.mask) masked = a.mask[dof] != 0;
     }
@@ -297,14 +305,15 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::CTAS) k_tile_spmm(const Til
         if (lane == c) yc = acc[c];
       if (masked) yc = xd;
       if (DOT == 4) {
-        const int64_t dof = (int64_t)row * NC + lane;
+        const int64_t dof = (int64_t)row * NC + lane, tdof = (int64_t)(row0 + rl) * NC + lane;
         const double rn = wv - yc;
-        const double dn = a.ch_cdd * xd + a.ch_cr * a.ch_dinv[dof] * rn;
-        double z = (a.ch_zin ? a.ch_zin[dof] : 0.0) + xd;
-        if (a.ch_last) z += dn;
-        a.ch_zout[dof] = z;
-        if (!a.ch_last) {
-          a.ch_rout[dof] = rn;
+        const double dn = a.ch_cdd * xd + a.ch_cr * dinv * rn;
+        double z = zin + xd;
+        if (a.ch_last) {
+          a.ch_zout[dof] = z + dn;
+        } else {
+          a.ch_zout[tdof] = z;
+          a.ch_rout[tdof] = rn;
           a.ch_dout[dof] = dn;
         }
       } else {
@@ -706,6 +715,24 @@ extern "C" int fb_space_tile_check(fb_space *s, int64_t *stats) {
   return FB_OK;
 }
 
+namespace {
+__global__ void k_tile_order(int64_t nrows, int ncomp, const int *__restrict__ rowid, const double *__restrict__ x, double *__restrict__ xt) {
+  const int64_t total = nrows * ncomp;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = t / ncomp;
+    xt[t] = x[(int64_t)rowid[q] * ncomp + (t - q * ncomp)];
+  }
+}
+}  // namespace
+
+// xt = x in the tile order of the format's rows (owned rows only)
+void tile_to_tile_order(fb_ctx *ctx, const TileFormat &tf, int ncomp, const double *x, double *xt) {
+  const int64_t n = (int64_t)tf.rowid.n * ncomp;
+  int64_t g = (n + 255) / 256;
+  g = std::max<int64_t>(1, std::min<int64_t>(g, ctx->dev->sm_count * 8));
+  FB_LAUNCH(ctx, k_tile_order, (int)g, 256, 0, (int64_t)tf.rowid.n, ncomp, tf.rowid.p, x, xt);
+}
+
 void tile_pack(fb_ctx *ctx, const TileFormat &tf, const double *val, double *tval) {
   const int64_t n = tf.nent;
   int64_t g = (n + 255) / 256;
@@ -751,15 +778,18 @@ void tile_spmm(fb_ctx *ctx, const LinOp &A, const double *x, double *y, int dot_
 }
 
 // One Chebyshev step fused into the product (see TileArgs): the caller refreshed the ghosts of d.
-void tile_cheb_step(fb_ctx *ctx, const LinOp &A, const double *d, const double *rin, double *rout, const double *zin, double *zout,
-                    double *dout, const double *dinv, double cdd, double cr, bool last) {
+// rin: canonical numbering if rin_canonical (the preconditioner's input), tile order otherwise; rout, zin, dinv_t: tile
+// order; zout: tile order, canonical in the last step; d, dout: canonical.
+void tile_cheb_step(fb_ctx *ctx, const LinOp &A, const double *d, const double *rin, bool rin_canonical, double *rout,
+                    const double *zin, double *zout, double *dout, const double *dinv_t, double cdd, double cr, bool last) {
   TileArgs a = tile_args(ctx, A, d, nullptr, nullptr, 0, nullptr);
   a.ch_rin = rin;
   a.ch_rout = rout;
   a.ch_zin = zin;
   a.ch_zout = zout;
   a.ch_dout = dout;
-  a.ch_dinv = dinv;
+  a.ch_dinv = dinv_t;
+  a.ch_rin_canonical = rin_canonical ? 1 : 0;
   a.ch_cdd = cdd;
   a.ch_cr = cr;
   a.ch_last = last ? 1 : 0;

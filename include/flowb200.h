@@ -172,7 +172,8 @@ typedef struct fb_ns_opts {
   int correction_maxit;  /* default 1000 */
   int gmres_restart;     /* restart length of the FB_GMRES solver: default 30 (PETSc default), at most 20 vectors are kept */
   int check_every;       /* Krylov iterations enqueued between host convergence checks */
-  int chebyshev_degree;  /* degree of the Chebyshev preconditioner (inner_chebyshev), default 4 */
+  int chebyshev_degree;  /* degree of the Chebyshev preconditioner (inner_chebyshev); 0 (default): chosen from the estimated
+                            condition number of D^-1 S: 4 up to kappa = 50, then round(1.2 sqrt(kappa)), at most 12 */
   int jacobian_reuse;    /* 0 (default): the reference's Newton iteration -- Jacobian of the current iterate at every
                             iteration, first iterate with |F|_2 < newton_atol accepted, updates solved to the tolerance
                             above, so that the iterates are those of the reference's Newton + LU (pressure_correction.py:

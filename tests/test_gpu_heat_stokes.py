@@ -50,9 +50,13 @@ def test_heat_operator_eval_solve(gpu_ctx, name, degree):
     assert np.allclose(th1._vec[hot], 320.0)
 
 
+@pytest.mark.parametrize("amg", [False, True])
 @pytest.mark.parametrize("name", ["tri_leftright", "tet"])
-def test_stokes_matches_oracle(gpu_ctx, name):
+def test_stokes_matches_oracle(gpu_ctx, name, amg, monkeypatch):
+    """amg = True forces the AMG-preconditioned velocity-block solves (default from 4096 P2 nodes) on the small mesh."""
     from flow_b200 import dolfin as d, stokes
+
+    monkeypatch.setenv("FB_STOKES_AMG_MIN", "0" if amg else "1000000000")
 
     om = oracle_mesh(name)
     dim = om.dim
@@ -72,6 +76,39 @@ def test_stokes_matches_oracle(gpu_ctx, name):
     bcs = [d.DirichletBC(WP.sub(0), d.Function(WP.sub(0).collapse(), g.reshape(-1)), "on_boundary"),
            d.DirichletBC(WP.sub(1), d.Function(WP.sub(1).collapse(), gp), "on_boundary")]
     u, p = stokes.solve(WP, bcs, mu, d.Constant(fvec), verbose=False, tol=1e-12, max_iter=500)
+    assert np.linalg.norm(u._vec - uo) / np.linalg.norm(uo) < 1e-8
+    assert np.linalg.norm(p._vec - po) / np.linalg.norm(po) < 1e-8
+
+
+def test_stokes_component_bcs_amg(gpu_ctx, monkeypatch):
+    """Velocity conditions that differ per component (y-component on the whole boundary, x-component everywhere but on the
+    right edge, whose natural condition fixes the pressure level; per-component conditions as in
+    tests/test_karman_vortex_street.py:139-150) with the AMG-preconditioned velocity-block solves forced on: one
+    hierarchy per constraint set."""
+    from flow_b200 import dolfin as d, stokes
+
+    monkeypatch.setenv("FB_STOKES_AMG_MIN", "0")
+    om = oracle_mesh("tri_leftright")
+    m = facade_mesh(om)
+    cell = m.ufl_cell()
+    WP = d.FunctionSpace(m, d.VectorElement("Lagrange", cell, 2) * d.FiniteElement("Lagrange", cell, 1))
+    Wo = fem.Space(om, 2, 2)
+    X = Wo.node_coords
+    g = np.stack([np.sin(X[:, 1]), 0.3 * np.cos(X[:, 0])], 1)
+    xmax = X[:, 0].max()
+    bnodes = np.unique(Wo.boundary_dofs() // 2)
+    right = bnodes[X[bnodes, 0] > xmax - 1e-12]
+    ubd = np.sort(np.concatenate([2 * bnodes + 1, 2 * np.setdiff1d(bnodes, right)]))
+    mu = 0.7
+    Mv = __import__("scipy.sparse", fromlist=["kron"]).kron(forms.mass_matrix(fem.Space(om, 2, 1)), np.eye(2))
+    load = Mv @ np.tile((0.3, -1.0), Wo.nnodes)
+    uo, po = ostokes.solve(om, mu, load, (ubd, g.reshape(-1)[ubd]), None)
+    V = WP.sub(0)
+    gx = d.Function(V.sub(0).collapse(), g[:, 0].copy())
+    gy = d.Function(V.sub(1).collapse(), g[:, 1].copy())
+    bcs = [d.DirichletBC(V.sub(1), gy, "on_boundary"),
+           d.DirichletBC(V.sub(0), gx, lambda x, on: on and x[0] < xmax - 1e-12)]
+    u, p = stokes.solve(WP, bcs, mu, d.Constant((0.3, -1.0)), verbose=False, tol=1e-12, max_iter=500)
     assert np.linalg.norm(u._vec - uo) / np.linalg.norm(uo) < 1e-8
     assert np.linalg.norm(p._vec - po) / np.linalg.norm(po) < 1e-8
 
