@@ -63,6 +63,11 @@ struct fb_device_state {
   cudaEvent_t ev[12];  // 0-5: fb_ns_step phases, 6-7: fb_ctx_timer, 8-11: local stopwatches
 };
 
+// device blocks of DBuf come from a per-(device, size) cache of released blocks (fb_kernels.cu): no cudaFree /
+// cudaMalloc pair when an object of the same shape is rebuilt
+void *fb_block_alloc(size_t bytes);
+void fb_block_free(void *p, size_t bytes);
+
 template <typename T>
 struct DBuf {
   T *p = nullptr;
@@ -72,7 +77,7 @@ struct DBuf {
   DBuf &operator=(const DBuf &) = delete;
   ~DBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) fb_block_free(p, n * sizeof(T));
     p = nullptr;
     n = 0;
   }
@@ -80,7 +85,7 @@ struct DBuf {
     if (count == n && p) return;
     release();
     if (count == 0) return;
-    FB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+    p = static_cast<T *>(fb_block_alloc(count * sizeof(T)));
     n = count;
   }
   void upload(const T *src, size_t count, cudaStream_t s) {

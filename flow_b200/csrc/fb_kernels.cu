@@ -136,6 +136,77 @@ int fb_clamp_grid(fb_ctx *ctx, const void *kernel, int grid, int block, size_t s
   return grid < wave ? grid : wave;
 }
 
+// ---- device block cache behind DBuf (fb_device.cuh) ---------------------------------------------------------------
+// cudaFree synchronises the device and, like cudaMalloc, costs 0.1 - 1 ms: drivers that rebuild an operator every step
+// (a new Heat per Banach iteration, tests/test_boussinesq.py:220-227) or solvers whose work vectors alternate between two
+// sizes paid that dozens of times per step.  Released blocks are kept per (device, size) and handed out again; every
+// user of a context enqueues on the context's one stream, so a recycled block is ordered behind its previous uses.
+namespace {
+struct BlockCache {
+  std::mutex m;
+  std::unordered_multimap<uint64_t, void *> free_blocks;  // key: device << 48 | bytes / 256
+  size_t cached = 0;
+};
+BlockCache &block_cache() {
+  static BlockCache c;
+  return c;
+}
+constexpr size_t FB_CACHE_TOTAL = size_t(8) << 30, FB_CACHE_BLOCK = size_t(1) << 30;
+inline uint64_t cache_key(int dev, size_t bytes) { return ((uint64_t)dev << 48) | (uint64_t)(bytes >> 8); }
+void cache_flush(int dev) {  // caller holds the lock
+  BlockCache &c = block_cache();
+  for (auto it = c.free_blocks.begin(); it != c.free_blocks.end();) {
+    if ((int)(it->first >> 48) == dev) {
+      cudaFree(it->second);
+      c.cached -= (size_t)(it->first & ((uint64_t(1) << 48) - 1)) << 8;
+      it = c.free_blocks.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
+}  // namespace
+
+void *fb_block_alloc(size_t bytes) {
+  bytes = (bytes + 255) & ~size_t(255);
+  int dev = 0;
+  FB_CUDA(cudaGetDevice(&dev));
+  BlockCache &c = block_cache();
+  std::lock_guard<std::mutex> guard(c.m);
+  auto it = c.free_blocks.find(cache_key(dev, bytes));
+  if (it != c.free_blocks.end()) {
+    void *p = it->second;
+    c.free_blocks.erase(it);
+    c.cached -= bytes;
+    return p;
+  }
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back and try again
+    cudaGetLastError();
+    cache_flush(dev);
+    e = cudaMalloc(&p, bytes);
+  }
+  FB_CUDA(e);
+  return p;
+}
+
+void fb_block_free(void *p, size_t bytes) {
+  if (!p) return;
+  bytes = (bytes + 255) & ~size_t(255);
+  int dev = 0;
+  BlockCache &c = block_cache();
+  if (bytes <= FB_CACHE_BLOCK && cudaGetDevice(&dev) == cudaSuccess) {
+    std::lock_guard<std::mutex> guard(c.m);
+    if (c.cached + bytes <= FB_CACHE_TOTAL) {
+      c.free_blocks.emplace(cache_key(dev, bytes), p);
+      c.cached += bytes;
+      return;
+    }
+  }
+  cudaFree(p);
+}
+
 static inline int grid_for(int64_t work_items, int block, int cap) {
   int64_t g = (work_items + block - 1) / block;
   if (g < 1) g = 1;

@@ -62,7 +62,7 @@ struct Stokes {
   fb_mat K, Mp;
   DBuf<uint8_t> mask;  // nu + np
   DBuf<double> dinv_u, dinv_p, tmp;
-  KrylovWork kw;
+  KrylovWork kw, kw_p;  // one set of work vectors per block size: DBuf::alloc reallocates (cudaFree + cudaMalloc) on every size change
   int64_t inner_k = 0, inner_m = 0;  // inner PCG iterations spent in the two blocks (FB_VERBOSE)
   // AMG on mu K, one hierarchy per component (each with that component's Dirichlet dofs eliminated symmetrically, so that
   // the V-cycle maps into the space the masked PCG operator works in); components with identical constraints share one
@@ -110,7 +110,7 @@ struct Stokes {
       if (st == FB_ENAN) return st;
     }
     LinOp Mop = make_linop(Mp, 1, mask.p + nu);
-    st = krylov_pcg(ctx, Mop, dinv_p.p, v + nu, z + nu, rtol_in, 0.0, 500, 10, kw, &its);
+    st = krylov_pcg(ctx, Mop, dinv_p.p, v + nu, z + nu, rtol_in, 0.0, 500, 10, kw_p, &its);
     inner_m += its;
     if (st == FB_ENAN) return st;
     return FB_OK;
