@@ -17,8 +17,11 @@
 // sub-solves): no communication inside the preconditioner; CG's operator stays the global one.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <numeric>
+#include <utility>
 #include <vector>
 
 #include "fb_amg_host.h"
@@ -104,7 +107,14 @@ __global__ void k_amg_dense(int n, const double *__restrict__ Ainv, const double
 // In-place inverse of a dense symmetric positive definite matrix (row-major, n x n) by Cholesky; false if a pivot fails.
 int lanes_for(const HostCsr &M) {
   const double mean = M.nrows > 0 ? (double)M.val.size() / M.nrows : 0.0;
-  int at = mean <= 12.0 ? 4 : (mean <= 32.0 ? 8 : (mean <= 96.0 ? 16 : 32));
+  // The kernels are latency bound (row pointer -> entries -> x[col], three dependent loads per row): fewer lanes per row
+  // put more rows in flight per warp.  FB_AMG_LANES=0: the first thresholds (12 / 32 / 96).
+  static const int mode = getenv("FB_AMG_LANES") ? atoi(getenv("FB_AMG_LANES")) : 1;
+  int at;
+  if (mode == 0)
+    at = mean <= 12.0 ? 4 : (mean <= 32.0 ? 8 : (mean <= 96.0 ? 16 : 32));
+  else
+    at = mean <= 20.0 ? 4 : (mean <= 56.0 ? 8 : (mean <= 160.0 ? 16 : 32));
   // few rows: spend more lanes per row rather than leave the GPU idle
   while (at < 32 && (int64_t)M.nrows * at < 148 * 256) at *= 2;
   return at;
@@ -131,7 +141,19 @@ struct fb_amg {
   int n_owned = 0;
   double operator_complexity = 1.0;
   bool singular = false;
+  // The V-cycle is a chain of ~16 kernels of 3 - 30 us each: replayed as ONE CUDA graph per (input, output) pair, the
+  // launch gaps between them shrink (the work vectors of the PCG iteration that calls it keep their addresses).
+  std::map<std::pair<const double *, double *>, cudaGraphExec_t> graphs;
+  std::map<std::pair<const double *, double *>, int> seen;  // direct runs of a pair before it is captured
+  int graph_kernels = 0;                                    // kernels per cycle (for the launch counter)
+  bool graphs_enabled = true;
+  void drop_graphs() {
+    for (auto &g : graphs) cudaGraphExecDestroy(g.second);
+    graphs.clear();
+    seen.clear();
+  }
   ~fb_amg() {
+    drop_graphs();
     for (auto *l : levels) delete l;
     if (gather) fb_peer_vec_destroy(gather);
   }
@@ -214,11 +236,68 @@ static void amg_jacobi(fb_ctx *ctx, const AmgLevel &L, const double *b, const do
 // in L.tmp (pre-smooth, residual, coarse correction) and the post-smoothed result in L.x (z on the fine level).
 static void amg_cycle(fb_amg *amg, const double *r, double *z);
 
+// amg_cycle through a CUDA graph: the first two calls with a given (r, z) run directly (they also fill the occupancy cache
+// of FB_LAUNCH), the third is captured, later ones replay it.  Any failure of the graph API switches the hierarchy back to
+// direct launches for good.  FB_AMG_GRAPH=0 disables the graphs.
+static void amg_cycle_graphed(fb_amg *amg, const double *r, double *z) {
+  static const bool env_on = !(getenv("FB_AMG_GRAPH") && atoi(getenv("FB_AMG_GRAPH")) == 0);
+  fb_ctx *ctx = amg->ctx;
+  cudaStream_t st = ctx->dev->stream;
+  if (!env_on || !amg->graphs_enabled) return amg_cycle(amg, r, z);
+  const auto key = std::make_pair(r, z);
+  auto it = amg->graphs.find(key);
+  if (it != amg->graphs.end()) {
+    if (cudaGraphLaunch(it->second, st) == cudaSuccess) {
+      ctx->launches += amg->graph_kernels;
+      return;
+    }
+    cudaGetLastError();
+    amg->graphs_enabled = false;
+    amg->drop_graphs();
+    return amg_cycle(amg, r, z);
+  }
+  if (amg->seen[key]++ < 2) return amg_cycle(amg, r, z);
+  if (amg->graphs.size() >= 8) amg->drop_graphs();  // callers with ever-changing vectors: start over
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  const long long before = ctx->launches;
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    amg->graphs_enabled = false;
+    return amg_cycle(amg, r, z);
+  }
+  bool ok = true;
+  try {
+    amg_cycle(amg, r, z);
+  } catch (...) {
+    ok = false;
+  }
+  if (cudaStreamEndCapture(st, &graph) != cudaSuccess || !graph) ok = false;
+  amg->graph_kernels = (int)(ctx->launches - before);
+  ctx->launches = before;
+  if (ok && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) ok = false;
+  if (graph) cudaGraphDestroy(graph);
+  if (!ok) {
+    cudaGetLastError();
+    if (exec) cudaGraphExecDestroy(exec);
+    amg->graphs_enabled = false;
+    return amg_cycle(amg, r, z);  // nothing ran during the failed capture
+  }
+  amg->graphs[key] = exec;
+  if (cudaGraphLaunch(exec, st) != cudaSuccess) {
+    cudaGetLastError();
+    amg->graphs_enabled = false;
+    amg->drop_graphs();
+    return amg_cycle(amg, r, z);
+  }
+  ctx->launches += amg->graph_kernels;
+}
+
 void amg_apply(fb_amg *amg, const double *r, double *z) {
-  if (!amg->gather) return amg_cycle(amg, r, z);
+  if (!amg->gather) return amg_cycle_graphed(amg, r, z);
   fb_ctx *ctx = amg->ctx;
   const double *rg = fb_peer_vec_gather(ctx, amg->gather, r, amg->l2g.p, amg->n_owned);
-  amg_cycle(amg, rg, amg->zg.p);
+  amg_cycle_graphed(amg, rg, amg->zg.p);
   FB_LAUNCH(ctx, k_amg_extract, agrid(amg->n_owned, 1), 256, 0, amg->n_owned, amg->l2g.p, amg->zg.p, z);
 }
 

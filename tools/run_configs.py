@@ -122,7 +122,7 @@ def boussinesq(steps):
     ubcs = [d.DirichletBC(W, (0.0, 0.0), "on_boundary")]
     st = nav.Rotational()
     dt, t = 1e-2, 0.0
-    hist, t_heat = [], 0.0
+    hist, t_heat, heat_its = [], 0.0, []
     for k in range(steps + 3):
         if k == 3:
             t0 = time.perf_counter()
@@ -131,6 +131,7 @@ def boussinesq(steps):
         stepper = heat.ImplicitEuler(heat.Heat(Q, u, KAPPA_WATER, RHO_WATER, CP_WATER, heat_bcs, d.Constant(0.0)))
         theta1 = stepper.step(theta, t, dt)
         t_heat += time.perf_counter() - th0
+        heat_its.append(stepper.problem.last_iterations)
         f = d.Function(W)
         f.nodal_view()[:, 1] = rho(theta.vector().get_local()) * g
         u, p = st.step(d.Constant(dt), {0: u}, p, ubcs, [], RHO_WATER, d.Constant(MU_WATER), {0: f, 1: f}, verbose=False)
@@ -142,7 +143,7 @@ def boussinesq(steps):
     th = theta.vector().get_local()
     return {"config": "4: Boussinesq heated cavity, UnitSquareMesh(667), heat implicit Euler + Rotational, dt=1e-2",
             "dofs": W.dim() + P.dim() + Q.dim(), "steps": steps, "steps_per_s_e2e": 1.0 / sec,
-            "ms_per_step_ns_device": float(np.mean([s["ms_total"] for s in h])), "heat_s_per_step_e2e": t_heat / steps,
+            "ms_per_step_ns_device": float(np.mean([s["ms_total"] for s in h])), "heat_s_per_step_e2e": t_heat / steps, "heat_solver_its": float(np.mean(heat_its[3:])),
             "newton": float(np.mean([s["newton_its"] for s in h])), "momentum_its": float(np.mean([s["momentum_its"] for s in h])),
             "pressure_its": float(np.mean([s["pressure_its"] for s in h])), "theta_min": float(th.min()), "theta_max": float(th.max()),
             "umax": float(np.sqrt((u.nodal() ** 2).sum(axis=1)).max())}
