@@ -2,7 +2,9 @@
 // pressure-correction step, the heat operator.  See include/flowb200.h for the
 // reference call each entry point replaces.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -1414,6 +1416,7 @@ int fb_heat_create_supg(fb_space *Vsp, fb_space *Wsp, const double *conv, double
     return fb_fail(ctx, FB_EINVAL, "fb_heat_create: conv needs a vector P2 space on the same mesh");
   FB_API_BEGIN(ctx)
   cudaStream_t st = ctx->dev->stream;
+  const auto t_begin = std::chrono::steady_clock::now();
   std::unique_ptr<fb_heat> h(new fb_heat());
   h->ctx = ctx;
   h->V = dev_space(Vsp);
@@ -1443,6 +1446,9 @@ int fb_heat_create_supg(fb_space *Vsp, fb_space *Wsp, const double *conv, double
   h->S.alloc((size_t)h->V->nnz);
   h->mask.alloc((size_t)n);
   FB_CUDA(cudaStreamSynchronize(st));
+  if (getenv("FB_VERBOSE"))
+    fprintf(stderr, "[flow_b200] heat operator: %lld dofs assembled in %.2f ms\n", (long long)n,
+            1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count());
   *out = h.release();
   FB_API_END
 }
@@ -1506,6 +1512,7 @@ int fb_heat_solve(fb_heat *h, double alpha, double beta, double *b, int64_t nbc,
   if (nbc > 0 && (!bc_dofs || !bc_vals)) return FB_EINVAL;
   FB_API_BEGIN(h->ctx)
   cudaStream_t st = _ctx->dev->stream;
+  const auto t_begin = std::chrono::steady_clock::now();
   const int64_t n = h->V->nnodes, nnz = h->V->nnz;
   for (int64_t i = 0; i < nbc; ++i) {
     if (bc_dofs[i] < 0 || bc_dofs[i] >= n) return fb_fail(_ctx, FB_EINVAL, "fb_heat_solve: Dirichlet dof out of range");
@@ -1532,6 +1539,9 @@ int fb_heat_solve(fb_heat *h, double alpha, double beta, double *b, int64_t nbc,
   if (iterations) *iterations = its;
   FB_CUDA(cudaMemcpyAsync(x, h->x.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   FB_CUDA(cudaStreamSynchronize(st));
+  if (getenv("FB_VERBOSE"))
+    fprintf(stderr, "[flow_b200] heat solve: %d BiCGStab iterations, %.2f ms\n", its,
+            1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count());
   if (status != FB_OK) return fb_fail(_ctx, status == FB_ENAN ? FB_ENAN : FB_ENOCONV_KRYLOV, "fb_heat_solve: BiCGStab failed");
   FB_API_END
 }

@@ -194,9 +194,10 @@ void *fb_block_alloc(size_t bytes) {
 void fb_block_free(void *p, size_t bytes) {
   if (!p) return;
   bytes = (bytes + 255) & ~size_t(255);
-  int dev = 0;
   BlockCache &c = block_cache();
-  if (bytes <= FB_CACHE_BLOCK && cudaGetDevice(&dev) == cudaSuccess) {
+  cudaPointerAttributes attr;  // the device that owns the block (the caller's current device may be another one)
+  if (bytes <= FB_CACHE_BLOCK && cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeDevice) {
+    const int dev = attr.device;
     std::lock_guard<std::mutex> guard(c.m);
     if (c.cached + bytes <= FB_CACHE_TOTAL) {
       c.free_blocks.emplace(cache_key(dev, bytes), p);
