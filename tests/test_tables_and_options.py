@@ -61,5 +61,7 @@ def test_set_options_contract():
         assert _lib.lib.fb_ns_opts_default(o) == 0
         assert o.momentum_solver == _lib.GMRES and o.pressure_precond == _lib.AMG and o.newton_atol == 1e-10
         assert o.newton_maxit == 10 and o.jacobian_fp32 == 0 and o.inner_fp32 == 0 and o.momentum_inner_its == 4
+        # 0 = degree of the Chebyshev preconditioner chosen from the spectrum estimate; the exact defaults carry no mixed precision
+        assert o.chebyshev_degree == 0 and o.inner_chebyshev == 1 and o.semi_implicit == 0 and o.jacobian_reuse == 0
     finally:
         nav.reset_options()
