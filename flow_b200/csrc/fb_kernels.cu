@@ -1355,6 +1355,24 @@ __global__ void __launch_bounds__(128)
           }
         }
       }
+      // point quantities: the integrand of (a, i) is  phi_a X_i + sum_k d_k phi_a Z_ik  with
+      //   X_i  = w [ cm u_i + cdt rho/2 ((grad u) b)_i ],
+      //   Z_ik = -w cdt [ rho/2 b_k u_i - mu (d_k u_i + d_i u_k) + p0 delta_ik ]        (b: advecting velocity)
+      // (fb_rhs_point written out, with everything that does not depend on the test node hoisted: 4 FMAs per (a, i))
+      double X[D], Z[D][D];
+      {
+        const double *bq = (adv && need_R) ? wq : uq;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          double conv = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) conv += gu[i][k] * bq[k];
+          X[i] = w * (cm * uq[i] + (need_R ? cdt * 0.5 * rho * conv : 0.0));
+#pragma unroll
+          for (int k = 0; k < D; ++k)
+            Z[i][k] = need_R ? -w * cdt * (0.5 * rho * bq[k] * uq[i] - mu * (gu[i][k] + gu[k][i]) + (i == k ? pq : 0.0)) : 0.0;
+        }
+      }
 #pragma unroll
       for (int a = 0; a < NL; ++a) {
         const double pa = fb_p2_phi<D>(a, lam);
@@ -1362,8 +1380,11 @@ __global__ void __launch_bounds__(128)
         if (need_R) fb_p2_grad<D>(a, lam, glam, ga);
 #pragma unroll
         for (int i = 0; i < D; ++i) {
-          double v = cm * w * pa * uq[i];
-          if (need_R) v -= cdt * w * fb_rhs_point<D>(i, rho, mu, pa, ga, uq, gu, pq, adv ? wq : nullptr);
+          double v = pa * X[i];
+          if (need_R) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) v += ga[k] * Z[i][k];
+          }
           acc[a][i] += v;
         }
       }
