@@ -498,6 +498,8 @@ struct fb_ns {
   DBuf<double> Sval, dinv_S, Sval_t;
   DBuf<double> dprev, dprev2;  // total Newton updates u0 - ui of the previous two steps: initial guess of this step's first update
   double dprev_dt = 0.0, dprev2_dt = 0.0;  // their time steps (0: none yet)
+  DBuf<double> cprev, cprev2;  // velocity-correction increments u1 - ui of the previous two steps (initial guess of the CG)
+  double cprev_dt = 0.0, cprev2_dt = 0.0;
   ChebWork cheb;             // Chebyshev preconditioner on S (opts.inner_chebyshev)
   int cheb_auto_degree = 4;  // degree chosen from the spectrum of D^-1 S (opts.chebyshev_degree = 0)
   double S_key = -1.0;       // theta dt mu / rho of the current Sval
@@ -1379,8 +1381,19 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
   // ---- velocity correction (pressure_correction.py:436-465)
   spmv(ctx, make_linop(ns->Mu, D, nullptr), ns->ui.p, ns->bu.p);
   assemble_correction_grad(ctx, *ns->W, *ns->P, dt, rho, mu, rotational, ns->ui.p, ns->p1.p, ns->p0.p, ns->bu.p);
+  // FB_WARM_DELTA (see the momentum solve): the correction increment u1 - ui = -dt/rho M^-1 grad(phi) of the previous two
+  // steps, extrapolated like the Newton update, is added to the initial guess ui of the mass solve
+  static const int warm_corr = getenv("FB_WARM_DELTA") ? atoi(getenv("FB_WARM_DELTA")) : 2;
   if (o.warm_start) {  // x0 = ui on the free dofs (the lifted unknown vanishes on the constrained ones)
-    FB_CUDA(cudaMemcpyAsync(ns->u1.p, ns->ui.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
+    if (warm_corr >= 2 && ns->cprev_dt > 0.0 && ns->cprev2_dt > 0.0 && ns->cprev.n == (size_t)nu && ns->cprev2.n == (size_t)nu) {
+      const double th = (dt + ns->cprev_dt) / (ns->cprev_dt + ns->cprev2_dt);
+      vec_axpby(ctx, ns->u1.p, dt * (1.0 + th) / ns->cprev_dt, ns->cprev.p, -dt * th / ns->cprev2_dt, ns->cprev2.p, nu_o);
+      vec_axpy(ctx, ns->u1.p, 1.0, ns->ui.p, nu_o);
+    } else if (warm_corr >= 1 && ns->cprev_dt > 0.0 && ns->cprev.n == (size_t)nu) {
+      vec_axpby(ctx, ns->u1.p, 1.0, ns->ui.p, dt / ns->cprev_dt, ns->cprev.p, nu_o);
+    } else {
+      FB_CUDA(cudaMemcpyAsync(ns->u1.p, ns->ui.p, sizeof(double) * nu, cudaMemcpyDeviceToDevice, st));
+    }
     vec_zero_at(ctx, ns->u1.p, ns->ubc_dofs.p, n_ubc);
   }
   status = solve_cg_masked(ctx, ns->Mu, D, ns->bu.p, ns->u1.p, n_ubc, ns->ubc_dofs.p, ns->ubc_vals.p, g2u, ns->mask_u.p,
@@ -1393,6 +1406,14 @@ int fb_ns_step(fb_ns *ns, double dt, double rho, double mu, int scheme, int flag
     return fb_fail(ctx, status == FB_ENAN ? FB_ENAN : FB_ENOCONV_KRYLOV, buf);
   }
   (void)g2p;
+  if (o.warm_start && warm_corr >= 1) {  // u1 - ui: what the next step's correction solve starts from
+    std::swap(ns->cprev.p, ns->cprev2.p);
+    std::swap(ns->cprev.n, ns->cprev2.n);
+    ns->cprev2_dt = ns->cprev_dt;
+    ns->cprev.alloc((size_t)nu);
+    vec_axpby(ctx, ns->cprev.p, 1.0, ns->u1.p, -1.0, ns->ui.p, nu_o);
+    ns->cprev_dt = dt;
+  }
   halo_exchange(ctx, *ns->W, ns->u1.p, D);  // hand back a state whose ghost copies are current
   const cudaMemcpyKind back = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   FB_CUDA(cudaMemcpyAsync(u1, ns->u1.p, sizeof(double) * nu, back, st));
