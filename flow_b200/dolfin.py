@@ -467,6 +467,8 @@ class Constant(object):
         return out[:, 0] if self.scalar else out
 
     def __mul__(self, o):
+        if isinstance(o, Expression):  # Constant * coordinate expression: the expression's reflected operator takes over
+            return NotImplemented
         return Constant(self._v * float(o)) if not self.scalar else Constant(float(self) * float(o))
 
     __rmul__ = __mul__
@@ -669,6 +671,84 @@ def assemble(form):
     if isinstance(f, Expression):
         return hostfem.integrate_expression(mesh.coordinates(), mesh.cells(), f, f.degree())
     return float(f) * float(mesh.volumes().sum())
+
+
+class _CoordinateExpr(Expression):
+    """Polynomial expression in the spatial coordinates with the arithmetic the reference's drivers use on
+    `SpatialCoordinate(mesh)[i]` (`g * y`, tests/test_sealed_box.py:84-88; `rho * g * y`, tests/test_boussinesq.py:152):
+    a callable of the points plus its polynomial degree, closed under +, -, * with numbers, `Constant`s and each other."""
+
+    def __init__(self, fn, degree):
+        Expression.__init__(self, fn, degree=degree)
+
+    @staticmethod
+    def _wrap(o):
+        if isinstance(o, _CoordinateExpr):
+            return o._fn, o.degree()
+        v = float(o)  # numbers and scalar Constants
+        return (lambda X: np.full(np.atleast_2d(X).shape[0], v)), 0
+
+    def __mul__(self, o):
+        f, g = self._fn, None
+        g, dg = self._wrap(o)
+        return _CoordinateExpr(lambda X: f(X) * g(X), self.degree() + dg)
+
+    __rmul__ = __mul__
+
+    def __add__(self, o):
+        f = self._fn
+        g, dg = self._wrap(o)
+        return _CoordinateExpr(lambda X: f(X) + g(X), max(self.degree(), dg))
+
+    __radd__ = __add__
+
+    def __neg__(self):
+        f = self._fn
+        return _CoordinateExpr(lambda X: -f(X), self.degree())
+
+    def __sub__(self, o):
+        return self + (-o if isinstance(o, _CoordinateExpr) else -float(o))
+
+    def __rsub__(self, o):
+        return (-self) + o
+
+    def __truediv__(self, o):
+        return self * (1.0 / float(o))
+
+    def __pow__(self, k):
+        f = self._fn
+        assert int(k) == k and k >= 0
+        return _CoordinateExpr(lambda X: f(X) ** int(k), self.degree() * int(k))
+
+
+class SpatialCoordinate(object):
+    """`SpatialCoordinate(mesh)[i]`: coordinate i as a degree-1 expression (see _CoordinateExpr)."""
+
+    def __init__(self, mesh):
+        self._dim = int(np.asarray(mesh.coordinates()).shape[1])
+
+    def __getitem__(self, i):
+        if not 0 <= i < self._dim:
+            raise IndexError(i)
+        return _CoordinateExpr(lambda X, i=i: np.atleast_2d(np.asarray(X, dtype=float))[:, i], 1)
+
+
+def sqrt(x):
+    """Square root of numbers / arrays.  The one finite-element use in the reference's drivers,
+    `project(sqrt(ux**2 + uy**2), P2, quadrature_degree 4)` (tests/test_karman_vortex_street.py:262-268,
+    tests/test_sealed_box.py:134-140), is one device call here: `flow_b200.drivers.velocity_magnitude(u, P)`."""
+    if isinstance(x, (Function, Expression)):
+        raise NotImplementedError("sqrt of a finite-element expression: use flow_b200.drivers.velocity_magnitude(u, P)")
+    return np.sqrt(x)
+
+
+def plot(*args, **kwargs):
+    """No-op (the reference's drivers call dolfin.plot / interactive only behind `if show:` switches)."""
+    return None
+
+
+def interactive(*args, **kwargs):
+    return None
 
 
 def _callable_of(f):

@@ -146,3 +146,29 @@ def test_pinned_block_outlives_views_of_a_dropped_function(monkeypatch):
     del view
     gc.collect()
     assert len(_lib._pinned_pool[800]) == 1  # now it is back in the pool
+
+
+def test_spatial_coordinate_expressions_and_display_stubs():
+    """`SpatialCoordinate(mesh)[1]` with the arithmetic of the reference's drivers (`g * y`, tests/test_sealed_box.py:84-88;
+    `rho * g * y`, tests/test_boussinesq.py:152), and the display calls they make (`plot`, `interactive`)."""
+    from flow_b200 import dolfin as d
+
+    mesh = d.UnitSquareMesh(3, 4)
+    x, y = d.SpatialCoordinate(mesh)[0], d.SpatialCoordinate(mesh)[1]
+    g, rho = -9.81, 998.2
+    X = np.array([[0.5, 0.25], [1.0, 2.0], [0.0, 0.0]])
+    e = d.Constant(g) * y * rho + 3.0 - x ** 2
+    assert np.allclose(e(X), g * rho * X[:, 1] + 3.0 - X[:, 0] ** 2)
+    assert e.degree() == 2 and (g * y).degree() == 1 and (y / 2.0 - 1.0).degree() == 1
+    assert np.allclose((1.0 - y)(X), 1.0 - X[:, 1]) and np.allclose((-y)(X), -X[:, 1])
+    with pytest.raises(IndexError):
+        d.SpatialCoordinate(mesh)[2]
+    # a degree-1 expression interpolates exactly into P1 (what project(g * y, P1) returns in the reference's driver)
+    P = d.FunctionSpace(mesh, "CG", 1)
+    p0 = d.interpolate(g * y, P)
+    assert np.allclose(p0.vector().get_local(), g * P.nodes.coords[:, 1])
+    # Constant arithmetic with plain numbers is unchanged
+    assert (d.Constant(2.0) * 3.0).values()[0] == 6.0 and (2 * d.Constant(2.0)).values()[0] == 4.0
+    assert d.sqrt(4.0) == 2.0 and d.plot(p0) is None and d.interactive() is None
+    with pytest.raises(NotImplementedError):
+        d.sqrt(p0)
